@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py - kana chars/sec decoded (BASELINE.json metric) on the configuration the metric is quoted on:
+configs[1] = V=50000 H=512 embed=256, standard (tied) softmax, beam=10, 1 GPU.
+
+A "step" is one pass of the hot path over one batch of synthetic sentences: lattice (CSR, already
+built on the host) -> n-best lists, S sentences decoded in lock-step per GPU.  Independent
+sentences are partitioned across ranks (weak scaling: S per GPU), no collective on the data path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--sentences S] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract:
+  value      chars/s, device-resident inputs, CUDA-event time, max over ranks
+  e2e        chars/s through the C-ABI call jlm_decode_batch with HOST buffers (H2D + D2H inside)
+  roofline   the dominant kernel (output-projection GEMM + online-LSE epilogue): algorithmic FLOP/s
+             over its CUDA-event duration vs the measured bf16 peak; `gate` holds the same for the
+             LSTM gate GEMM the north star names
+  cpu_baseline  the CPU oracle (numpy port of the reference) on a bounded sample, same host
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOAD = 'cfg2: V=50000 H=512 E=256 tied standard softmax, beam=10, topN=10, >=20 kana/sentence'
+V, H, E, BEAM, TOPN, MIN_LEN = 50000, 512, 256, 10, 10, 20
+METRIC = 'kana chars/sec decoded at V=50k H=512 beam=10'
+
+
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1431.6), d.get('bf16_tflops', 1644.3), d.get('hbm_gbs', 6454.6), 'measured'
+    return 1400.0, 1590.0, 6650.0, 'fallback'
+
+
+def make_inputs(root, n_sent, seed):
+    from jlm_b200 import synth
+    cfg, weights, lexicon, reading_dict = synth.make_experiment(root, 1, V, H, E, 'tied', seed=0)
+    sents = synth.make_sentences(lexicon, n_sent, min_len=MIN_LEN, seed=seed, vocab_size=V)
+    return cfg, weights, lexicon, reading_dict, sents
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(',')])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (numpy oracle port - the Python reference
+    itself cannot travel to the GPU box) on the host cores, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import jlm_oracle as O
+    root = tempfile.mkdtemp(prefix='jlm_bench_ref_')
+    n = max(1, args.ref_sentences)
+    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, n, seed=1)
+    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict)
+    frames = [O.build_lattice(s, ora.w2i, lexicon, reading_dict) for s in sents]
+    chars = sum(len(s) for s in sents)
+
+    def step():
+        for fr in frames:
+            O.decode_static(ora.model, fr, TOPN, BEAM, None)
+
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = chars * args.steps / dt
+    sample = '%d sentences (%d chars) per step, lattice->n-best (decode minus _build_lattice)' % (n, chars)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'chars/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'sentences_per_step': n},
+            'cpu_baseline': {'value': val, 'unit': 'chars/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'chars/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--sentences', type=int, default=1024, help='sentences per GPU per step (lock-step batch)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ref-sentences', type=int, default=8)
+    ap.add_argument('--cpu-baseline-sentences', type=int, default=12)
+    ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: libjlm_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    import jlm_b200
+    from jlm_b200 import _lib, config, lattice
+    lib = _lib.load()
+    root = tempfile.mkdtemp(prefix='jlm_bench_r%d_' % rank)
+    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, args.sentences, seed=100 + rank)
+    config.set_root(root)
+    dec = jlm_b200.Decoder(1, device=local)
+    hdl = dec.model._handle
+    stream = torch.cuda.current_stream()
+    _lib.check(lib.jlm_set_stream(hdl, C.c_void_p(stream.cuda_stream)))
+    t_lat = time.perf_counter()
+    frames = [dec._builder.build(s) for s in sents]
+    t_lat = time.perf_counter() - t_lat
+    packed = lattice.PackedLattices(frames)
+    lb = packed.c_struct()
+    chars = sum(len(s) for s in sents)
+    S = packed.n_sent
+    max_len = int(packed.sent_len.max()) + 1
+    scores = np.empty((S, TOPN))
+    n_paths = np.empty(S, dtype=np.int32)
+    path_len = np.empty((S, TOPN), dtype=np.int32)
+    path_nodes = np.zeros((S, TOPN, max_len), dtype=np.int32)
+    nb = _lib.NBest()
+    nb.top_n, nb.max_len = TOPN, max_len
+    nb.scores, nb.n_paths = _lib.ptr(scores, C.c_double), _lib.ptr(n_paths, C.c_int32)
+    nb.path_len, nb.path_nodes = _lib.ptr(path_len, C.c_int32), _lib.ptr(path_nodes, C.c_int32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- device-resident arm: lattices uploaded once, K timed runs ----------------
+    batch = C.c_void_p()
+    _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(batch)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
+    for _ in range(max(args.warmup, 3)):
+        _lib.check(lib.jlm_batch_run(batch))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)                     # evict weights / state from L2 between timed steps (not timed)
+        a.record(stream)
+        _lib.check(lib.jlm_batch_run(batch))
+        b.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    ms_dev = max_over_ranks(ms_dev)
+    total_chars = sum_over_ranks(float(chars))
+    value = total_chars * args.steps / (ms_dev * 1e-3)
+    info = _lib.BatchInfo()
+    _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
+    _lib.check(lib.jlm_batch_get_info(batch, C.byref(info)))
+    launches = int(info.kernel_launches) * args.steps
+    rows_stepped = int(info.n_slots)
+
+    # ---------------- roofline pass: same K steps with per-kernel CUDA events ----------------
+    _lib.check(lib.jlm_batch_enable_timers(batch, 1))
+    gate_ms = proj_ms = 0.0
+    n_gate = n_proj = 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        _lib.check(lib.jlm_batch_run(batch))
+        _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
+        _lib.check(lib.jlm_batch_get_info(batch, C.byref(info)))
+        gate_ms += info.ms_gate_gemm
+        proj_ms += info.ms_proj_gemm
+        n_gate += info.n_gate_launches
+        n_proj += info.n_proj_launches
+    clocks = sampler.stop() if rank == 0 else None
+    _lib.check(lib.jlm_batch_destroy(batch))
+
+    # ---------------- e2e arm: the public C-ABI call with host buffers ----------------
+    for _ in range(2):
+        _lib.check(lib.jlm_decode_batch(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(nb)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _lib.check(lib.jlm_decode_batch(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(nb)))
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = total_chars * args.steps / e2e_s
+    # one more upload to read the byte counters of a single call
+    b2 = C.c_void_p()
+    _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(b2)))
+    _lib.check(lib.jlm_batch_run(b2))
+    _lib.check(lib.jlm_batch_fetch(b2, C.byref(nb)))
+    i2 = _lib.BatchInfo()
+    _lib.check(lib.jlm_batch_get_info(b2, C.byref(i2)))
+    _lib.check(lib.jlm_batch_destroy(b2))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    sus, burst, hbm, src = peaks()
+    # algorithmic flops per LM row: gate 2*(E+H)*4H ; projection 2*H*E + 2*E*V
+    f_gate_row = 2.0 * (E + H) * 4 * H
+    f_proj_row = 2.0 * E * V
+    rows_total = rows_stepped * args.steps
+    roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': sus, 'peak_source': src + ' bf16 sustained', 'traffic': None}
+    if proj_ms > 0 and args.backend == 2:
+        ach = f_proj_row * rows_total / (proj_ms * 1e-3) / 1e12
+        roof.update({'kernel': 'k_tc_gemm<256,EPI_LSE> (output projection + online LSE)', 'achieved': ach,
+                     'frac': ach / sus, 'issued_frac': 3 * ach / sus,
+                     'flops_per_launch': f_proj_row * rows_total / max(n_proj, 1),
+                     'avg_launch_ms': proj_ms / max(n_proj, 1), 'launches': n_proj,
+                     'note': 'useful flops; each product is 3 fp16 MMAs (2-term split), issued_frac counts those'})
+        g_ach = f_gate_row * rows_total / (gate_ms * 1e-3) / 1e12 if gate_ms > 0 else None
+        roof['gate'] = {'kernel': 'k_tc_gemm<256,EPI_LSTM> (gate GEMM + LSTM epilogue)', 'achieved': g_ach,
+                        'frac': g_ach / sus if g_ach else None, 'issued_frac': 3 * g_ach / sus if g_ach else None,
+                        'avg_launch_ms': gate_ms / max(n_gate, 1), 'launches': n_gate}
+    else:
+        roof.update({'achieved': None, 'frac': None})
+
+    # ---------------- CPU baseline: oracle port on a bounded sample of the same workload ----------------
+    from oracle import jlm_oracle as O
+    nb_cpu = max(1, min(args.cpu_baseline_sentences, len(sents)))
+    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict)
+    sub = sents[:nb_cpu]
+    ofr = [O.build_lattice(s, ora.w2i, lexicon, reading_dict) for s in sub]
+    t0 = time.perf_counter()
+    cpu_out = [O.decode_static(ora.model, fr, TOPN, BEAM, None) for fr in ofr]
+    cpu_s = time.perf_counter() - t0
+    cpu_chars = sum(len(s) for s in sub)
+    # parity spot-check of the timed GPU output against the oracle on the same sentences
+    words = [packed.node_words(s) for s in range(nb_cpu)]
+    top1_same = 0
+    for s in range(nb_cpu):
+        off = int(packed.node_off[s])
+        ids = path_nodes[s, 0, :path_len[s, 0]]
+        got = [w for w in (words[s][i - off] for i in ids) if w != '<eos>']
+        top1_same += int(got == cpu_out[s][0][1])
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'chars/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp16x2-split->f32' if args.backend == 2 else 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sentences_per_gpu_per_step': S, 'chars_per_gpu_per_step': chars,
+                   'lm_rows_per_step': rows_stepped, 'backend': 'tcgen05' if args.backend == 2 else 'exact-f64',
+                   'l2': 'explicit 256 MiB flush between timed steps', 'host_lattice_build_s': t_lat,
+                   'wall_s_timed_region': wall},
+        'e2e': {'value': e2e, 'unit': 'chars/s', 'h2d_bytes_per_step': int(i2.h2d_bytes),
+                'd2h_bytes_per_step': int(i2.d2h_bytes), 'call': 'jlm_decode_batch (host CSR lattices -> host n-best)'},
+        'gpu_launches': launches,
+        'roofline': roof,
+        'cpu_baseline': {'value': cpu_chars / cpu_s, 'unit': 'chars/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': 'first %d sentences (%d chars), lattice->n-best, numpy oracle' % (nb_cpu, cpu_chars),
+                         'top1_identical_to_gpu': '%d/%d' % (top1_same, nb_cpu)},
+        'clocks': clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

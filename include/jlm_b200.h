@@ -1,0 +1,204 @@
+/*
+ * jlm_b200.h - C ABI of libjlm_b200.so: the B200 (sm_100a) implementation of JLM's numpy
+ * inference hot path (decoder/model.py LSTM step + projection + softmax, decoder/decoder.py and
+ * decoder/decoder_dynamic.py beam search).
+ *
+ * The reference has no FFI of its own: its boundary is the Python class surface
+ * LSTM_Model.predict()/project() and Decoder.decode().  Each entry point
+ * below names the reference interface it replaces; the Python mirror in jlm_b200/model.py,
+ * decoder.py and decoder_dynamic.py binds them with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure with a message available
+ * from jlm_last_error().  Handles are opaque, caller-owned, bound to one CUDA device and one
+ * stream, and NOT thread-safe (the reference objects are not re-entrant either).  Host buffers
+ * are caller-owned, dense row-major, little-endian.  Device memory is owned by the handle.
+ * No call ever falls back to a CPU implementation: without a CUDA device jlm_create fails.
+ */
+#ifndef JLM_B200_H
+#define JLM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JLM_ABI_VERSION 1
+#define JLM_MAX_SEGMENTS 8
+#define JLM_MAX_BEAM 128
+
+/* projection modes, decoder/model.py:141-193 */
+enum {
+  JLM_PROJ_UNTIED = 0,        /* share_embedding=False: h.UM + b2                 (model.py:187-191) */
+  JLM_PROJ_TIED = 1,          /* (h.PM).LM^T + b2                                 (model.py:182-186) */
+  JLM_PROJ_DSOFTMAX = 2,      /* per segment (h.PM)[:,cols_i].LM_i^T              (model.py:144-160) */
+  JLM_PROJ_DSOFTMAX_STAR = 3  /* per segment ((h.PM).VT_i^T).LM_i^T               (model.py:161-181) */
+};
+
+/* arithmetic back ends */
+enum {
+  JLM_BACKEND_AUTO = 0,   /* exact for few rows in flight, tensor cores for lock-step batches */
+  JLM_BACKEND_EXACT = 1,  /* CUDA-core kernels, float64 accumulation over float32 weights (mirrors the
+                             reference's float64 state, model.py:44-45,128-139) */
+  JLM_BACKEND_TC = 2      /* tcgen05 tensor-core GEMMs on 2-term fp16 splits of fp32 operands
+                             (3 MMAs per product, fp32 accumulate in TMEM), fp32 state */
+};
+
+/* decode modes */
+enum {
+  JLM_DECODE_FULL = 0,          /* softmax over the whole vocabulary  (decoder.py:220-241)          */
+  JLM_DECODE_STATIC_VOCAB = 1,  /* vocab_select=True: one sorted list per sentence (decoder.py:137-151) */
+  JLM_DECODE_DYNAMIC = 2        /* DynamicDecoder: per-frame cumulative vocab (decoder_dynamic.py)   */
+};
+
+typedef struct jlm_handle jlm_handle;
+typedef struct jlm_batch jlm_batch;
+
+/* config.json keys the hot path reads (model.py:41-56,117) after normalisation by the host. */
+typedef struct {
+  int32_t vocab_size;    /* V */
+  int32_t hidden_size;   /* H */
+  int32_t input_embed;   /* width of the LSTM input embedding rows (model.py:43,49,56-71) */
+  int32_t proj_mode;     /* JLM_PROJ_* */
+  int32_t self_norm;     /* pred = exp(y) instead of softmax(y) (model.py:117-118) */
+  int32_t n_seg;         /* 1 for untied / tied */
+  int32_t seg_width[JLM_MAX_SEGMENTS];  /* e_i, config['embedding_seg'][i][0] */
+  int32_t seg_start[JLM_MAX_SEGMENTS];  /* first word id of the segment */
+  int32_t seg_end[JLM_MAX_SEGMENTS];    /* one past the last word id (None -> V) */
+} jlm_config;
+
+/* float32 weights in the layout of lstm_weights.pkl (train/weights.py:30-58; shapes from
+ * train/model.py:137-150,188-193,54-62).  Gate order i,f,o,g. */
+typedef struct {
+  const float* HM[4];   /* [H,H]                                                         */
+  const float* IM[4];   /* [input_embed,H]                                               */
+  const float* b[4];    /* [H]                                                           */
+  const float* b2;      /* [V]                                                           */
+  const float* LM_in;   /* [V,input_embed] LSTM input table as materialised by model.py:47-71 */
+  const float* PM;      /* tied modes: [H, sum(seg_width)] (dsoftmax) or [H, seg_width[0]] ; untied: NULL */
+  const float* UM;      /* untied: [H,V]; else NULL                                      */
+  const float* seg_LM[JLM_MAX_SEGMENTS]; /* output blocks [seg_end-seg_start, seg_width] (tied: LM) */
+  const float* seg_VT[JLM_MAX_SEGMENTS]; /* dsoftmax*: VT_i [seg_width[i], seg_width[0]] for i>=1 */
+} jlm_weights;
+
+const char* jlm_last_error(void);
+int32_t jlm_abi_version(void);
+
+/* LSTM_Model.__init__ / _load_model (model.py:37-104): uploads and re-lays-out the weights on
+ * `device`.  Fails (no fallback) when no CUDA device is usable. */
+int32_t jlm_create(const jlm_config* cfg, const jlm_weights* w, int32_t device, jlm_handle** out);
+int32_t jlm_destroy(jlm_handle* h);
+/* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*), e.g.
+ * torch.cuda.current_stream().cuda_stream so torch.cuda.Event timing sees the kernels. */
+int32_t jlm_set_stream(jlm_handle* h, void* cuda_stream);
+int32_t jlm_synchronize(jlm_handle* h);
+
+/* LSTM_Model._lstm_cell (model.py:125-139) for B rows; state in/out float64 [B,H]. */
+int32_t jlm_lstm_step(jlm_handle* h, const int32_t* index, const double* h_in, const double* c_in,
+                      int32_t B, double* h_out, double* c_out);
+
+/* LSTM_Model.project (model.py:141-193).  cols==NULL: y_out is [B,V].  Otherwise y_out is
+ * [B,n_cols] with y[:,j] = logit_without_bias(cols[j]) + b2[bias_idx[j]]; passing two lists lets
+ * the host reproduce the reference's column order for segmented models. */
+int32_t jlm_project(jlm_handle* h, const double* hidden, int32_t B, const int32_t* cols,
+                    const int32_t* bias_idx, int32_t n_cols, double* y_out);
+
+/* LSTM_Model.predict / predict_with_context (model.py:106-123,195-198): step + project + softmax
+ * (or exp when self_norm).  pred_out / y_out are [B,N], N = V or n_cols.  ms_lstm / ms_softmax
+ * receive CUDA-event milliseconds for the two buckets the reference times (model.py:111-121). */
+int32_t jlm_predict(jlm_handle* h, const int32_t* index, const double* h_in, const double* c_in,
+                    int32_t B, const int32_t* cols, const int32_t* bias_idx, int32_t n_cols,
+                    double* pred_out, double* y_out, double* h_out, double* c_out,
+                    float* ms_lstm, float* ms_softmax);
+
+/* A batch of kana lattices (Decoder._build_lattice output, decoder.py:79-135) in CSR form.
+ * Sentence s has frames 0..sent_len[s]; frame_ptr holds, per sentence, sent_len[s]+2 offsets
+ * (starting at frame_ptr_off[s]) into node_start/node_word: the nodes ENDING at each frame, in
+ * the reference's order.  Frame 0 of every sentence holds exactly the <eos> node (start -1). */
+typedef struct {
+  int32_t n_sent;
+  const int32_t* sent_len;       /* [n_sent] kana per sentence (T) */
+  const int64_t* frame_ptr_off;  /* [n_sent] */
+  const int64_t* frame_ptr;      /* [sum(T+2)] absolute node indices */
+  const int32_t* node_start;     /* [n_nodes] start frame, -1 for <eos> */
+  const int32_t* node_word;      /* [n_nodes] word id */
+  /* vocabulary lists, only for JLM_DECODE_STATIC_VOCAB / JLM_DECODE_DYNAMIC:
+   * STATIC : vocab_ids[vocab_ptr[s]..vocab_ptr[s+1]) is lattice_vocab (decoder.py:142-151).
+   * DYNAMIC: the same range lists the sentence's words ordered by the first frame whose
+   *          lattice_vocab contains them (decoder_dynamic.py:30-46); vocab_frame_ptr holds, per
+   *          sentence, sent_len[s]+2 offsets (at frame_ptr_off[s]) relative to vocab_ptr[s]: entries
+   *          [0, vocab_frame_ptr[i+1]) form lattice_vocab[i].  dup_ids (per sentence, dup_ptr) are the
+   *          extra duplicate entries the reference keeps in lattice_vocab[0] only. */
+  const int64_t* vocab_ptr;        /* [n_sent+1] or NULL */
+  const int32_t* vocab_ids;
+  const int32_t* vocab_frame_ptr;  /* DYNAMIC only */
+  const int64_t* dup_ptr;          /* DYNAMIC only, [n_sent+1] */
+  const int32_t* dup_ids;
+} jlm_lattice_batch;
+
+/* n-best output of Decoder.decode (decoder.py:237-241) for every sentence. */
+typedef struct {
+  int32_t top_n;        /* capacity per sentence */
+  int32_t max_len;      /* capacity of one path, >= max(sent_len)+1 */
+  double* scores;       /* [n_sent, top_n] neg_log_prob, ascending */
+  int32_t* n_paths;     /* [n_sent] min(topN, paths in the last frame) */
+  int32_t* path_len;    /* [n_sent, top_n] nodes per path, <eos> node included */
+  int32_t* path_nodes;  /* [n_sent, top_n, max_len] absolute node indices, first to last */
+} jlm_nbest;
+
+/* Decoder.decode / DynamicDecoder.decode (decoder.py:220-241, decoder_dynamic.py:177-194) for a
+ * batch of independent sentences decoded in lock-step: plan + host->device copy + all frames +
+ * device->host copy of the n-best lists.  beam_width <= JLM_MAX_BEAM. */
+int32_t jlm_decode_batch(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
+                         int32_t mode, int32_t backend, jlm_nbest* out);
+
+/* The same call split in three so a benchmark can time the device part with the lattices already
+ * resident in HBM: upload (plan + H2D), run (enqueue every frame, asynchronous), fetch (D2H). */
+int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
+                         int32_t mode, int32_t backend, jlm_batch** out);
+int32_t jlm_batch_run(jlm_batch* b);
+int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out);
+int32_t jlm_batch_destroy(jlm_batch* b);
+
+/* Introspection used by the parity tests and the benchmark. */
+typedef struct {
+  int64_t n_slots;        /* beam entries over all sentences and frames (= LM rows stepped) */
+  int64_t n_candidates;   /* expanded candidates scored over all frames */
+  int64_t n_nodes;
+  int32_t n_steps;        /* lock-step frames */
+  int32_t backend;        /* resolved JLM_BACKEND_* */
+  int64_t kernel_launches;/* kernels enqueued by the last jlm_batch_run */
+  int64_t h2d_bytes;      /* bytes copied by jlm_batch_upload */
+  int64_t d2h_bytes;      /* bytes copied by jlm_batch_fetch */
+  float ms_lstm;          /* CUDA-event totals of the last run when timers are enabled */
+  float ms_softmax;
+  float ms_beam;
+  /* tensor-core back end, timers enabled: CUDA-event time spent inside the two GEMM kernels alone
+   * (gate GEMM + LSTM epilogue; output projection + online-LSE epilogue), their launch counts and
+   * the LM rows they processed, for roofline accounting. */
+  float ms_gate_gemm;
+  float ms_proj_gemm;
+  int32_t n_gate_launches;
+  int32_t n_proj_launches;
+} jlm_batch_info;
+int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info);
+int32_t jlm_batch_enable_timers(jlm_batch* b, int32_t on);
+
+/* Per-frame beams of one sentence after jlm_batch_run (+ synchronize): for frame t the entries
+ * [t*beam_width, t*beam_width + count[t]).  parent_rank/parent_frame identify the back-pointer
+ * (-1 for the <eos> path); node is the absolute node index; lse is the row's log-sum-exp.
+ * h_out/c_out (nullable) receive the float64 state rows [ (T+1)*beam_width, H ]. */
+int32_t jlm_batch_get_beams(jlm_batch* b, int32_t sentence, int32_t* count, double* score,
+                            int32_t* parent_frame, int32_t* parent_rank, int32_t* node, double* lse,
+                            double* h_out, double* c_out);
+
+/* Tensor-core GEMM self-test hook (tests only): C[M,N] = A[M,K].B[N,K]^T through the split-fp16
+ * tcgen05 kernel, float32 in/out on the host. */
+int32_t jlm_tc_gemm_selftest(jlm_handle* h, const float* A, const float* B, int32_t M, int32_t N,
+                             int32_t K, float* C, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JLM_B200_H */

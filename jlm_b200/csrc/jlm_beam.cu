@@ -1,0 +1,926 @@
+// Batched Viterbi beam search over kana lattices (decoder/decoder.py:164-241,
+// decoder/decoder_dynamic.py:53-194), many independent sentences in lock-step.
+//
+// Everything structural is known from the lattice alone: the number of paths kept in frame t of a
+// sentence is min(beam, sum over nodes ending at t of the count kept at the node's start frame), so
+// the host plans every beam slot, LM row and candidate offset up front and the device never
+// synchronises with the host inside the frame loop.  Beam slots are laid out frame-major (all
+// sentences' frame t are contiguous) so one LM step is one GEMM over a contiguous row range.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "jlm_beam.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// device kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_frame0(BeamDev d, int S) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= S) return;
+  const int fid = (int)d.fbase[p];
+  const int64_t s0 = d.slot0[fid];
+  const int node = d.frame_lo[fid];
+  d.slot_score[s0] = 0.0;
+  d.slot_lse[s0] = 0.0;
+  d.slot_parent[s0] = -1;
+  d.slot_node[s0] = node;
+  d.slot_word[s0] = d.node_word[node];
+  if (d.slot_cumy) d.slot_cumy[s0] = 0.0;
+}
+
+// One warp per sentence: expand (decoder.py:172-182), score (Path.append_node, decoder.py:43-49)
+// and keep the beam_width best under the reference's stable sort (decoder.py:227-229): candidates
+// are visited in the reference's enumeration order (node order, then parent rank) and a candidate
+// only displaces kept entries that are strictly worse, so equal scores keep the earlier ordinal.
+// The kept list lives in registers, sorted, entry e at (lane e%32, register e/32); a warp ballot
+// finds the few candidates that beat the current k-th score.
+template <int L, bool DYN>
+__global__ void __launch_bounds__(128)
+k_expand_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nact) return;
+  const unsigned FULL = 0xffffffffu;
+  const int fid = (int)d.fbase[warp] + t;
+  const int lo = d.frame_lo[fid], hi = d.frame_hi[fid];
+
+  if (DYN && use_lse) {
+    // _fix_neg_log (decoder_dynamic.py:150-175): every ancestor transition is re-scored with the
+    // softmax over lattice_vocab[t]; sum the ancestors' LSEs once per potential parent.
+    for (int pf = d.frame_minpf[fid]; pf < fid; ++pf) {
+      const int pc = d.bc[pf];
+      const int64_t ps0 = d.slot0[pf];
+      for (int r = lane; r < pc; r += 32) {
+        double sum = 0.0;
+        int a = (int)(ps0 + r);
+        while (a >= 0) {
+          sum += d.dyn_lse[(int64_t)a * tstride + t];
+          a = d.slot_parent[a];
+        }
+        d.dyn_chain[ps0 + r] = sum;
+      }
+    }
+    __syncwarp();
+  }
+
+  double es[L], ey[L];
+  int ep[L], en[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    es[l] = INFINITY;
+    ey[l] = 0.0;
+    ep[l] = -1;
+    en[l] = -1;
+  }
+  const int kl = (W - 1) >> 5, klane = (W - 1) & 31;
+  double kth = INFINITY;
+
+  for (int n = lo; n < hi; ++n) {
+    const int pf = d.node_pfid[n];
+    const int pc = d.bc[pf];
+    const int64_t ps0 = d.slot0[pf];
+    const int64_t loff = d.logit_off[n];
+    for (int base = 0; base < pc; base += 32) {
+      const int r = base + lane;
+      const bool valid = r < pc;
+      double y = 0.0, sc = INFINITY;
+      if (valid) {
+        y = d.node_logit[loff + r];
+        if (DYN)
+          sc = (use_lse ? d.dyn_chain[ps0 + r] : 0.0) - (d.slot_cumy[ps0 + r] + y);
+        else
+          sc = d.slot_score[ps0 + r] + ((use_lse ? d.slot_lse[ps0 + r] : 0.0) - y);
+      }
+      unsigned m = __ballot_sync(FULL, valid && sc < kth);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const double x = __shfl_sync(FULL, sc, b);
+        const double xy = __shfl_sync(FULL, y, b);
+        if (!(x < kth)) continue;
+        const int xp = (int)(ps0 + base + b);
+        int pos = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) pos += __popc(__ballot_sync(FULL, es[l] <= x));
+#pragma unroll
+        for (int l = L - 1; l >= 0; --l) {
+          const int idx = l * 32 + lane;
+          double us = __shfl_up_sync(FULL, es[l], 1);
+          double uy = __shfl_up_sync(FULL, ey[l], 1);
+          int up = __shfl_up_sync(FULL, ep[l], 1);
+          int un = __shfl_up_sync(FULL, en[l], 1);
+          if (l > 0) {
+            const double cs = __shfl_sync(FULL, es[l > 0 ? l - 1 : 0], 31);
+            const double cy = __shfl_sync(FULL, ey[l > 0 ? l - 1 : 0], 31);
+            const int cp = __shfl_sync(FULL, ep[l > 0 ? l - 1 : 0], 31);
+            const int cn = __shfl_sync(FULL, en[l > 0 ? l - 1 : 0], 31);
+            if (lane == 0) {
+              us = cs;
+              uy = cy;
+              up = cp;
+              un = cn;
+            }
+          }
+          if (idx > pos) {
+            es[l] = us;
+            ey[l] = uy;
+            ep[l] = up;
+            en[l] = un;
+          } else if (idx == pos) {
+            es[l] = x;
+            ey[l] = xy;
+            ep[l] = xp;
+            en[l] = n;
+          }
+        }
+        double kv = es[0];
+#pragma unroll
+        for (int l = 1; l < L; ++l)
+          if (l == kl) kv = es[l];
+        kth = __shfl_sync(FULL, kv, klane);
+      }
+    }
+  }
+
+  const int cnt = d.bc[fid];
+  const int64_t s0 = d.slot0[fid];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int idx = l * 32 + lane;
+    if (idx < cnt) {
+      d.slot_score[s0 + idx] = es[l];
+      d.slot_parent[s0 + idx] = ep[l];
+      d.slot_node[s0 + idx] = en[l];
+      d.slot_word[s0 + idx] = en[l] >= 0 ? d.node_word[en[l]] : 0;
+      if (DYN) d.slot_cumy[s0 + idx] = (ep[l] >= 0 ? d.slot_cumy[ep[l]] : 0.0) + ey[l];
+    }
+  }
+}
+
+// decoder.py:237: walk the back-pointers of the best paths of the last frame.
+__global__ void k_backtrace(BeamDev d, int S, int topN, int max_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * topN) return;
+  const int p = i / topN, k = i % topN;
+  const int fid = (int)d.fbase[p] + d.sent_T[p];
+  const int cnt = min(topN, d.bc[fid]);
+  if (k == 0) d.out_npaths[p] = cnt;
+  if (k >= cnt) {
+    d.out_len[i] = 0;
+    d.out_score[i] = INFINITY;
+    return;
+  }
+  const int slot = (int)d.slot0[fid] + k;
+  int depth = 0;
+  for (int a = slot; a >= 0; a = d.slot_parent[a]) ++depth;
+  d.out_len[i] = depth;
+  d.out_score[i] = d.slot_score[slot];
+  int q = depth - 1;
+  for (int a = slot; a >= 0; a = d.slot_parent[a], --q)
+    if (q < max_len) d.out_nodes[(int64_t)i * max_len + q] = d.slot_node[a];
+}
+
+// static vocab_select: one warp per LM row, LSE over the sentence's lattice_vocab logits.
+__global__ void __launch_bounds__(128)
+k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv, double* __restrict__ lse_out) {
+  const SubsetJob job = jobs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= job.rows) return;
+  const double* p = yv + job.out0 + (int64_t)r * job.ncols;
+  double mx = -INFINITY;
+  for (int j = lane; j < job.ncols; j += 32) mx = fmax(mx, p[j]);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double s = 0.0;
+  for (int j = lane; j < job.ncols; j += 32) s += exp(p[j] - mx);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) lse_out[job.row0 + r] = mx + log(s);
+}
+
+// DynamicDecoder: the row stepped at frame k is later scored under lattice_vocab[i] for every
+// i > k (decoder_dynamic.py:112-148).  Columns are ordered by first appearance, so LSE_i is a
+// running log-sum-exp cut at the per-frame boundaries; frame 0 also counts the duplicate entries the
+// reference keeps in lattice_vocab[0].
+__global__ void __launch_bounds__(128)
+k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restrict__ info,
+                 const int32_t* __restrict__ vfp, const double* __restrict__ yv, double* __restrict__ dyn_lse,
+                 int64_t slot_base, int k, int tstride) {
+  const SubsetJob job = jobs[blockIdx.y];
+  const DynJobInfo inf = info[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= job.rows) return;
+  const double* p = yv + job.out0 + (int64_t)r * job.ncols;
+  const int64_t slot = slot_base + job.row0 + r;
+  double M = -INFINITY, Ssum = 0.0;
+  int pos = 0;
+  for (int i = k + 1; i <= inf.T; ++i) {
+    const int end = vfp[inf.vfp_off + i + 1];
+    double mx = -INFINITY;
+    for (int j = pos + lane; j < end; j += 32) mx = fmax(mx, p[j]);
+    if (i == k + 1 && k == 0)
+      for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) mx = fmax(mx, p[j]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (mx > -INFINITY) {
+      double s = 0.0;
+      for (int j = pos + lane; j < end; j += 32) s += exp(p[j] - mx);
+      if (i == k + 1 && k == 0)
+        for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) s += exp(p[j] - mx);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const double nm = fmax(M, mx);
+      Ssum = Ssum * exp(M - nm) + s * exp(mx - nm);
+      M = nm;
+    }
+    pos = end;
+    if (lane == 0) dyn_lse[slot * tstride + i] = M + log(Ssum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: plan
+// ------------------------------------------------------------------------------------------------
+struct HostPlan {
+  std::vector<int32_t> node_word, node_pfid, frame_lo, frame_hi, frame_minpf, bc, sent_T, start_words;
+  std::vector<int64_t> logit_off, slot0, fbase;
+  std::vector<SubsetJob> node_jobs, vocab_jobs;
+  std::vector<DynJobInfo> dyn_info;
+  std::vector<int32_t> vocab_cols, vfp;
+};
+
+template <class T>
+T* place(Arena& a, const std::vector<T>& v) { return a.take<T>(v.size() ? v.size() : 1); }
+
+int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
+  jlm_handle* h = b->h;
+  const int S = lat->n_sent;
+  JLM_REQUIRE(S > 0, "decode: empty batch");
+  JLM_REQUIRE(lat->sent_len && lat->frame_ptr_off && lat->frame_ptr && lat->node_start && lat->node_word,
+              "decode: null lattice arrays");
+  b->S = S;
+  b->order.resize(S);
+  std::iota(b->order.begin(), b->order.end(), 0);
+  std::stable_sort(b->order.begin(), b->order.end(),
+                   [&](int a, int c) { return lat->sent_len[a] > lat->sent_len[c]; });
+  b->sent_T.resize(S);
+  b->fbase.resize(S + 1);
+  int64_t F = 0;
+  int Tmax = 0;
+  for (int p = 0; p < S; ++p) {
+    const int T = lat->sent_len[b->order[p]];
+    JLM_REQUIRE(T >= 0, "decode: negative sentence length");
+    b->sent_T[p] = T;
+    b->fbase[p] = F;
+    F += T + 1;
+    Tmax = std::max(Tmax, T);
+  }
+  b->fbase[S] = F;
+  JLM_REQUIRE(F < (int64_t)1 << 30, "decode: too many frames");
+  b->F = F;
+  b->Tmax = Tmax;
+  b->n_steps = Tmax + 1;
+  b->max_len = Tmax + 1;
+
+  int64_t N = 0;
+  for (int s = 0; s < S; ++s) {
+    const int64_t* fp = lat->frame_ptr + lat->frame_ptr_off[s];
+    N = std::max<int64_t>(N, fp[lat->sent_len[s] + 1]);
+  }
+  JLM_REQUIRE(N < (int64_t)1 << 31, "decode: too many lattice nodes");
+  b->N = N;
+  P.node_word.assign(lat->node_word, lat->node_word + N);
+  P.node_pfid.assign(N, -1);
+  P.logit_off.assign(N, 0);
+  P.frame_lo.assign(F, 0);
+  P.frame_hi.assign(F, 0);
+  P.frame_minpf.assign(F, 0);
+  P.bc.assign(F, 0);
+  P.slot0.assign(F, 0);
+  P.sent_T = b->sent_T;
+  P.fbase = b->fbase;
+
+  std::vector<int32_t> nstart(F, 0);
+  int64_t n_cand_total = 0;
+  for (int p = 0; p < S; ++p) {
+    const int s = b->order[p];
+    const int T = b->sent_T[p];
+    const int64_t* fp = lat->frame_ptr + lat->frame_ptr_off[s];
+    const int64_t fb = b->fbase[p];
+    JLM_REQUIRE(fp[1] - fp[0] == 1 && lat->node_start[fp[0]] == -1,
+                "decode: frame 0 of sentence %d must hold exactly the <eos> node", s);
+    for (int t = 0; t <= T; ++t) {
+      JLM_REQUIRE(fp[t + 1] >= fp[t], "decode: frame_ptr not monotone (sentence %d)", s);
+      P.frame_lo[fb + t] = (int32_t)fp[t];
+      P.frame_hi[fb + t] = (int32_t)fp[t + 1];
+      int64_t ncand = 0;
+      int minpf = (int)(fb + t);
+      for (int64_t n = fp[t]; n < fp[t + 1]; ++n) {
+        const int w = lat->node_word[n];
+        JLM_REQUIRE(w >= 0 && w < h->V, "decode: word id %d out of range", w);
+        if (t == 0) continue;
+        const int st = lat->node_start[n];
+        JLM_REQUIRE(st >= 0 && st < t, "decode: node %lld of sentence %d has start %d at frame %d", (long long)n, s, st, t);
+        P.node_pfid[n] = (int32_t)(fb + st);
+        nstart[fb + st] += 1;
+        ncand += P.bc[fb + st];
+        minpf = std::min(minpf, (int)(fb + st));
+      }
+      P.frame_minpf[fb + t] = minpf;
+      P.bc[fb + t] = t == 0 ? 1 : (int32_t)std::min<int64_t>(b->W, ncand);
+      n_cand_total += ncand;
+    }
+  }
+  b->bc = P.bc;
+  b->n_cand = n_cand_total;
+
+  // frame-major slot layout + step table
+  b->steps.assign(b->n_steps, StepPlan{});
+  int64_t slot = 0;
+  for (int t = 0; t < b->n_steps; ++t) {
+    StepPlan& sp = b->steps[t];
+    sp.row0 = slot;
+    for (int p = 0; p < S && b->sent_T[p] >= t; ++p) {
+      const int64_t fid = b->fbase[p] + t;
+      P.slot0[fid] = slot;
+      slot += P.bc[fid];
+      sp.nact++;
+      sp.rows_all += P.bc[fid];
+      if (b->sent_T[p] > t) {
+        sp.nstep++;
+        sp.rows_step += P.bc[fid];
+      }
+    }
+    b->max_rows_step = std::max(b->max_rows_step, sp.rows_step);
+  }
+  JLM_REQUIRE(slot < (int64_t)1 << 31, "decode: too many beam slots");
+  b->n_slots = slot;
+  b->slot0 = P.slot0;
+
+  // nodes grouped by start frame; node logits are stored [start frame][node][parent rank]
+  std::vector<int64_t> start_ptr(F + 1, 0);
+  for (int64_t f = 0; f < F; ++f) start_ptr[f + 1] = start_ptr[f] + nstart[f];
+  P.start_words.assign(std::max<int64_t>(start_ptr[F], 1), 0);
+  std::vector<int64_t> cand_base(F, 0);
+  {
+    int64_t base = 0;
+    for (int64_t f = 0; f < F; ++f) {
+      cand_base[f] = base;
+      base += (int64_t)nstart[f] * P.bc[f];
+    }
+    JLM_REQUIRE(base == n_cand_total, "decode: internal candidate count mismatch");
+    std::vector<int64_t> fill(start_ptr.begin(), start_ptr.end() - 1);
+    for (int64_t n = 0; n < N; ++n) {
+      const int pf = P.node_pfid[n];
+      if (pf < 0) continue;
+      const int64_t q = fill[pf]++;
+      P.start_words[q] = P.node_word[n];
+      P.logit_off[n] = cand_base[pf] + (q - start_ptr[pf]) * P.bc[pf];
+    }
+  }
+
+  // per-step jobs
+  const bool vocab_mode = b->mode != JLM_DECODE_FULL;
+  if (vocab_mode) {
+    JLM_REQUIRE(lat->vocab_ptr && lat->vocab_ids, "decode: vocabulary lists missing for mode %d", b->mode);
+    JLM_REQUIRE(!h->untied, "decode: vocabulary selection with an untied projection raises in the reference "
+                            "(decoder/model.py:189); not supported");
+    if (b->dynamic) {
+      JLM_REQUIRE(lat->vocab_frame_ptr && lat->dup_ptr, "decode: dynamic mode needs vocab_frame_ptr and dup_ptr");
+      JLM_REQUIRE(h->n_seg == 1, "decode: DynamicDecoder with a segmented softmax reads permuted logits in the "
+                                 "reference (SURVEY quirk 3); not supported");
+    }
+  }
+  std::vector<int64_t> col_ptr(S + 1, 0);  // by caller's sentence index
+  if (vocab_mode) {
+    for (int s = 0; s < S; ++s) {
+      const int64_t nv = lat->vocab_ptr[s + 1] - lat->vocab_ptr[s];
+      const int64_t nd = b->dynamic ? lat->dup_ptr[s + 1] - lat->dup_ptr[s] : 0;
+      JLM_REQUIRE(nv > 0 && nd >= 0, "decode: empty vocabulary list for sentence %d", s);
+      col_ptr[s + 1] = col_ptr[s] + nv + nd;
+    }
+    P.vocab_cols.resize(col_ptr[S]);
+    for (int s = 0; s < S; ++s) {
+      const int64_t nv = lat->vocab_ptr[s + 1] - lat->vocab_ptr[s];
+      int32_t* dst = &P.vocab_cols[col_ptr[s]];
+      for (int64_t j = 0; j < nv; ++j) dst[j] = lat->vocab_ids[lat->vocab_ptr[s] + j];
+      if (b->dynamic)
+        for (int64_t j = 0; j < lat->dup_ptr[s + 1] - lat->dup_ptr[s]; ++j) dst[nv + j] = lat->dup_ids[lat->dup_ptr[s] + j];
+      for (int64_t j = 0; j < col_ptr[s + 1] - col_ptr[s]; ++j)
+        JLM_REQUIRE(dst[j] >= 0 && dst[j] < h->V, "decode: vocabulary id %d out of range", dst[j]);
+    }
+    if (b->dynamic) {
+      int64_t tot = 0;
+      for (int s = 0; s < S; ++s) tot += lat->sent_len[s] + 2;
+      P.vfp.assign(lat->vocab_frame_ptr, lat->vocab_frame_ptr + tot);
+    }
+  }
+  int64_t job = 0;
+  for (int t = 0; t < b->n_steps; ++t) {
+    StepPlan& sp = b->steps[t];
+    sp.job0 = job;
+    int64_t yv = 0;
+    for (int p = 0; p < sp.nstep; ++p) {
+      const int64_t fid = b->fbase[p] + t;
+      SubsetJob nj{P.slot0[fid] - sp.row0, P.bc[fid], start_ptr[fid], nstart[fid], cand_base[fid]};
+      P.node_jobs.push_back(nj);
+      sp.max_node_cols = std::max(sp.max_node_cols, nstart[fid]);
+      if (vocab_mode) {
+        const int s = b->order[p];
+        const int nc = (int)(col_ptr[s + 1] - col_ptr[s]);
+        SubsetJob vj{P.slot0[fid] - sp.row0, P.bc[fid], col_ptr[s], nc, yv};
+        yv += (int64_t)P.bc[fid] * nc;
+        P.vocab_jobs.push_back(vj);
+        sp.max_vocab_cols = std::max(sp.max_vocab_cols, nc);
+        if (b->dynamic) {
+          const int64_t nd = lat->dup_ptr[s + 1] - lat->dup_ptr[s];
+          DynJobInfo di{lat->frame_ptr_off[s], (int32_t)(nc - nd), (int32_t)nd, b->sent_T[p], 0};
+          P.dyn_info.push_back(di);
+        }
+      }
+      ++job;
+    }
+    sp.yv_elems = yv;
+    b->max_yv = std::max(b->max_yv, yv);
+  }
+  b->n_jobs = job;
+  return 0;
+}
+
+// device memory layout; called twice (dry run to size, then for real)
+void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
+  jlm_handle* h = b->h;
+  BeamDev& d = b->d;
+  d.node_word = place(a, P.node_word);
+  d.node_pfid = place(a, P.node_pfid);
+  d.logit_off = place(a, P.logit_off);
+  d.frame_lo = place(a, P.frame_lo);
+  d.frame_hi = place(a, P.frame_hi);
+  d.frame_minpf = place(a, P.frame_minpf);
+  d.bc = place(a, P.bc);
+  d.slot0 = place(a, P.slot0);
+  d.fbase = place(a, P.fbase);
+  d.sent_T = place(a, P.sent_T);
+  d.start_words = place(a, P.start_words);
+  d.node_jobs = place(a, P.node_jobs);
+  d.vocab_jobs = place(a, P.vocab_jobs);
+  d.dyn_info = place(a, P.dyn_info);
+  d.vocab_cols = place(a, P.vocab_cols);
+  d.vfp = place(a, P.vfp);
+  const size_t ns = (size_t)b->n_slots;
+  d.slot_score = a.take<double>(ns);
+  d.slot_lse = a.take<double>(ns);
+  d.slot_parent = a.take<int32_t>(ns);
+  d.slot_node = a.take<int32_t>(ns);
+  d.slot_word = a.take<int32_t>(ns);
+  d.slot_cumy = d.dyn_lse = d.dyn_chain = nullptr;
+  if (b->dynamic) {
+    d.slot_cumy = a.take<double>(ns);
+    d.dyn_chain = a.take<double>(ns);
+    d.dyn_lse = a.take<double>(ns * (size_t)(b->Tmax + 1));
+  }
+  d.node_logit = a.take<double>((size_t)std::max<int64_t>(b->n_cand, 1));
+  d.out_score = a.take<double>((size_t)b->S * b->topN);
+  d.out_npaths = a.take<int32_t>((size_t)b->S);
+  d.out_len = a.take<int32_t>((size_t)b->S * b->topN);
+  d.out_nodes = a.take<int32_t>((size_t)b->S * b->topN * b->max_len);
+  b->yv = b->max_yv ? a.take<double>((size_t)b->max_yv) : nullptr;
+  if (b->backend == JLM_BACKEND_EXACT) {
+    const size_t mr = (size_t)std::max(b->max_rows_step, 1);
+    b->hx = a.take<double>(ns * h->Hp);
+    b->cx = a.take<double>(ns * h->Hp);
+    b->A = a.take<double>(mr * h->Kg);
+    b->G = a.take<double>(mr * 4 * h->H);
+    b->T = h->untied ? nullptr : a.take<double>(mr * h->Kt);
+    b->part_tiles = 0;
+    for (int i = 0; i < h->n_seg; ++i) b->part_tiles += exact_tiles_n(h->seg[i].end - h->seg[i].start);
+    b->part = (b->mode == JLM_DECODE_FULL && b->use_lse) ? a.take<double2>(mr * b->part_tiles) : nullptr;
+  }
+}
+
+template <class T>
+void stage(char* host, char* dev_base, T* dev_ptr, const std::vector<T>& v) {
+  if (v.empty()) return;
+  memcpy(host + (reinterpret_cast<char*>(dev_ptr) - dev_base), v.data(), v.size() * sizeof(T));
+}
+
+// Shared tail of an LM step: vocabulary-subset softmax statistics (static / dynamic selection) and
+// the logits of the words that can follow each kept path (nodes starting at this frame).
+template <typename TT>
+int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
+  jlm_handle* h = b->h;
+  cudaStream_t st = h->stream;
+  const StepPlan& sp = b->steps[t];
+  BeamDev& d = b->d;
+  if (b->use_lse && b->mode != JLM_DECODE_FULL) {
+    JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.vocab_jobs + sp.job0, sp.nstep, sp.max_vocab_cols, d.vocab_cols, nullptr,
+                              b->yv, 1));
+    dim3 grid(ceil_div(b->W, 4), sp.nstep);
+    if (b->dynamic)
+      k_dyn_prefix_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse,
+                                             sp.row0, t, b->Tmax + 1);
+    else
+      k_job_rows_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0);
+    JLM_CUDA(cudaGetLastError());
+    b->launches += 2;
+  }
+  if (sp.max_node_cols > 0) {
+    JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.node_jobs + sp.job0, sp.nstep, sp.max_node_cols, d.start_words, nullptr,
+                              d.node_logit, 0));
+    b->launches += 1;
+  }
+  return 0;
+}
+
+int32_t exact_lm_step(jlm_batch* b, int t) {
+  jlm_handle* h = b->h;
+  cudaStream_t st = h->stream;
+  const StepPlan& sp = b->steps[t];
+  const int M = sp.rows_step;
+  if (M == 0) return 0;
+  BeamDev& d = b->d;
+  const int32_t* parent = d.slot_parent + sp.row0;
+  const int32_t* word = d.slot_word + sp.row0;
+  double* hrow = b->hx + sp.row0 * h->Hp;
+  double* crow = b->cx + sp.row0 * h->Hp;
+  if (b->timers) cudaEventRecord(b->events[3 * t + 1], st);
+  JLM_TRY(exact_gather_gate_input(st, h, b->hx, parent, word, M, b->A));
+  JLM_TRY(exact_gemm_f32w(st, b->A, h->Kg, h->Wg, h->Kg, h->bg, b->G, 4 * h->H, M, 4 * h->H, h->Kg, nullptr, 0, 0));
+  JLM_TRY(exact_lstm_pointwise(st, h, b->G, b->cx, parent, M, hrow, crow));
+  b->launches += 3;
+  if (b->timers) cudaEventRecord(b->events[3 * t + 2], st);
+  const double* T = hrow;
+  int ldt = h->Hp;
+  if (!h->untied) {
+    JLM_TRY(exact_gemm_f64w(st, hrow, h->Hp, h->P1, h->Hp, b->T, h->Kt, M, h->Kt, h->Hp));
+    b->launches += 1;
+    T = b->T;
+    ldt = h->Kt;
+  }
+  if (b->use_lse && b->mode == JLM_DECODE_FULL) {
+    int tile0 = 0;
+    for (int i = 0; i < h->n_seg; ++i) {
+      const SegDev& s = h->seg[i];
+      const int Vi = s.end - s.start;
+      JLM_TRY(exact_gemm_f32w(st, T + s.koff, ldt, s.W, s.kpad, h->b2 + s.start, nullptr, 0, M, Vi, s.kpad, b->part,
+                              b->part_tiles, tile0));
+      tile0 += exact_tiles_n(Vi);
+      b->launches += 1;
+    }
+    JLM_TRY(exact_lse_merge(st, b->part, b->part_tiles, b->part_tiles, M, d.slot_lse + sp.row0, 0));
+    b->launches += 1;
+  }
+  return lm_step_tail<double>(b, t, T, ldt);
+}
+
+template <bool DYN>
+int32_t launch_prune(jlm_batch* b, int t) {
+  const StepPlan& sp = b->steps[t];
+  if (sp.nact == 0) return 0;
+  const int grid = ceil_div(sp.nact, 4);
+  const int L = ceil_div(b->W, 32);
+  const int ul = b->use_lse ? 1 : 0;
+  cudaStream_t st = b->h->stream;
+  if (L <= 1)
+    k_expand_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+  else if (L <= 2)
+    k_expand_prune<2, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+  else
+    k_expand_prune<4, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+  JLM_CUDA(cudaGetLastError());
+  b->launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
+                                    int32_t mode, int32_t backend, jlm_batch** out) {
+  JLM_REQUIRE(h && lat && out, "jlm_batch_upload: null argument");
+  JLM_REQUIRE(beam_width >= 1 && beam_width <= JLM_MAX_BEAM, "jlm_batch_upload: beam_width %d not in [1,%d]", beam_width,
+              JLM_MAX_BEAM);
+  JLM_REQUIRE(top_n >= 1, "jlm_batch_upload: top_n must be >= 1");
+  JLM_REQUIRE(mode >= 0 && mode <= 2, "jlm_batch_upload: bad mode %d", mode);
+  JLM_CUDA(cudaSetDevice(h->device));
+  *out = nullptr;
+  jlm_batch* b = new jlm_batch();
+  b->h = h;
+  b->W = beam_width;
+  b->topN = std::min(top_n, beam_width);
+  b->mode = mode;
+  b->dynamic = mode == JLM_DECODE_DYNAMIC;
+  b->use_lse = h->cfg.self_norm == 0;
+  HostPlan P;
+  if (build_plan(b, lat, P)) {
+    delete b;
+    return 1;
+  }
+  if (backend == JLM_BACKEND_AUTO) backend = (b->max_rows_step >= 512) ? JLM_BACKEND_TC : JLM_BACKEND_EXACT;
+  JLM_REQUIRE(backend == JLM_BACKEND_EXACT || backend == JLM_BACKEND_TC, "jlm_batch_upload: bad backend %d", backend);
+  b->backend = backend;
+  int32_t rc = 0;
+  Arena a;
+  a.begin_plan();
+  layout(b, a, P);
+  if (backend == JLM_BACKEND_TC) rc = tc_batch_plan(b, a);
+  if (!rc) {
+    std::swap(b->mem, h->batch_cache);   // reuse the previous batch's allocation when it is big enough
+    std::swap(a.buf, b->mem);
+    rc = a.commit();
+    std::swap(a.buf, b->mem);
+  }
+  if (!rc) {
+    a.buf = b->mem;
+    a.off = 0;
+    a.dry = false;
+    layout(b, a, P);
+    const size_t plan_bytes = reinterpret_cast<char*>(b->d.slot_score) - reinterpret_cast<char*>(b->mem.p);
+    if (backend == JLM_BACKEND_TC) rc = tc_batch_plan(b, a);
+    a.buf = DevBuf();  // ownership stays with b->mem
+    if (!rc) rc = h->pinned[0].reserve(plan_bytes);
+    if (!rc) {
+      char* host = h->pinned[0].as<char>();
+      char* base = static_cast<char*>(b->mem.p);
+      memset(host, 0, plan_bytes);
+      stage(host, base, b->d.node_word, P.node_word);
+      stage(host, base, b->d.node_pfid, P.node_pfid);
+      stage(host, base, b->d.logit_off, P.logit_off);
+      stage(host, base, b->d.frame_lo, P.frame_lo);
+      stage(host, base, b->d.frame_hi, P.frame_hi);
+      stage(host, base, b->d.frame_minpf, P.frame_minpf);
+      stage(host, base, b->d.bc, P.bc);
+      stage(host, base, b->d.slot0, P.slot0);
+      stage(host, base, b->d.fbase, P.fbase);
+      stage(host, base, b->d.sent_T, P.sent_T);
+      stage(host, base, b->d.start_words, P.start_words);
+      stage(host, base, b->d.node_jobs, P.node_jobs);
+      stage(host, base, b->d.vocab_jobs, P.vocab_jobs);
+      stage(host, base, b->d.dyn_info, P.dyn_info);
+      stage(host, base, b->d.vocab_cols, P.vocab_cols);
+      stage(host, base, b->d.vfp, P.vfp);
+      if (cudaMemcpyAsync(base, host, plan_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+        jlm_set_error("jlm_batch_upload: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+      }
+      b->h2d_bytes = (int64_t)plan_bytes;
+      // the pinned staging buffer is reused by the next upload: wait for the copy
+      if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        jlm_set_error("jlm_batch_upload: sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+      }
+    }
+  }
+  if (rc) {
+    jlm_batch_destroy(b);
+    return 1;
+  }
+  *out = b;
+  return 0;
+}
+
+extern "C" int32_t jlm_batch_run(jlm_batch* b) {
+  JLM_REQUIRE(b, "jlm_batch_run: null batch");
+  jlm_handle* h = b->h;
+  JLM_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  b->launches = 0;
+  if (b->timers && b->events.empty()) {
+    b->events.resize(3 * (size_t)b->n_steps + 1);
+    for (auto& e : b->events) JLM_CUDA(cudaEventCreate(&e));
+    b->kev.resize(4 * (size_t)b->n_steps);
+    for (auto& e : b->kev) JLM_CUDA(cudaEventCreate(&e));
+  }
+  for (int t = 0; t < b->n_steps; ++t) {
+    if (b->timers) cudaEventRecord(b->events[3 * t], st);
+    if (t == 0) {
+      k_init_frame0<<<ceil_div(b->S, 128), 128, 0, st>>>(b->d, b->S);
+      JLM_CUDA(cudaGetLastError());
+      b->launches += 1;
+    } else if (b->dynamic) {
+      JLM_TRY(launch_prune<true>(b, t));
+    } else {
+      JLM_TRY(launch_prune<false>(b, t));
+    }
+    if (b->backend == JLM_BACKEND_EXACT) {
+      JLM_TRY(exact_lm_step(b, t));
+    } else {
+      const float* T32 = nullptr;
+      int ldt = 0;
+      JLM_TRY(tc_batch_lm_step(b, t, &T32, &ldt));
+      if (T32) JLM_TRY(lm_step_tail<float>(b, t, T32, ldt));
+    }
+  }
+  if (b->timers) cudaEventRecord(b->events[3 * (size_t)b->n_steps], st);
+  k_backtrace<<<ceil_div((int64_t)b->S * b->topN, 128), 128, 0, st>>>(b->d, b->S, b->topN, b->max_len);
+  JLM_CUDA(cudaGetLastError());
+  b->launches += 1;
+  b->ran = true;
+  return 0;
+}
+
+extern "C" int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out) {
+  JLM_REQUIRE(b && out, "jlm_batch_fetch: null argument");
+  JLM_REQUIRE(b->ran, "jlm_batch_fetch: jlm_batch_run has not been called");
+  JLM_REQUIRE(out->top_n >= b->topN && out->max_len >= b->max_len,
+              "jlm_batch_fetch: output capacity too small (top_n %d < %d or max_len %d < %d)", out->top_n, b->topN,
+              out->max_len, b->max_len);
+  jlm_handle* h = b->h;
+  JLM_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)b->S * b->topN;
+  const size_t bytes_score = n * sizeof(double), bytes_np = (size_t)b->S * sizeof(int32_t),
+               bytes_len = n * sizeof(int32_t), bytes_nodes = n * b->max_len * sizeof(int32_t);
+  // out_score .. out_nodes are consecutive 256-aligned arena blocks: copy them in one transfer
+  const char* src = reinterpret_cast<const char*>(b->d.out_score);
+  const size_t total = (reinterpret_cast<const char*>(b->d.out_nodes) - src) + bytes_nodes;
+  JLM_TRY(h->pinned[1].reserve(total));
+  char* host = h->pinned[1].as<char>();
+  JLM_CUDA(cudaMemcpyAsync(host, src, total, cudaMemcpyDeviceToHost, h->stream));
+  JLM_CUDA(cudaStreamSynchronize(h->stream));
+  b->d2h_bytes = (int64_t)total;
+  (void)bytes_score;
+  (void)bytes_np;
+  (void)bytes_len;
+  const double* sc = reinterpret_cast<const double*>(host);
+  const int32_t* np_ = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_npaths) - src));
+  const int32_t* ln = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_len) - src));
+  const int32_t* nd = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_nodes) - src));
+  for (int p = 0; p < b->S; ++p) {
+    const int s = b->order[p];
+    out->n_paths[s] = np_[p];
+    for (int k = 0; k < out->top_n; ++k) {
+      const size_t o = (size_t)s * out->top_n + k;
+      if (k < b->topN) {
+        const size_t i = (size_t)p * b->topN + k;
+        out->scores[o] = sc[i];
+        out->path_len[o] = ln[i];
+        memcpy(out->path_nodes + o * out->max_len, nd + i * b->max_len, sizeof(int32_t) * std::min(ln[i], b->max_len));
+      } else {
+        out->scores[o] = INFINITY;
+        out->path_len[o] = 0;
+      }
+    }
+  }
+  if (b->timers && !b->events.empty()) {
+    b->ms_lstm = b->ms_softmax = b->ms_beam = 0.f;
+    for (int t = 0; t < b->n_steps; ++t) {
+      if (b->steps[t].rows_step == 0) {
+        float x = 0.f;
+        cudaEventElapsedTime(&x, b->events[3 * t], b->events[3 * t + 3]);
+        b->ms_beam += x;
+        continue;
+      }
+      float x = 0.f, y = 0.f, z = 0.f;
+      cudaEventElapsedTime(&x, b->events[3 * t], b->events[3 * t + 1]);
+      cudaEventElapsedTime(&y, b->events[3 * t + 1], b->events[3 * t + 2]);
+      cudaEventElapsedTime(&z, b->events[3 * t + 2], b->events[3 * t + 3]);
+      b->ms_beam += x;
+      b->ms_lstm += y;
+      b->ms_softmax += z;
+    }
+    b->ms_gate_gemm = b->ms_proj_gemm = 0.f;
+    b->n_gate_launches = b->n_proj_launches = 0;
+    if (b->backend == JLM_BACKEND_TC) {
+      const bool proj = b->mode == JLM_DECODE_FULL && b->use_lse;
+      for (int t = 0; t < b->n_steps; ++t) {
+        if (b->steps[t].rows_step == 0) continue;
+        float x = 0.f;
+        cudaEventElapsedTime(&x, b->kev[4 * t], b->kev[4 * t + 1]);
+        b->ms_gate_gemm += x;
+        b->n_gate_launches += 1;
+        if (proj) {
+          cudaEventElapsedTime(&x, b->kev[4 * t + 2], b->kev[4 * t + 3]);
+          b->ms_proj_gemm += x;
+          b->n_proj_launches += b->h->n_seg;
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" int32_t jlm_batch_destroy(jlm_batch* b) {
+  if (!b) return 0;
+  cudaSetDevice(b->h->device);
+  cudaStreamSynchronize(b->h->stream);
+  tc_batch_free(b);
+  for (auto& e : b->events) cudaEventDestroy(e);
+  for (auto& e : b->kev) cudaEventDestroy(e);
+  if (b->mem.cap > b->h->batch_cache.cap) std::swap(b->mem, b->h->batch_cache);
+  b->mem.release();
+  delete b;
+  return 0;
+}
+
+extern "C" int32_t jlm_decode_batch(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
+                                    int32_t mode, int32_t backend, jlm_nbest* out) {
+  jlm_batch* b = nullptr;
+  JLM_TRY(jlm_batch_upload(h, lat, beam_width, top_n, mode, backend, &b));
+  int32_t rc = jlm_batch_run(b);
+  if (!rc) rc = jlm_batch_fetch(b, out);
+  jlm_batch_destroy(b);
+  return rc;
+}
+
+extern "C" int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info) {
+  JLM_REQUIRE(b && info, "jlm_batch_get_info: null argument");
+  int64_t stepped = 0;
+  for (auto& s : b->steps) stepped += s.rows_step;
+  info->n_slots = stepped;
+  info->n_candidates = b->n_cand;
+  info->n_nodes = b->N;
+  info->n_steps = b->n_steps;
+  info->backend = b->backend;
+  info->kernel_launches = b->launches;
+  info->h2d_bytes = b->h2d_bytes;
+  info->d2h_bytes = b->d2h_bytes;
+  info->ms_lstm = b->ms_lstm;
+  info->ms_softmax = b->ms_softmax;
+  info->ms_beam = b->ms_beam;
+  info->ms_gate_gemm = b->ms_gate_gemm;
+  info->ms_proj_gemm = b->ms_proj_gemm;
+  info->n_gate_launches = b->n_gate_launches;
+  info->n_proj_launches = b->n_proj_launches;
+  return 0;
+}
+
+extern "C" int32_t jlm_batch_enable_timers(jlm_batch* b, int32_t on) {
+  JLM_REQUIRE(b, "jlm_batch_enable_timers: null batch");
+  b->timers = on != 0;
+  return 0;
+}
+
+extern "C" int32_t jlm_batch_get_beams(jlm_batch* b, int32_t sentence, int32_t* count, double* score,
+                                       int32_t* parent_frame, int32_t* parent_rank, int32_t* node, double* lse,
+                                       double* h_out, double* c_out) {
+  JLM_REQUIRE(b && b->ran, "jlm_batch_get_beams: run the batch first");
+  JLM_REQUIRE(sentence >= 0 && sentence < b->S, "jlm_batch_get_beams: sentence out of range");
+  jlm_handle* h = b->h;
+  JLM_CUDA(cudaSetDevice(h->device));
+  JLM_CUDA(cudaStreamSynchronize(h->stream));
+  int p = 0;
+  while (b->order[p] != sentence) ++p;
+  const int T = b->sent_T[p];
+  const int W = b->W;
+  std::vector<int32_t> par(W);
+  std::vector<double> tmp((size_t)W * h->Hp);
+  for (int t = 0; t <= T; ++t) {
+    const int64_t fid = b->fbase[p] + t;
+    const int cnt = b->bc[fid];
+    const int64_t s0 = b->slot0[fid];
+    if (count) count[t] = cnt;
+    if (cnt == 0) continue;
+    const size_t o = (size_t)t * W;
+    if (score) JLM_CUDA(cudaMemcpy(score + o, b->d.slot_score + s0, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+    if (node) JLM_CUDA(cudaMemcpy(node + o, b->d.slot_node + s0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost));
+    if (lse) {
+      if (b->dynamic && b->use_lse && t < T) {
+        // report LSE over lattice_vocab[t+1], the first set the row is scored under
+        for (int k = 0; k < cnt; ++k)
+          JLM_CUDA(cudaMemcpy(lse + o + k, b->d.dyn_lse + (s0 + k) * (b->Tmax + 1) + t + 1, sizeof(double),
+                              cudaMemcpyDeviceToHost));
+      } else {
+        JLM_CUDA(cudaMemcpy(lse + o, b->d.slot_lse + s0, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+      }
+    }
+    if (parent_frame || parent_rank) {
+      JLM_CUDA(cudaMemcpy(par.data(), b->d.slot_parent + s0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost));
+      for (int k = 0; k < cnt; ++k) {
+        int pf = -1, pr = -1;
+        if (par[k] >= 0) {
+          for (int q = 0; q < t; ++q) {
+            const int64_t f2 = b->fbase[p] + q;
+            if (par[k] >= b->slot0[f2] && par[k] < b->slot0[f2] + b->bc[f2]) {
+              pf = q;
+              pr = (int)(par[k] - b->slot0[f2]);
+            }
+          }
+        }
+        if (parent_frame) parent_frame[o + k] = pf;
+        if (parent_rank) parent_rank[o + k] = pr;
+      }
+    }
+    if ((h_out || c_out) && t < T) {
+      if (b->backend == JLM_BACKEND_EXACT) {
+        if (h_out) {
+          JLM_CUDA(cudaMemcpy(tmp.data(), b->hx + s0 * h->Hp, sizeof(double) * cnt * h->Hp, cudaMemcpyDeviceToHost));
+          for (int k = 0; k < cnt; ++k) memcpy(h_out + (o + k) * h->H, &tmp[(size_t)k * h->Hp], sizeof(double) * h->H);
+        }
+        if (c_out) {
+          JLM_CUDA(cudaMemcpy(tmp.data(), b->cx + s0 * h->Hp, sizeof(double) * cnt * h->Hp, cudaMemcpyDeviceToHost));
+          for (int k = 0; k < cnt; ++k) memcpy(c_out + (o + k) * h->H, &tmp[(size_t)k * h->Hp], sizeof(double) * h->H);
+        }
+      } else {
+        JLM_TRY(tc_batch_get_state(b, s0, cnt, h_out ? h_out + o * h->H : nullptr, c_out ? c_out + o * h->H : nullptr));
+      }
+    }
+  }
+  return 0;
+}

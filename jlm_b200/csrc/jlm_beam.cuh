@@ -1,0 +1,102 @@
+// Batch decode engine: host-side plan + device beam state shared by both arithmetic back ends.
+#pragma once
+#include "jlm_common.cuh"
+
+struct StepPlan {
+  int64_t row0;      // first beam slot of this lock-step frame (slots are frame-major)
+  int rows_step;     // rows that take an LM step (sentences that continue past this frame)
+  int rows_all;      // all beam entries of the frame
+  int nact;          // sentences (sorted positions 0..nact) that have this frame
+  int nstep;         // sentences that continue (prefix of the active ones)
+  int64_t job0;      // first SubsetJob of the step (one per stepped sentence)
+  int max_node_cols; // largest number of nodes starting at this frame in one sentence
+  int max_vocab_cols;
+  int64_t yv_elems;  // elements of the per-step vocab-logit scratch
+};
+
+struct DynJobInfo {
+  int64_t vfp_off;   // into d_vfp (sentence's vocab_frame_ptr, T+2 entries)
+  int32_t nv, nd, T, pad;
+};
+
+struct BeamDev {
+  // plan (read-only on the device)
+  int32_t* node_word = nullptr;
+  int32_t* node_pfid = nullptr;     // frame id of the node's start frame, -1 for <eos>
+  int64_t* logit_off = nullptr;     // first node-logit slot of the node
+  int32_t* frame_lo = nullptr;      // per frame id: nodes ending here [lo, hi)
+  int32_t* frame_hi = nullptr;
+  int32_t* frame_minpf = nullptr;   // smallest parent frame id among them (dynamic chain sums)
+  int32_t* bc = nullptr;            // beam count per frame id
+  int64_t* slot0 = nullptr;         // first slot per frame id
+  int64_t* fbase = nullptr;         // first frame id per sorted sentence
+  int32_t* sent_T = nullptr;
+  int32_t* start_words = nullptr;   // words of nodes grouped by start frame
+  SubsetJob* node_jobs = nullptr;
+  SubsetJob* vocab_jobs = nullptr;
+  DynJobInfo* dyn_info = nullptr;
+  int32_t* vocab_cols = nullptr;
+  int32_t* vfp = nullptr;
+  // beam state
+  double* slot_score = nullptr;
+  double* slot_lse = nullptr;
+  double* slot_cumy = nullptr;      // dynamic: sum of the path's logits
+  double* dyn_lse = nullptr;        // dynamic: [slot, Tmax+1] LSE over lattice_vocab[i]
+  double* dyn_chain = nullptr;      // dynamic: per-slot chain sums for the frame being expanded
+  int32_t* slot_parent = nullptr;   // global slot of the parent, -1 for <eos>
+  int32_t* slot_node = nullptr;
+  int32_t* slot_word = nullptr;
+  double* node_logit = nullptr;
+  // n-best output
+  double* out_score = nullptr;
+  int32_t* out_npaths = nullptr;
+  int32_t* out_len = nullptr;
+  int32_t* out_nodes = nullptr;
+};
+
+struct TcBatchState;  // jlm_tc.cu
+
+struct jlm_batch {
+  jlm_handle* h = nullptr;
+  int S = 0, W = 0, topN = 0, mode = 0, backend = 0, Tmax = 0, n_steps = 0;
+  bool use_lse = true;
+  bool dynamic = false;
+  std::vector<int> order;        // sorted position -> caller's sentence index
+  std::vector<int> sent_T;       // by sorted position
+  std::vector<int64_t> fbase;
+  std::vector<int> bc;
+  std::vector<int64_t> slot0;
+  std::vector<StepPlan> steps;
+  int64_t F = 0, N = 0, n_slots = 0, n_cand = 0, n_jobs = 0;
+  int max_rows_step = 0;
+  int64_t max_yv = 0;
+  int max_len = 0;
+  DevBuf mem;
+  BeamDev d;
+  // exact back end state
+  double* hx = nullptr;          // [n_slots, Hp]
+  double* cx = nullptr;
+  double* A = nullptr;           // [max_rows_step, Kg]
+  double* G = nullptr;           // [max_rows_step, 4H]
+  double* T = nullptr;           // [max_rows_step, Kt]
+  double2* part = nullptr;
+  int part_tiles = 0;
+  double* yv = nullptr;          // vocab logits scratch
+  TcBatchState* tc = nullptr;
+  // bookkeeping
+  int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  bool timers = false;
+  bool ran = false;
+  std::vector<cudaEvent_t> events;
+  float ms_lstm = 0.f, ms_softmax = 0.f, ms_beam = 0.f;
+  std::vector<cudaEvent_t> kev;  // tensor-core back end: 4 per step around the gate / projection GEMMs
+  float ms_gate_gemm = 0.f, ms_proj_gemm = 0.f;
+  int n_gate_launches = 0, n_proj_launches = 0;
+};
+
+// tensor-core back end hooks (jlm_tc.cu)
+int32_t tc_batch_plan(jlm_batch* b, Arena& a);                 // called twice: dry run + real
+// gate GEMM .. full-vocabulary LSE for step t; returns the fp32 stage-1 rows for the needed-word dots
+int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out);
+int32_t tc_batch_get_state(jlm_batch* b, int64_t slot, int count, double* h_out, double* c_out);
+void tc_batch_free(jlm_batch* b);

@@ -1,0 +1,188 @@
+// Internal declarations shared by the translation units of libjlm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/jlm_b200.h"
+
+void jlm_set_error(const char* fmt, ...);
+
+#define JLM_CUDA(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e__ = (x);                                                                   \
+    if (e__ != cudaSuccess) {                                                                \
+      jlm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e__));      \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define JLM_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      jlm_set_error(__VA_ARGS__);   \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+#define JLM_TRY(x)            \
+  do {                        \
+    int32_t r__ = (x);        \
+    if (r__) return r__;      \
+  } while (0)
+
+static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+constexpr int JLM_KALIGN = 64;  // every GEMM K extent on the device is padded to this (zero filled)
+
+// Grow-only device / pinned-host buffers, reused across calls so the steady state allocates nothing.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int32_t reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    JLM_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int32_t reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    JLM_CUDA(cudaMallocHost(&p, want));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Bump allocator over one DevBuf: plan sizes first (dry run), reserve once, then hand out pointers.
+struct Arena {
+  DevBuf buf;
+  size_t off = 0;
+  bool dry = true;
+  void begin_plan() { off = 0; dry = true; }
+  int32_t commit() {
+    JLM_TRY(buf.reserve(off));
+    off = 0;
+    dry = false;
+    return 0;
+  }
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* r = dry ? nullptr : reinterpret_cast<T*>(static_cast<char*>(buf.p) + off);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+struct SegDev {
+  int width;   // e_i: K of the segment's output GEMM
+  int kpad;    // width rounded up to JLM_KALIGN
+  int koff;    // column offset of the segment's slice inside the stage-1 output T (padded layout)
+  int start, end;
+  const float* W;   // [end-start, kpad] K-major, zero padded (exact back end + needed-word dots)
+};
+
+struct TcWeights;  // tensor-core operand copies (jlm_tc.cu)
+
+struct jlm_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  jlm_config cfg{};
+  int V = 0, H = 0, E = 0;
+  int Hp = 0, Ep = 0;   // padded to JLM_KALIGN
+  int Kg = 0;           // gate GEMM K = Hp + Ep
+  int Kt = 0;           // stage-1 output width (sum of kpad); untied: Hp (T aliases h)
+  int n_seg = 0;
+  SegDev seg[JLM_MAX_SEGMENTS];
+  bool untied = false;
+  // device weights (exact layouts)
+  float* Wg = nullptr;      // [4H, Kg]  row n = gate*H + j ; k < Hp: HM, k >= Hp: IM
+  float* bg = nullptr;      // [4H]
+  float* b2 = nullptr;      // [V]
+  float* LM_in = nullptr;   // [V, Ep] zero padded
+  double* P1 = nullptr;     // [Kt, Hp] stage-1 weight, K-major, float64 (NULL when untied)
+  float* Wseg_store[JLM_MAX_SEGMENTS] = {};
+  TcWeights* tc = nullptr;
+  // scratch for the model-level API and the batch engine
+  DevBuf scratch[8];
+  DevBuf batch_cache;     // device memory of the last destroyed batch, reused by the next upload
+  HostBuf pinned[4];
+  cudaEvent_t ev[4] = {};
+};
+
+// ---------------------------------------------------------------- exact back end (jlm_exact.cu)
+// C[M,N] (+bias) = A[M,K] . B[N,K]^T, float64 accumulation.  K % 32 == 0, lda/ldb % 4 == 0.
+// part != nullptr: also emit per-(row, 64-column tile) (max, sum exp) partials, tile index offset
+// part_tile0, row stride part_ld (in tiles).  C may be nullptr when only partials are wanted.
+int32_t exact_gemm_f32w(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias,
+                        double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                        int part_tile0);
+int32_t exact_gemm_f64w(cudaStream_t st, const double* A, int lda, const double* B, int ldb,
+                        double* C, int64_t ldc, int M, int N, int K);
+int exact_tiles_n(int N);
+// lse[m] = log sum exp over the partial tiles of row m
+int32_t exact_lse_merge(cudaStream_t st, const double2* part, int part_ld, int n_tiles, int M, double* lse,
+                        int self_norm);
+// lse[m] = log sum exp of the dense row y[m, 0..N)
+int32_t exact_rows_lse(cudaStream_t st, const double* y, int64_t ld, int M, int N, double* lse);
+// pred = exp(y - lse[m]) (softmax) ; lse == nullptr -> exp(y)
+int32_t exact_softmax_rows(cudaStream_t st, const double* y, int64_t ld, int M, int N, const double* lse,
+                           double* pred);
+// A[m] = [ h_src[parent[m]] (Hp) | LM_in[word[m]] (Ep) ] as float64; parent < 0 -> zero state.
+int32_t exact_gather_gate_input(cudaStream_t st, const jlm_handle* h, const double* h_src, const int32_t* parent,
+                                const int32_t* word, int M, double* A);
+// gates -> (h,c): c' = c*f + g*i ; h' = tanh(c')*o.  c_src rows gathered through parent (<0 -> 0).
+int32_t exact_lstm_pointwise(cudaStream_t st, const jlm_handle* h, const double* gates, const double* c_src,
+                             const int32_t* parent, int M, double* h_out, double* c_out);
+
+// y[r, j] for selected words: out[job.out0 + j*job.rows + r] (col-major per job, "node logits")
+// or row-major [r, j] when row_major != 0.
+struct SubsetJob {
+  int64_t row0;      // first T row
+  int32_t rows;
+  int64_t col0;      // first entry of cols/bias_idx
+  int32_t ncols;
+  int64_t out0;
+};
+template <typename TT>
+int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t ldt, const SubsetJob* jobs,
+                      int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out,
+                      int row_major);
+
+// ---------------------------------------------------------------- tensor-core back end (jlm_tc.cu)
+int32_t tc_prepare_weights(jlm_handle* h);
+void tc_free_weights(jlm_handle* h);

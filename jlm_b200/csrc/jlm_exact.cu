@@ -1,0 +1,380 @@
+// Exact back end: CUDA-core kernels with float64 accumulation over float32 weights.
+//
+// The reference keeps hidden/cell/logits in float64 (decoder/model.py:44-45; np.dot(float64,float32)
+// promotes), so the few-rows-in-flight path (one sentence, <= beam rows) mirrors that arithmetic
+// here.  These kernels are weight-streaming (HBM/L2 bound): every weight element is read once per
+// LM step and used for all rows of the step.  Large lock-step batches use the tensor-core back end
+// (jlm_tc.cu); this one doubles as its on-device float64 cross-check.
+#include "jlm_common.cuh"
+
+namespace {
+
+constexpr int BN = 64;
+constexpr int BK = 32;
+
+template <typename TB, int TM>
+__global__ void __launch_bounds__(256)
+k_gemm_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
+           const float* __restrict__ bias, double* __restrict__ C, int64_t ldc, int M, int N, int K,
+           double2* __restrict__ part, int part_ld, int part_tile0) {
+  constexpr int BM = 16 * TM;
+  __shared__ double As[BM][BK + 2];
+  __shared__ TB Bs[BK][BN + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+
+  double acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // A tile: BM x BK doubles as double2
+    for (int idx = tid; idx < BM * BK / 2; idx += 256) {
+      int m = idx / (BK / 2), kq = idx % (BK / 2);
+      double2 v = make_double2(0.0, 0.0);
+      if (m0 + m < M) v = *reinterpret_cast<const double2*>(A + (int64_t)(m0 + m) * lda + k0 + kq * 2);
+      As[m][kq * 2] = v.x;
+      As[m][kq * 2 + 1] = v.y;
+    }
+    // B tile: BN x BK elements, transposed into Bs[k][n]
+    if (sizeof(TB) == 4) {
+      for (int idx = tid; idx < BN * BK / 4; idx += 256) {
+        int n = idx / (BK / 4), kq = idx % (BK / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + n < N)
+          v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(B) + (int64_t)(n0 + n) * ldb + k0 + kq * 4);
+        Bs[kq * 4 + 0][n] = (TB)v.x;
+        Bs[kq * 4 + 1][n] = (TB)v.y;
+        Bs[kq * 4 + 2][n] = (TB)v.z;
+        Bs[kq * 4 + 3][n] = (TB)v.w;
+      }
+    } else {
+      for (int idx = tid; idx < BN * BK / 2; idx += 256) {
+        int n = idx / (BK / 2), kq = idx % (BK / 2);
+        double2 v = make_double2(0.0, 0.0);
+        if (n0 + n < N)
+          v = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(B) + (int64_t)(n0 + n) * ldb + k0 + kq * 2);
+        Bs[kq * 2 + 0][n] = (TB)v.x;
+        Bs[kq * 2 + 1][n] = (TB)v.y;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < BK; ++k) {
+      double a[TM], b[4];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[ty * TM + i][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = (double)Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    double v[4];
+    double mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      v[j] = acc[i][j];
+      if (n < N) {
+        if (bias) v[j] += (double)bias[n];
+        if (C && m < M) C[(int64_t)m * ldc + n] = v[j];
+        mx = fmax(mx, v[j]);
+      } else {
+        v[j] = -INFINITY;
+      }
+    }
+    if (part) {
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += (v[j] == -INFINITY) ? 0.0 : exp(v[j] - mx);
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (tx == 0 && m < M) part[(int64_t)m * part_ld + part_tile0 + blockIdx.x] = make_double2(mx, s);
+    }
+  }
+}
+
+__global__ void k_lse_merge(const double2* __restrict__ part, int part_ld, int n_tiles, int M,
+                            double* __restrict__ lse, int self_norm) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  if (self_norm) {
+    if (lane == 0) lse[warp] = 0.0;
+    return;
+  }
+  const double2* p = part + (int64_t)warp * part_ld;
+  double mx = -INFINITY;
+  for (int t = lane; t < n_tiles; t += 32) mx = fmax(mx, p[t].x);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double s = 0.0;
+  for (int t = lane; t < n_tiles; t += 32) s += p[t].y * exp(p[t].x - mx);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) lse[warp] = mx + log(s);
+}
+
+__global__ void k_rows_lse(const double* __restrict__ y, int64_t ld, int M, int N, double* __restrict__ lse) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const double* p = y + (int64_t)warp * ld;
+  double mx = -INFINITY;
+  for (int t = lane; t < N; t += 32) mx = fmax(mx, p[t]);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double s = 0.0;
+  for (int t = lane; t < N; t += 32) s += exp(p[t] - mx);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) lse[warp] = mx + log(s);
+}
+
+__global__ void k_softmax_rows(const double* __restrict__ y, int64_t ld, int M, int N,
+                               const double* __restrict__ lse, double* __restrict__ pred) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N);
+    const int n = (int)(i % N);
+    const double v = y[(int64_t)m * ld + n];
+    pred[i] = lse ? exp(v - lse[m]) : exp(v);
+  }
+}
+
+__global__ void k_gather_gate_input(const double* __restrict__ h_src, const int32_t* __restrict__ parent,
+                                    const int32_t* __restrict__ word, const float* __restrict__ LM_in, int Hp,
+                                    int Ep, int M, double* __restrict__ A) {
+  const int Kg = Hp + Ep;
+  const int64_t total = (int64_t)M * Kg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / Kg);
+    const int k = (int)(i % Kg);
+    double v;
+    if (k < Hp) {
+      const int p = parent ? parent[m] : m;
+      v = (p >= 0) ? h_src[(int64_t)p * Hp + k] : 0.0;
+    } else {
+      v = (double)LM_in[(int64_t)word[m] * Ep + (k - Hp)];
+    }
+    A[i] = v;
+  }
+}
+
+// decoder/model.py:132-139: i,f,o = sigmoid ; g = tanh ; c = c*f + g*i ; h = tanh(c)*o
+__global__ void k_lstm_pointwise(const double* __restrict__ gates, const double* __restrict__ c_src,
+                                 const int32_t* __restrict__ parent, int H, int Hp, int M,
+                                 double* __restrict__ h_out, double* __restrict__ c_out) {
+  const int64_t total = (int64_t)M * Hp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / Hp);
+    const int j = (int)(idx % Hp);
+    if (j >= H) {
+      h_out[idx] = 0.0;
+      c_out[idx] = 0.0;
+      continue;
+    }
+    const double* g = gates + (int64_t)m * 4 * H;
+    const double gi = 1.0 / (exp(-g[j]) + 1.0);
+    const double gf = 1.0 / (exp(-g[H + j]) + 1.0);
+    const double go = 1.0 / (exp(-g[2 * H + j]) + 1.0);
+    const double gg = tanh(g[3 * H + j]);
+    const int p = parent ? parent[m] : m;
+    const double cp = (p >= 0) ? c_src[(int64_t)p * Hp + j] : 0.0;
+    const double c = cp * gf + gg * gi;
+    c_out[idx] = c;
+    h_out[idx] = tanh(c) * go;
+  }
+}
+
+struct SegTable {
+  int n;
+  int start[JLM_MAX_SEGMENTS], end[JLM_MAX_SEGMENTS], koff[JLM_MAX_SEGMENTS], kpad[JLM_MAX_SEGMENTS];
+  const float* W[JLM_MAX_SEGMENTS];
+};
+
+constexpr int SUB_RC = 8;        // rows accumulated per pass
+constexpr int SUB_WARPS = 8;     // warps per CTA, one column per warp per iteration
+
+template <typename TT>
+__global__ void __launch_bounds__(SUB_WARPS * 32)
+k_subset_logits(SegTable seg, const TT* __restrict__ T, int64_t ldt, const SubsetJob* __restrict__ jobs,
+                const int32_t* __restrict__ cols, const int32_t* __restrict__ bias_idx,
+                const float* __restrict__ b2, double* __restrict__ out, int row_major) {
+  const SubsetJob job = jobs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  for (int j = blockIdx.x * SUB_WARPS + warp; j < job.ncols; j += gridDim.x * SUB_WARPS) {
+    const int w = cols[job.col0 + j];
+    const int bw = bias_idx ? bias_idx[job.col0 + j] : w;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
+      if (i < seg.n && w >= seg.start[i]) s = i;
+    const int kpad = seg.kpad[s];
+    const float* wrow = seg.W[s] + (int64_t)(w - seg.start[s]) * kpad;
+    const double bias = (double)b2[bw];
+    for (int r0 = 0; r0 < job.rows; r0 += SUB_RC) {
+      double acc[SUB_RC];
+#pragma unroll
+      for (int r = 0; r < SUB_RC; ++r) acc[r] = 0.0;
+      for (int k = lane * 4; k < kpad; k += 128) {
+        const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+#pragma unroll
+        for (int r = 0; r < SUB_RC; ++r) {
+          if (r0 + r < job.rows) {
+            const TT* t = T + (job.row0 + r0 + r) * ldt + seg.koff[s] + k;
+            acc[r] = fma((double)t[0], (double)wv.x, acc[r]);
+            acc[r] = fma((double)t[1], (double)wv.y, acc[r]);
+            acc[r] = fma((double)t[2], (double)wv.z, acc[r]);
+            acc[r] = fma((double)t[3], (double)wv.w, acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < SUB_RC; ++r) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+#pragma unroll
+      for (int r = 0; r < SUB_RC; ++r) {
+        if (lane == r && r0 + r < job.rows) {
+          const int64_t o = row_major ? job.out0 + (int64_t)(r0 + r) * job.ncols + j
+                                      : job.out0 + (int64_t)j * job.rows + (r0 + r);
+          out[o] = acc[r] + bias;
+        }
+      }
+    }
+  }
+}
+
+SegTable make_seg_table(const jlm_handle* h) {
+  SegTable t{};
+  t.n = h->n_seg;
+  for (int i = 0; i < h->n_seg; ++i) {
+    t.start[i] = h->seg[i].start;
+    t.end[i] = h->seg[i].end;
+    t.koff[i] = h->seg[i].koff;
+    t.kpad[i] = h->seg[i].kpad;
+    t.W[i] = h->seg[i].W;
+  }
+  return t;
+}
+
+int grid_1d(int64_t total, int block, int cap) {
+  int64_t g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <typename TB>
+int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* bias, double* C,
+                    int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
+  JLM_REQUIRE(K % BK == 0 && lda % 2 == 0 && ldb % 4 == 0, "exact gemm: unaligned K=%d lda=%d ldb=%d", K, lda, ldb);
+  if (M <= 0 || N <= 0) return 0;
+  if (M <= 16) {
+    dim3 grid(ceil_div(N, BN), ceil_div(M, 16));
+    k_gemm_f64<TB, 1><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  } else if (M <= 32) {
+    dim3 grid(ceil_div(N, BN), ceil_div(M, 32));
+    k_gemm_f64<TB, 2><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  } else {
+    dim3 grid(ceil_div(N, BN), ceil_div(M, 64));
+    k_gemm_f64<TB, 4><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  }
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int exact_tiles_n(int N) { return ceil_div(N, BN); }
+
+int32_t exact_gemm_f32w(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias,
+                        double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                        int part_tile0) {
+  return launch_gemm<float>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+}
+
+int32_t exact_gemm_f64w(cudaStream_t st, const double* A, int lda, const double* B, int ldb, double* C,
+                        int64_t ldc, int M, int N, int K) {
+  return launch_gemm<double>(st, A, lda, B, ldb, nullptr, C, ldc, M, N, K, nullptr, 0, 0);
+}
+
+int32_t exact_lse_merge(cudaStream_t st, const double2* part, int part_ld, int n_tiles, int M, double* lse,
+                        int self_norm) {
+  if (M <= 0) return 0;
+  k_lse_merge<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(part, part_ld, n_tiles, M, lse, self_norm);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int32_t exact_rows_lse(cudaStream_t st, const double* y, int64_t ld, int M, int N, double* lse) {
+  if (M <= 0) return 0;
+  k_rows_lse<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(y, ld, M, N, lse);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int32_t exact_softmax_rows(cudaStream_t st, const double* y, int64_t ld, int M, int N, const double* lse,
+                           double* pred) {
+  if (M <= 0 || N <= 0) return 0;
+  k_softmax_rows<<<grid_1d((int64_t)M * N, 256, 148 * 16), 256, 0, st>>>(y, ld, M, N, lse, pred);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int32_t exact_gather_gate_input(cudaStream_t st, const jlm_handle* h, const double* h_src, const int32_t* parent,
+                                const int32_t* word, int M, double* A) {
+  if (M <= 0) return 0;
+  k_gather_gate_input<<<grid_1d((int64_t)M * h->Kg, 256, 148 * 16), 256, 0, st>>>(h_src, parent, word, h->LM_in,
+                                                                                 h->Hp, h->Ep, M, A);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int32_t exact_lstm_pointwise(cudaStream_t st, const jlm_handle* h, const double* gates, const double* c_src,
+                             const int32_t* parent, int M, double* h_out, double* c_out) {
+  if (M <= 0) return 0;
+  k_lstm_pointwise<<<grid_1d((int64_t)M * h->Hp, 256, 148 * 16), 256, 0, st>>>(gates, c_src, parent, h->H, h->Hp, M,
+                                                                              h_out, c_out);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename TT>
+int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t ldt, const SubsetJob* jobs,
+                      int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out,
+                      int row_major) {
+  if (n_jobs <= 0 || max_cols <= 0) return 0;
+  int gx = ceil_div(max_cols, SUB_WARPS);
+  if (gx > 64) gx = 64;
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    dim3 grid(gx, nj);
+    k_subset_logits<TT><<<grid, SUB_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, jobs + j0, cols, bias_idx, h->b2,
+                                                         out, row_major);
+  }
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template int32_t subset_logits<double>(cudaStream_t, const jlm_handle*, const double*, int64_t, const SubsetJob*, int,
+                                       int, const int32_t*, const int32_t*, double*, int);
+template int32_t subset_logits<float>(cudaStream_t, const jlm_handle*, const float*, int64_t, const SubsetJob*, int,
+                                      int, const int32_t*, const int32_t*, double*, int);

@@ -1,0 +1,792 @@
+// Tensor-core back end (sm_100a): TMA-fed tcgen05 GEMMs with fused epilogues.
+//
+// Precision.  The reference evaluates hidden -> logits in float64 over float32 weights, and beam
+// indices are only reproducible with ~fp32-accurate logits.  fp16 tensor-core
+// operands are therefore 2-term splits x*s = hi + lo (hi = fp16(x*s), lo = fp16(x*s - hi), s a power
+// of two that places the tensor's max near 2^15 so `lo` stays a normal fp16): 22 significant bits
+// per operand.  One product is three MMAs (hi.lo + lo.hi + hi.hi; lo.lo ~ 2^-22 is dropped) into
+// one fp32 TMEM accumulator, un-scaled in the epilogue.
+//
+// Kernel.  One persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected lane) + TMEM owner, warps 2-5 = epilogue (one TMEM lane quarter each).  128 x BN x 64
+// tiles, smem ring of {A_hi, A_lo, B_hi, B_lo} stages in SWIZZLE_128B layout, two TMEM accumulator
+// stages so the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogues:
+//   EPI_LSTM  : gate bias + sigmoid/tanh + cell update (decoder/model.py:132-139), writes h, c and
+//               the fp16 split of h for the next GEMM.
+//   EPI_STORE : un-scale (+bias), write fp32 and/or the fp16 split (stage-1 projection h.PM).
+//   EPI_LSE   : + b2, online per-row (max, sum exp) over the tile's columns -> partials
+//               (softmax, decoder/model.py:15-20, never materialising [B,V]).
+#include <cmath>
+
+#include "jlm_beam.cuh"
+#include "jlm_tc_ptx.cuh"
+
+struct TcOperand {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int64_t rows = 0, K = 0;
+  float scale = 1.f;
+  CUtensorMap map_hi, map_lo;
+};
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE = BM * BK * 2;  // bytes of one fp16 A tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum { EPI_LSE = 0, EPI_STORE = 1, EPI_LSTM = 2 };
+
+template <int BN>
+struct TileCfg {
+  static constexpr int B_TILE = BN * BK * 2;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * STAGE + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks;
+  float inv_scale;      // 1 / (scale_A * scale_B)
+  const float* bias;    // [N] (tile order) or nullptr
+  // EPI_LSE
+  float2* part;
+  int part_ld, part_tile0;
+  // EPI_STORE
+  float* C32;
+  int64_t ldc;
+  __half* s_hi;
+  __half* s_lo;
+  int64_t lds;
+  float split_scale;
+  // EPI_LSTM (row pointers already offset to the step's first row)
+  const float* c_src;
+  const int32_t* parent;
+  float* h_out;
+  float* c_out;
+  int64_t ld_state;
+};
+
+__device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* v, float scale) {
+  // 16 consecutive values -> two 32-byte runs (hi, lo)
+  uint32_t ph[8], pl[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = v[2 * j] * scale, b = v[2 * j + 1] * scale;
+    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+    ph[j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    pl[j] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+  }
+  uint4* dh = reinterpret_cast<uint4*>(hi);
+  uint4* dl = reinterpret_cast<uint4*>(lo);
+  dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+  dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+          const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const GemmArgs g) {
+  using C = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  float* bias_s = reinterpret_cast<float*>(gen + C::STAGES * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + C::STAGES * C::STAGE + C::BIAS_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + 2 + a); };
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&mAh);
+    ptx::prefetch_tensormap(&mAl);
+    ptx::prefetch_tensormap(&mBh);
+    ptx::prefetch_tensormap(&mBl);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < C::STAGES; ++s) {
+        ptx::mbar_init(full_bar(s), 1);
+        ptx::mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(tfull_bar(a), 1);
+        ptx::mbar_init(tempty_bar(a), 4);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
+  const int num_kb = g.K / BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), C::STAGE);
+          const uint32_t sa = base + stage * C::STAGE;
+          ptx::tma_load_2d(sa, &mAh, full_bar(stage), kb * BK, m_blk * BM);
+          ptx::tma_load_2d(sa + A_TILE, &mAl, full_bar(stage), kb * BK, m_blk * BM);
+          ptx::tma_load_2d(sa + 2 * A_TILE, &mBh, full_bar(stage), kb * BK, n_blk * BN);
+          ptx::tma_load_2d(sa + 2 * A_TILE + C::B_TILE, &mBl, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = base + stage * C::STAGE;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ah = ptx::umma_desc_sw128(sa + k * 32);
+            const uint64_t al = ptx::umma_desc_sw128(sa + A_TILE + k * 32);
+            const uint64_t bh = ptx::umma_desc_sw128(sa + 2 * A_TILE + k * 32);
+            const uint64_t bl = ptx::umma_desc_sw128(sa + 2 * A_TILE + C::B_TILE + k * 32);
+            ptx::mma_f16_ss(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss(d_tmem, al, bh, idesc, 1u);
+            ptx::mma_f16_ss(d_tmem, ah, bh, idesc, 1u);
+          }
+          ptx::tc_commit(empty_bar(stage));
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::tc_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    const int te = threadIdx.x - 64;      // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+      float* bs = bias_s + acc * BN;
+      for (int c = te; c < BN; c += 128) {
+        const int n = n_blk * BN + c;
+        float v = (EPI == EPI_LSE) ? -INFINITY : 0.f;
+        if (n < g.N) v = g.bias ? g.bias[n] : 0.f;
+        bs[c] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+
+      if (EPI == EPI_LSE) {
+        float m_run = -INFINITY, c_run = -INFINITY, s_run = 0.f;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          float v[32];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaf(__uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
+            cm = fmaxf(cm, v[j]);
+          }
+          if (cm > -INFINITY) {
+            const float m_new = fmaxf(m_run, cm);
+            const float c_new = m_new * LOG2E;
+            s_run *= exp2f(c_run - c_new);
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) part += exp2f(fmaf(v[j], LOG2E, -c_new));
+            s_run += part;
+            m_run = m_new;
+            c_run = c_new;
+          }
+        }
+        if (row_ok) g.part[(int64_t)row * g.part_ld + g.part_tile0 + n_blk] = make_float2(c_run, s_run);
+      } else if (EPI == EPI_STORE) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          const int n0 = n_blk * BN + c0;
+          if (row_ok && n0 < g.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
+            if (n0 + 32 <= g.N) {
+              if (g.C32) {
+                float4* dst = reinterpret_cast<float4*>(g.C32 + (int64_t)row * g.ldc + n0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+              if (g.s_hi) {
+                split_store16(g.s_hi + (int64_t)row * g.lds + n0, g.s_lo + (int64_t)row * g.lds + n0, v, g.split_scale);
+                split_store16(g.s_hi + (int64_t)row * g.lds + n0 + 16, g.s_lo + (int64_t)row * g.lds + n0 + 16, v + 16,
+                              g.split_scale);
+              }
+            } else if (g.C32) {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) g.C32[(int64_t)row * g.ldc + n0 + j] = v[j];
+            }
+          }
+        }
+      } else {
+        // EPI_LSTM: tile columns are [i | f | o | g] x (BN/4) units (weights permuted on the host)
+        constexpr int UPT = BN / 4;
+        for (int uc = 0; uc < UPT / 16; ++uc) {
+          uint32_t ri[16], rf[16], ro[16], rg[16];
+          ptx::tmem_ld_x16(taddr + uc * 16, ri);
+          ptx::tmem_ld_x16(taddr + UPT + uc * 16, rf);
+          ptx::tmem_ld_x16(taddr + 2 * UPT + uc * 16, ro);
+          ptx::tmem_ld_x16(taddr + 3 * UPT + uc * 16, rg);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            const int u0 = n_blk * UPT + uc * 16;
+            const int par = g.parent[row];
+            float cp[16];
+            if (par >= 0) {
+              const float4* src = reinterpret_cast<const float4*>(g.c_src + (int64_t)par * g.ld_state + u0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t = src[j];
+                cp[4 * j] = t.x;
+                cp[4 * j + 1] = t.y;
+                cp[4 * j + 2] = t.z;
+                cp[4 * j + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+            }
+            float hv[16], cv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float pi = fmaf(__uint_as_float(ri[j]), g.inv_scale, bs[uc * 16 + j]);
+              const float pf = fmaf(__uint_as_float(rf[j]), g.inv_scale, bs[UPT + uc * 16 + j]);
+              const float po = fmaf(__uint_as_float(ro[j]), g.inv_scale, bs[2 * UPT + uc * 16 + j]);
+              const float pg = fmaf(__uint_as_float(rg[j]), g.inv_scale, bs[3 * UPT + uc * 16 + j]);
+              const float gi = 1.f / (expf(-pi) + 1.f);
+              const float gf = 1.f / (expf(-pf) + 1.f);
+              const float go = 1.f / (expf(-po) + 1.f);
+              const float gg = tanhf(pg);
+              const float c = fmaf(cp[j], gf, gg * gi);
+              cv[j] = c;
+              hv[j] = tanhf(c) * go;
+            }
+            float4* dc = reinterpret_cast<float4*>(g.c_out + (int64_t)row * g.ld_state + u0);
+            float4* dh = reinterpret_cast<float4*>(g.h_out + (int64_t)row * g.ld_state + u0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dc[j] = make_float4(cv[4 * j], cv[4 * j + 1], cv[4 * j + 2], cv[4 * j + 3]);
+              dh[j] = make_float4(hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
+            }
+            split_store16(g.s_hi + (int64_t)row * g.lds + u0, g.s_lo + (int64_t)row * g.lds + u0, hv, g.split_scale);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// A = [ h[parent] | LM_in[word] ] * scale -> fp16 hi/lo, 8 elements per thread
+__global__ void k_tc_gather_split(const float* __restrict__ h_src, const int32_t* __restrict__ parent,
+                                  const int32_t* __restrict__ word, const float* __restrict__ LM_in, int Hp, int Ep,
+                                  int M, float scale, __half* __restrict__ A_hi, __half* __restrict__ A_lo) {
+  const int Kg = Hp + Ep;
+  const int64_t total = (int64_t)M * (Kg / 8);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (Kg / 8));
+    const int k = (int)(i % (Kg / 8)) * 8;
+    float v[8];
+    const float* src = nullptr;
+    if (k < Hp) {
+      const int p = parent[m];
+      if (p >= 0) src = h_src + (int64_t)p * Hp + k;
+    } else {
+      src = LM_in + (int64_t)word[m] * Ep + (k - Hp);
+    }
+    if (src) {
+      const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x = v[2 * j] * scale, y = v[2 * j + 1] * scale;
+      const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
+      const __half lx = __float2half_rn(x - __half2float(hx)), ly = __float2half_rn(y - __half2float(hy));
+      ph[j] = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
+      pl[j] = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
+    }
+    *reinterpret_cast<uint4*>(A_hi + (int64_t)m * Kg + k) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(A_lo + (int64_t)m * Kg + k) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// partial (c = max*log2e, s = sum 2^(v*log2e - c)) per 256-column tile -> natural-log LSE in float64
+__global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, int n_tiles, int M,
+                               double* __restrict__ lse) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float2* p = part + (int64_t)warp * part_ld;
+  float mx = -INFINITY;
+  for (int t = lane; t < n_tiles; t += 32) mx = fmaxf(mx, p[t].x);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double s = 0.0;
+  for (int t = lane; t < n_tiles; t += 32) {
+    const float2 v = p[t];
+    if (v.x > -INFINITY) s += (double)v.y * exp2((double)v.x - (double)mx);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) lse[warp] = 0.6931471805599453094 * ((double)mx + log2(s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp16 K-major operand [rows, K] with row pitch `pitch_elems`; box = 64 (K) x box_rows, SWIZZLE_128B
+int32_t make_map(CUtensorMap* m, const __half* base, int64_t K, int64_t rows, int64_t pitch_elems, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  JLM_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  JLM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) K=%lld rows=%lld pitch=%lld box_rows=%d", (int)r,
+              (long long)K, (long long)rows, (long long)pitch_elems, box_rows);
+  return 0;
+}
+
+float pow2_scale_for(double max_abs) {
+  if (!(max_abs > 0)) return 1.f;
+  int e = (int)std::floor(std::log2(32768.0 / max_abs));
+  if (e > 24) e = 24;
+  if (e < -24) e = -24;
+  return std::ldexp(1.f, e);
+}
+
+// split a host matrix (float64 values) [rows, K] into device fp16 hi/lo
+int32_t upload_split(TcOperand* op, const std::vector<double>& w, int64_t rows, int64_t K, int box_rows) {
+  double mx = 0;
+  for (double v : w) mx = std::max(mx, std::fabs(v));
+  op->scale = pow2_scale_for(mx);
+  op->rows = rows;
+  op->K = K;
+  std::vector<__half> hi(w.size()), lo(w.size());
+  for (size_t i = 0; i < w.size(); ++i) {
+    const double x = w[i] * (double)op->scale;
+    const __half a = __float2half_rn((float)x);
+    hi[i] = a;
+    lo[i] = __float2half_rn((float)(x - (double)__half2float(a)));
+  }
+  JLM_CUDA(cudaMalloc(&op->hi, w.size() * sizeof(__half)));
+  JLM_CUDA(cudaMalloc(&op->lo, w.size() * sizeof(__half)));
+  JLM_CUDA(cudaMemcpy(op->hi, hi.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  JLM_CUDA(cudaMemcpy(op->lo, lo.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  JLM_TRY(make_map(&op->map_hi, op->hi, K, rows, K, box_rows));
+  JLM_TRY(make_map(&op->map_lo, op->lo, K, rows, K, box_rows));
+  return 0;
+}
+
+void free_operand(TcOperand* op) {
+  cudaFree(op->hi);
+  cudaFree(op->lo);
+  op->hi = op->lo = nullptr;
+}
+
+template <int BN, int EPI>
+int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al, const CUtensorMap& Bh,
+                    const CUtensorMap& Bl, GemmArgs g) {
+  using C = TileCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  JLM_REQUIRE(g.K % BK == 0 && g.K > 0, "tc gemm: K=%d must be a positive multiple of %d", g.K, BK);
+  g.num_m_blocks = ceil_div(g.M, BM);
+  g.num_n_blocks = ceil_div(g.N, BN);
+  const int tiles = g.num_m_blocks * g.num_n_blocks;
+  if (tiles <= 0) return 0;
+  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  k_tc_gemm<BN, EPI><<<grid, 192, C::SMEM, h->stream>>>(Ah, Al, Bh, Bl, g);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle-level tensor-core weights
+// ------------------------------------------------------------------------------------------------
+struct TcWeights {
+  TcOperand Wg;                       // [4*Hp, Kg], tile-permuted rows
+  float* bg_perm = nullptr;           // [4*Hp]
+  TcOperand P1;                       // [Kt, Hp]
+  TcOperand seg[JLM_MAX_SEGMENTS];    // [V_i, kpad_i]
+  float sA = 1.f;                     // gate-input scale (h and embedding share it)
+  float sH = 16384.f;                 // |h| < 1
+  float sT = 1.f;                     // stage-1 output scale
+  int lse_tiles = 0;
+};
+
+constexpr int GATE_BN = 256;
+
+int32_t tc_prepare_weights(jlm_handle* h) {
+  if (h->tc) return 0;
+  JLM_CUDA(cudaSetDevice(h->device));
+  TcWeights* w = new TcWeights();
+  h->tc = w;
+  const int H = h->H, Hp = h->Hp, Kg = h->Kg, V = h->V;
+  const int UPT = GATE_BN / 4;
+  // pull the exact-layout weights back from the device (they are the single source of truth)
+  std::vector<float> Wg((size_t)4 * H * Kg), bg((size_t)4 * H), LM((size_t)V * h->Ep);
+  JLM_CUDA(cudaMemcpy(Wg.data(), h->Wg, Wg.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  JLM_CUDA(cudaMemcpy(bg.data(), h->bg, bg.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  JLM_CUDA(cudaMemcpy(LM.data(), h->LM_in, LM.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  {
+    std::vector<double> P((size_t)4 * Hp * Kg, 0.0);
+    std::vector<float> bp((size_t)4 * Hp, 0.f);
+    for (int gate = 0; gate < 4; ++gate)
+      for (int j = 0; j < H; ++j) {
+        const size_t dst = (size_t)(j / UPT) * GATE_BN + (size_t)gate * UPT + (j % UPT);
+        const float* src = &Wg[((size_t)gate * H + j) * Kg];
+        for (int k = 0; k < Kg; ++k) P[dst * Kg + k] = src[k];
+        bp[dst] = bg[(size_t)gate * H + j];
+      }
+    JLM_TRY(upload_split(&w->Wg, P, 4 * Hp, Kg, GATE_BN));
+    JLM_CUDA(cudaMalloc(&w->bg_perm, bp.size() * sizeof(float)));
+    JLM_CUDA(cudaMemcpy(w->bg_perm, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  {
+    double mx = 1.0;
+    for (float v : LM) mx = std::max(mx, (double)std::fabs(v));
+    w->sA = pow2_scale_for(mx);
+  }
+  if (!h->untied) {
+    std::vector<double> P1((size_t)h->Kt * Hp);
+    JLM_CUDA(cudaMemcpy(P1.data(), h->P1, P1.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    JLM_TRY(upload_split(&w->P1, P1, h->Kt, Hp, 256));
+    double bound = 0;
+    for (int n = 0; n < h->Kt; ++n) {
+      double s = 0;
+      for (int k = 0; k < Hp; ++k) s += std::fabs(P1[(size_t)n * Hp + k]);
+      bound = std::max(bound, s);
+    }
+    w->sT = pow2_scale_for(bound);
+  } else {
+    w->sT = w->sH;
+  }
+  w->lse_tiles = 0;
+  for (int i = 0; i < h->n_seg; ++i) {
+    const SegDev& s = h->seg[i];
+    const int64_t Vi = s.end - s.start;
+    std::vector<float> Wf((size_t)Vi * s.kpad);
+    JLM_CUDA(cudaMemcpy(Wf.data(), s.W, Wf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<double> Wd(Wf.begin(), Wf.end());
+    JLM_TRY(upload_split(&w->seg[i], Wd, Vi, s.kpad, 256));
+    w->lse_tiles += ceil_div(Vi, 256);
+  }
+  return 0;
+}
+
+void tc_free_weights(jlm_handle* h) {
+  if (!h->tc) return;
+  TcWeights* w = h->tc;
+  free_operand(&w->Wg);
+  free_operand(&w->P1);
+  for (auto& s : w->seg) free_operand(&s);
+  cudaFree(w->bg_perm);
+  delete w;
+  h->tc = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch-level state
+// ------------------------------------------------------------------------------------------------
+struct TcBatchState {
+  float* h32 = nullptr;   // [n_slots, Hp]
+  float* c32 = nullptr;
+  __half *Ag_hi = nullptr, *Ag_lo = nullptr;   // [Mpad, Kg]
+  __half *Hs_hi = nullptr, *Hs_lo = nullptr;   // [Mpad, Hp]
+  float* T32 = nullptr;                        // [Mpad, Kt]
+  __half *Ts_hi = nullptr, *Ts_lo = nullptr;   // [Mpad, Kt]
+  float2* part = nullptr;
+  int64_t Mpad = 0;
+  CUtensorMap mAg_hi, mAg_lo, mHs_hi, mHs_lo;
+  CUtensorMap mTs_hi[JLM_MAX_SEGMENTS], mTs_lo[JLM_MAX_SEGMENTS];
+};
+
+int32_t tc_batch_plan(jlm_batch* b, Arena& a) {
+  jlm_handle* h = b->h;
+  JLM_TRY(tc_prepare_weights(h));
+  if (!b->tc) b->tc = new TcBatchState();
+  TcBatchState* s = b->tc;
+  const size_t ns = (size_t)b->n_slots;
+  s->Mpad = round_up64(std::max(b->max_rows_step, 1), BM);
+  const size_t mp = (size_t)s->Mpad;
+  s->h32 = a.take<float>(ns * h->Hp);
+  s->c32 = a.take<float>(ns * h->Hp);
+  s->Ag_hi = a.take<__half>(mp * h->Kg);
+  s->Ag_lo = a.take<__half>(mp * h->Kg);
+  s->Hs_hi = a.take<__half>(mp * h->Hp);
+  s->Hs_lo = a.take<__half>(mp * h->Hp);
+  if (!h->untied) {
+    s->T32 = a.take<float>(mp * h->Kt);
+    s->Ts_hi = a.take<__half>(mp * h->Kt);
+    s->Ts_lo = a.take<__half>(mp * h->Kt);
+  } else {
+    s->T32 = nullptr;
+    s->Ts_hi = s->Hs_hi;
+    s->Ts_lo = s->Hs_lo;
+  }
+  s->part = (b->mode == JLM_DECODE_FULL && b->use_lse) ? a.take<float2>(mp * h->tc->lse_tiles) : nullptr;
+  if (a.dry) return 0;
+  JLM_TRY(make_map(&s->mAg_hi, s->Ag_hi, h->Kg, s->Mpad, h->Kg, BM));
+  JLM_TRY(make_map(&s->mAg_lo, s->Ag_lo, h->Kg, s->Mpad, h->Kg, BM));
+  JLM_TRY(make_map(&s->mHs_hi, s->Hs_hi, h->Hp, s->Mpad, h->Hp, BM));
+  JLM_TRY(make_map(&s->mHs_lo, s->Hs_lo, h->Hp, s->Mpad, h->Hp, BM));
+  const int64_t ldT = h->untied ? h->Hp : h->Kt;
+  for (int i = 0; i < h->n_seg; ++i) {
+    JLM_TRY(make_map(&s->mTs_hi[i], s->Ts_hi + h->seg[i].koff, h->seg[i].kpad, s->Mpad, ldT, BM));
+    JLM_TRY(make_map(&s->mTs_lo[i], s->Ts_lo + h->seg[i].koff, h->seg[i].kpad, s->Mpad, ldT, BM));
+  }
+  return 0;
+}
+
+void tc_batch_free(jlm_batch* b) {
+  delete b->tc;
+  b->tc = nullptr;
+}
+
+int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out) {
+  jlm_handle* h = b->h;
+  TcWeights* w = h->tc;
+  TcBatchState* s = b->tc;
+  cudaStream_t st = h->stream;
+  const StepPlan& sp = b->steps[t];
+  const int M = sp.rows_step;
+  *T_out = nullptr;
+  *ldt_out = 0;
+  if (M == 0) return 0;
+  const int32_t* parent = b->d.slot_parent + sp.row0;
+  const int32_t* word = b->d.slot_word + sp.row0;
+  float* hrow = s->h32 + sp.row0 * h->Hp;
+  float* crow = s->c32 + sp.row0 * h->Hp;
+  if (b->timers) cudaEventRecord(b->events[3 * t + 1], st);
+  {
+    const int64_t total = (int64_t)M * (h->Kg / 8);
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+    k_tc_gather_split<<<grid, 256, 0, st>>>(s->h32, parent, word, h->LM_in, h->Hp, h->Ep, M, w->sA, s->Ag_hi, s->Ag_lo);
+    JLM_CUDA(cudaGetLastError());
+  }
+  {
+    GemmArgs g{};
+    g.M = M;
+    g.N = 4 * h->Hp;
+    g.K = h->Kg;
+    g.inv_scale = 1.f / (w->sA * w->Wg.scale);
+    g.bias = w->bg_perm;
+    g.c_src = s->c32;
+    g.parent = parent;
+    g.h_out = hrow;
+    g.c_out = crow;
+    g.ld_state = h->Hp;
+    g.s_hi = s->Hs_hi;
+    g.s_lo = s->Hs_lo;
+    g.lds = h->Hp;
+    g.split_scale = w->sH;
+    if (b->timers) cudaEventRecord(b->kev[4 * t], st);
+    JLM_TRY((launch_gemm<GATE_BN, EPI_LSTM>(h, s->mAg_hi, s->mAg_lo, w->Wg.map_hi, w->Wg.map_lo, g)));
+    if (b->timers) cudaEventRecord(b->kev[4 * t + 1], st);
+  }
+  b->launches += 2;
+  if (b->timers) cudaEventRecord(b->events[3 * t + 2], st);
+  const float* T32 = hrow;
+  int ldt = h->Hp;
+  if (!h->untied) {
+    GemmArgs g{};
+    g.M = M;
+    g.N = h->Kt;
+    g.K = h->Hp;
+    g.inv_scale = 1.f / (w->sH * w->P1.scale);
+    g.C32 = s->T32;
+    g.ldc = h->Kt;
+    g.s_hi = s->Ts_hi;
+    g.s_lo = s->Ts_lo;
+    g.lds = h->Kt;
+    g.split_scale = w->sT;
+    JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1.map_hi, w->P1.map_lo, g)));
+    b->launches += 1;
+    T32 = s->T32;
+    ldt = h->Kt;
+  }
+  if (b->use_lse && b->mode == JLM_DECODE_FULL) {
+    int tile0 = 0;
+    if (b->timers) cudaEventRecord(b->kev[4 * t + 2], st);
+    for (int i = 0; i < h->n_seg; ++i) {
+      const SegDev& sg = h->seg[i];
+      GemmArgs g{};
+      g.M = M;
+      g.N = sg.end - sg.start;
+      g.K = sg.kpad;
+      g.inv_scale = 1.f / (w->sT * w->seg[i].scale);
+      g.bias = h->b2 + sg.start;
+      g.part = s->part;
+      g.part_ld = w->lse_tiles;
+      g.part_tile0 = tile0;
+      JLM_TRY((launch_gemm<256, EPI_LSE>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i].map_hi, w->seg[i].map_lo, g)));
+      tile0 += ceil_div(g.N, 256);
+      b->launches += 1;
+    }
+    if (b->timers) cudaEventRecord(b->kev[4 * t + 3], st);
+    k_tc_lse_merge<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(s->part, w->lse_tiles, w->lse_tiles, M,
+                                                                  b->d.slot_lse + sp.row0);
+    JLM_CUDA(cudaGetLastError());
+    b->launches += 1;
+  }
+  *T_out = T32;
+  *ldt_out = ldt;
+  return 0;
+}
+
+int32_t tc_batch_get_state(jlm_batch* b, int64_t slot, int count, double* h_out, double* c_out) {
+  jlm_handle* h = b->h;
+  std::vector<float> tmp((size_t)count * h->Hp);
+  for (int which = 0; which < 2; ++which) {
+    double* dst = which ? c_out : h_out;
+    if (!dst) continue;
+    const float* src = (which ? b->tc->c32 : b->tc->h32) + slot * h->Hp;
+    JLM_CUDA(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < count; ++k)
+      for (int j = 0; j < h->H; ++j) dst[(size_t)k * h->H + j] = (double)tmp[(size_t)k * h->Hp + j];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self test: C = A . B^T through the split-fp16 kernel (EPI_STORE)
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t jlm_tc_gemm_selftest(jlm_handle* h, const float* A, const float* B, int32_t M, int32_t N, int32_t K,
+                                        float* C, float* ms) {
+  JLM_REQUIRE(h && A && B && C && M > 0 && N > 0 && K > 0 && K % BK == 0, "jlm_tc_gemm_selftest: bad argument");
+  JLM_CUDA(cudaSetDevice(h->device));
+  TcOperand a, bop;
+  std::vector<double> Ad(A, A + (size_t)M * K), Bd(B, B + (size_t)N * K);
+  int32_t rc = upload_split(&a, Ad, M, K, BM);
+  if (!rc) rc = upload_split(&bop, Bd, N, K, 256);
+  float* dC = nullptr;
+  if (!rc && cudaMalloc(&dC, sizeof(float) * (size_t)M * N) != cudaSuccess) {
+    jlm_set_error("selftest: cudaMalloc failed");
+    rc = 1;
+  }
+  if (!rc) {
+    GemmArgs g{};
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.inv_scale = 1.f / (a.scale * bop.scale);
+    g.C32 = dC;
+    g.ldc = N;
+    cudaEventRecord(h->ev[0], h->stream);
+    rc = launch_gemm<256, EPI_STORE>(h, a.map_hi, a.map_lo, bop.map_hi, bop.map_lo, g);
+    cudaEventRecord(h->ev[1], h->stream);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      jlm_set_error("selftest: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+    if (!rc) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, h->ev[0], h->ev[1]);
+      if (ms) *ms = t;
+      if (cudaMemcpy(C, dC, sizeof(float) * (size_t)M * N, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        jlm_set_error("selftest: D2H failed");
+        rc = 1;
+      }
+    }
+  }
+  cudaFree(dC);
+  free_operand(&a);
+  free_operand(&bop);
+  return rc;
+}

@@ -1,0 +1,183 @@
+"""Decoder: drop-in for the reference's Viterbi / beam-search kana->kanji decoder
+(decoder/decoder.py:54-241), running on a B200 through libjlm_b200.so.
+
+decode() keeps the reference signature and return value; decode_batch() decodes many independent
+sentences in lock-step (the throughput path).  The lattice is built on the host exactly as the
+reference does (order matters: ties are broken by enumeration order), everything after that - LM
+steps, softmax statistics, expand/score/prune, back-trace - runs on the device.
+"""
+import ctypes as C
+import os
+import pickle
+
+import numpy as np
+
+from . import _lib, config, lattice
+from .model import LSTM_Model
+from .vocab import Vocab
+
+
+class Decoder(object):
+    dynamic = False
+
+    def __init__(self, experiment_id=0, comp=0, device=0):
+        # decoder/decoder.py:55-69
+        self.config = config.load_config(experiment_id)
+        self._load_vocab()
+        with open(os.path.join(config.root_path, 'data', 'lexicon.pkl'), 'rb') as f:
+            self.full_lexicon = pickle.load(f)
+        with open(os.path.join(config.root_path, 'data', 'reading_dict.pkl'), 'rb') as f:
+            self.full_reading_dict = pickle.load(f)
+        if self.config.get('char_rnn'):
+            raise NotImplementedError('char_rnn experiments use CharRNNDecoder in the reference; out of scope here')
+        self.model = LSTM_Model(experiment_id, comp, device=device)
+        self.lattice_vocab = None
+        self.backward_lookup = None
+        self.perf_sen = 0
+        self.perf_log_lstm = []
+        self.perf_log_softmax = []
+        self._builder = lattice.LatticeBuilder(self.w2i, self.full_lexicon, self.full_reading_dict)
+        self._lib = _lib.load()
+        self.last_info = None
+
+    def _load_vocab(self):
+        # decoder/decoder.py:71-74
+        self.vocab = Vocab(self.config['vocab_size'])
+        self.i2w = self.vocab.i2w
+        self.w2i = self.vocab.w2i
+
+    def _check_oov(self, word):
+        # decoder/decoder.py:76-77
+        return word not in self.w2i
+
+    def _build_lattice(self, input, vocab_select=False, samples=0, top_sampling=False, random_sampling=False):
+        """decoder/decoder.py:79-135; returns frames (list of node tuples) and sets lattice_vocab."""
+        frames = self._builder.build(input)
+        if vocab_select:
+            self._build_lattice_vocab(frames, samples, top_sampling, random_sampling)
+        return frames
+
+    def _build_lattice_vocab(self, frames, samples=0, top_sampling=False, random_sampling=False):
+        # decoder/decoder.py:137-151
+        self.lattice_vocab = lattice.static_vocab(frames, len(self.w2i), samples, top_sampling, random_sampling)
+
+    # ------------------------------------------------------------------------------------------
+    def _pack(self, all_frames, vocab_state):
+        """vocab_state: per sentence None / list (static) -> PackedLattices + decode mode."""
+        if vocab_state[0] is None:
+            return lattice.PackedLattices(all_frames), _lib.DECODE_FULL
+        for frames, lv in zip(all_frames, vocab_state):
+            have = set(lv)
+            for fr in frames:
+                for n in fr:
+                    if n[1] not in have:
+                        # the reference fails in list.index (decoder.py:179-180, quirk 6)
+                        raise ValueError('{} is not in list'.format(n[1]))
+        return lattice.PackedLattices(all_frames, vocab_lists=vocab_state), _lib.DECODE_STATIC_VOCAB
+
+    def _run(self, packed, mode, topN, beam_width, backend, timers):
+        lib, h = self._lib, self.model._handle
+        if beam_width is None:
+            beam_width = _lib.MAX_BEAM       # decoder.py:226: no pruning; bounded by the engine's list size
+        top = max(1, min(int(topN), int(beam_width)))
+        lb = packed.c_struct()
+        batch = C.c_void_p()
+        _lib.check(lib.jlm_batch_upload(h, C.byref(lb), int(beam_width), top, mode, backend, C.byref(batch)))
+        try:
+            if timers:
+                _lib.check(lib.jlm_batch_enable_timers(batch, 1))
+            _lib.check(lib.jlm_batch_run(batch))
+            S = packed.n_sent
+            max_len = int(packed.sent_len.max()) + 1
+            scores = np.empty((S, top))
+            n_paths = np.empty(S, dtype=np.int32)
+            path_len = np.empty((S, top), dtype=np.int32)
+            path_nodes = np.zeros((S, top, max_len), dtype=np.int32)
+            nb = _lib.NBest()
+            nb.top_n, nb.max_len = top, max_len
+            nb.scores = _lib.ptr(scores, C.c_double)
+            nb.n_paths = _lib.ptr(n_paths, C.c_int32)
+            nb.path_len = _lib.ptr(path_len, C.c_int32)
+            nb.path_nodes = _lib.ptr(path_nodes, C.c_int32)
+            _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
+            info = _lib.BatchInfo()
+            _lib.check(lib.jlm_batch_get_info(batch, C.byref(info)))
+            self.last_info = info
+            self._last_batch_trace = None
+            if getattr(self, '_want_trace', False):
+                self._last_batch_trace = self._collect_trace(batch, packed, int(beam_width))
+        finally:
+            lib.jlm_batch_destroy(batch)
+        out = []
+        for s in range(S):
+            words = packed.node_words(s)
+            off = int(packed.node_off[s])
+            res = []
+            for k in range(int(n_paths[s])):
+                ids = path_nodes[s, k, :path_len[s, k]]
+                ws = [words[i - off] for i in ids]
+                res.append((float(scores[s, k]), [w for w in ws if w != '<eos>']))   # decoder.py:237
+            out.append(res[:topN])
+        return out
+
+    def _collect_trace(self, batch, packed, W):
+        """Per-frame pruned beams of every sentence (test / debugging aid)."""
+        lib = self._lib
+        H = self.model.hidden_size
+        traces = []
+        for s in range(packed.n_sent):
+            T = int(packed.sent_len[s])
+            n = (T + 1) * W
+            count = np.zeros(T + 1, dtype=np.int32)
+            score = np.zeros(n)
+            pf = np.zeros(n, dtype=np.int32)
+            pr = np.zeros(n, dtype=np.int32)
+            node = np.zeros(n, dtype=np.int32)
+            lse = np.zeros(n)
+            hh = np.zeros((n, H))
+            cc = np.zeros((n, H))
+            d = C.c_double
+            _lib.check(lib.jlm_batch_get_beams(batch, s, _lib.ptr(count, C.c_int32), _lib.ptr(score, d),
+                                               _lib.ptr(pf, C.c_int32), _lib.ptr(pr, C.c_int32),
+                                               _lib.ptr(node, C.c_int32), _lib.ptr(lse, d), _lib.ptr(hh, d),
+                                               _lib.ptr(cc, d)))
+            off = int(packed.node_off[s])
+            frames = []
+            for t in range(T + 1):
+                sl = slice(t * W, t * W + int(count[t]))
+                frames.append({'score': score[sl].copy(), 'parent_frame': pf[sl].copy(), 'parent_rank': pr[sl].copy(),
+                               'node': node[sl] - off, 'lse': lse[sl].copy(), 'h': hh[sl].copy(), 'c': cc[sl].copy()})
+            traces.append(frames)
+        return traces
+
+    # ------------------------------------------------------------------------------------------
+    def decode(self, input, topN=10, beam_width=10, vocab_select=False, samples=0, top_sampling=False,
+               random_sampling=False, backend=_lib.BACKEND_AUTO):
+        """decoder/decoder.py:220-241 -> [(neg_log_prob, [word, ...])][:topN]."""
+        frames = self._build_lattice(input, vocab_select=vocab_select, samples=samples, top_sampling=top_sampling,
+                                     random_sampling=random_sampling)
+        self.backward_lookup = lattice.to_backward_lookup(frames)
+        # a vocabulary selected by an earlier call keeps being used (decoder.py:66,179; quirk 6)
+        lv = self.lattice_vocab if self.lattice_vocab else None
+        packed, mode = self._pack([frames], [lv])
+        out = self._run(packed, mode, topN, beam_width, backend, timers=True)[0]
+        info = self.last_info
+        steps = max(int(info.n_steps), 1)
+        self.perf_log_lstm += [info.ms_lstm * 1e-3 / steps] * steps          # decoder.py:211-212
+        self.perf_log_softmax += [info.ms_softmax * 1e-3 / steps] * steps
+        self.perf_sen += 1
+        return out
+
+    def decode_batch(self, inputs, topN=10, beam_width=10, vocab_select=False, samples=0, top_sampling=False,
+                     random_sampling=False, backend=_lib.BACKEND_AUTO):
+        """decode() for many independent sentences decoded in lock-step; returns one n-best list per input."""
+        all_frames, vocabs = [], []
+        for text in inputs:
+            frames = self._build_lattice(text, vocab_select=vocab_select, samples=samples,
+                                         top_sampling=top_sampling, random_sampling=random_sampling)
+            all_frames.append(frames)
+            vocabs.append(list(self.lattice_vocab) if self.lattice_vocab else None)
+        packed, mode = self._pack(all_frames, vocabs)
+        out = self._run(packed, mode, topN, beam_width, backend, timers=False)
+        self.perf_sen += len(inputs)
+        return out

@@ -1,0 +1,221 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(a) the reference-generated golden fixtures and (b) the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): beam back-pointers / word indices bit-exact; logits within 1e-3
+(absolute, fp32).  The exact back end (float64 accumulation) is held to 1e-6 on scores; the
+tensor-core back end (split-fp16 tcgen05, fp32 state) to 1e-3, with identical beams.
+"""
+import numpy as np
+import pytest
+
+from tests.golden.cases import CASES
+from tests.helpers import build_case, load_golden, norm_paths, write_case
+
+pytestmark = pytest.mark.gpu
+
+EXACT, TC = 1, 2
+TOL = {EXACT: 2e-6, TC: 1e-3}
+
+STATIC_SMALL = ['small_tied', 'small_untied', 'small_dsoftmax', 'small_dsoftmax_star', 'small_tied_selfnorm',
+                'small_tied_beam50', 'small_tied_vs', 'small_tied_vs_top', 'small_tied_vs_rand',
+                'small_dsoftmax_star_vs', 'small_dsoftmax_vs']
+DYN_SMALL = ['small_tied_dyn', 'small_tied_dyn_top', 'small_tied_dyn_rand', 'small_tied_selfnorm_dyn']
+MODEL_CASES = ['small_tied', 'small_untied', 'small_dsoftmax', 'small_dsoftmax_star', 'small_tied_selfnorm',
+               'cfg2_tied', 'cfg3_dsoftmax_star']
+
+_decoders = {}
+
+
+def get_decoder(name, tmp_path_factory):
+    """One experiment directory + decoder per golden case, cached for the session."""
+    import jlm_b200
+    from jlm_b200 import config
+    if name not in _decoders:
+        root = tmp_path_factory.mktemp('exp_' + name)
+        case, sentences = write_case(str(root), name)
+        config.set_root(str(root))
+        cls = jlm_b200.DynamicDecoder if case.get('dynamic') else jlm_b200.Decoder
+        dec = cls(1)
+        dec._want_trace = True
+        _decoders[name] = (dec, case, sentences)
+    return _decoders[name]
+
+
+def device_paths(trace_frames, flat_nodes):
+    """Rebuild every kept path's node sequence [(start, word), ...] from the device back-pointers."""
+    paths = []
+    for t, fr in enumerate(trace_frames):
+        cur = []
+        for k in range(len(fr['score'])):
+            n = flat_nodes[int(fr['node'][k])]
+            if fr['parent_frame'][k] < 0:
+                seq = [(n[0], n[1])]
+            else:
+                seq = paths[int(fr['parent_frame'][k])][int(fr['parent_rank'][k])][1] + [(n[0], n[1])]
+            cur.append((float(fr['score'][k]), seq))
+        paths.append(cur)
+    return paths
+
+
+def check_decode(name, backend, tmp_path_factory):
+    dec, case, sentences = get_decoder(name, tmp_path_factory)
+    meta, arr = load_golden(name)
+    tol = TOL[backend]
+    dyn = case.get('dynamic', False)
+    hs = meta['h_stride']
+    for si, sent in enumerate(sentences):
+        g = meta['decode'][si]
+        if case['decode_kwargs'].get('random_sampling'):
+            np.random.seed(1234 + si)
+        res = dec.decode(sent, backend=backend, **case['decode_kwargs'])
+        assert dec.last_info.backend == backend
+        assert dec.last_info.kernel_launches > 0
+        # n-best list: identical word sequences, scores within tolerance
+        assert [ws for _, ws in res] == [ws for _, ws in g['nbest']], (name, si)
+        np.testing.assert_allclose([s for s, _ in res], [s for s, _ in g['nbest']], rtol=0, atol=tol)
+        # every frame: same kept paths in the same rank order (back-pointers bit-exact)
+        frames = dec._builder.build(sent)
+        flat = [n for fr in frames for n in fr]
+        dp = device_paths(dec._last_batch_trace[0], flat)
+        gold_frames = g['dyn_frames'] if dyn else [s['paths'] for s in g['steps']]
+        assert len(dp) == len(gold_frames)
+        for t, (a, b) in enumerate(zip(dp, gold_frames)):
+            b = norm_paths(b)
+            assert [p[1] for p in a] == [p[1] for p in b], (name, si, t)
+            np.testing.assert_allclose([p[0] for p in a], [p[0] for p in b], rtol=0, atol=tol)
+        # LM state and softmax statistics of every stepped frame
+        T = len(sent)
+        for t in range(T):
+            key = 's%d_f%d' % (si, t)
+            fr = dec._last_batch_trace[0][t]
+            np.testing.assert_allclose(fr['h'].sum(axis=1), arr[key + '_hsum'], rtol=0, atol=50 * tol)
+            if key + '_h' in arr:
+                np.testing.assert_allclose(fr['h'][:, ::hs], arr[key + '_h'], rtol=0, atol=tol)
+                np.testing.assert_allclose(fr['c'][:, ::hs], arr[key + '_c'], rtol=0, atol=tol)
+            if not case.get('self_norm') and not dyn:
+                np.testing.assert_allclose(fr['lse'], arr[key + '_lse'], rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize('name', STATIC_SMALL)
+def test_decode_exact_static(name, tmp_path_factory):
+    check_decode(name, EXACT, tmp_path_factory)
+
+
+@pytest.mark.parametrize('name', DYN_SMALL)
+def test_decode_exact_dynamic(name, tmp_path_factory):
+    check_decode(name, EXACT, tmp_path_factory)
+
+
+@pytest.mark.parametrize('name', ['cfg2_tied', 'cfg3_dsoftmax_star', 'cfg4_tied_dyn'])
+def test_decode_exact_full_size(name, tmp_path_factory):
+    check_decode(name, EXACT, tmp_path_factory)
+
+
+@pytest.mark.parametrize('name', MODEL_CASES)
+def test_model_api_matches_reference(name, tmp_path_factory):
+    """LSTM_Model.predict_with_context / project through jlm_predict / jlm_project."""
+    dec, case, _ = get_decoder(name, tmp_path_factory)
+    meta, arr = load_golden(name)
+    m = dec.model
+    ys = meta['y_stride']
+    probe = case['model_probe']
+    B = len(probe['index'][0])
+    h = np.zeros((B, m.hidden_size))
+    c = np.zeros((B, m.hidden_size))
+    for step, idx in enumerate(probe['index']):
+        (pred, y, t1, t2), h, c = m.predict_with_context(idx, h, c, None)
+        assert pred.dtype == np.float64 and pred.shape == (B, case['vocab_size'])
+        assert t1 > 0 and t2 > 0
+        np.testing.assert_allclose(y[:, ::ys], arr['m_step%d_y' % step], rtol=0, atol=1e-5)   # logits: bar is 1e-3
+        np.testing.assert_allclose(pred[:, ::ys], arr['m_step%d_pred' % step], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(h, arr['m_step%d_h' % step], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(c, arr['m_step%d_c' % step], rtol=0, atol=1e-6)
+        if not case.get('self_norm'):
+            np.testing.assert_allclose(pred.sum(axis=1), 1.0, rtol=0, atol=1e-9)
+    if probe.get('vocab') is not None:
+        if meta['model'] == ['vocab_ok']:
+            yv = m.project(h, probe['vocab'])
+            np.testing.assert_allclose(yv, arr['m_project_vocab_y'], rtol=0, atol=1e-5)
+            (pv, yv2, _, _), _, _ = m.predict_with_context(probe['index'][-1], h, c, probe['vocab'])
+            np.testing.assert_allclose(pv, arr['m_predict_vocab_pred'], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(yv2, arr['m_predict_vocab_y'], rtol=0, atol=1e-5)
+        else:
+            with pytest.raises((IndexError, ValueError)):      # quirk 2 (model.py:189)
+                m.project(h, probe['vocab'])
+
+
+def test_decode_batch_equals_single(tmp_path_factory):
+    dec, case, sentences = get_decoder('small_tied', tmp_path_factory)
+    single = [dec.decode(s, backend=EXACT, **case['decode_kwargs']) for s in sentences]
+    batch = dec.decode_batch(sentences, backend=EXACT, **case['decode_kwargs'])
+    assert len(batch) == len(single)
+    for a, b in zip(batch, single):
+        assert [w for _, w in a] == [w for _, w in b]
+        np.testing.assert_allclose([s for s, _ in a], [s for s, _ in b], rtol=0, atol=1e-12)
+
+
+def test_ragged_and_degenerate_inputs(tmp_path_factory):
+    dec, case, sentences = get_decoder('small_tied', tmp_path_factory)
+    texts = [sentences[0][:1], sentences[1], sentences[2][:5], sentences[0][:1]]
+    out = dec.decode_batch(texts, topN=3, beam_width=4, backend=EXACT)
+    assert [len(o) <= 3 for o in out] == [True] * 4
+    assert out[0] == out[3]
+    one = dec.decode(texts[2], topN=3, beam_width=4, backend=EXACT)
+    assert [w for _, w in one] == [w for _, w in out[2]]
+    # beam_width=1 is greedy Viterbi; scores ascending
+    g = dec.decode(sentences[1], topN=5, beam_width=1, backend=EXACT)
+    assert len(g) == 1
+    many = dec.decode(sentences[1], topN=10, beam_width=7, backend=EXACT)
+    assert [s for s, _ in many] == sorted(s for s, _ in many)
+
+
+def test_tc_gemm_selftest_accuracy(tmp_path_factory):
+    """split-fp16 tcgen05 GEMM vs float64: C = A.B^T, ragged M and N."""
+    import ctypes as C
+    from jlm_b200 import _lib
+    dec, _, _ = get_decoder('small_tied', tmp_path_factory)
+    rng = np.random.default_rng(0)
+    for (M, N, K) in [(300, 1000, 256), (128, 256, 64), (1000, 777, 768)]:
+        A = rng.normal(0, 1, size=(M, K)).astype(np.float32)
+        B = rng.normal(0, 0.5, size=(N, K)).astype(np.float32)
+        out = np.zeros((M, N), dtype=np.float32)
+        ms = C.c_float(0)
+        _lib.check(dec._lib.jlm_tc_gemm_selftest(dec.model._handle, _lib.ptr(A, C.c_float), _lib.ptr(B, C.c_float),
+                                                 M, N, K, _lib.ptr(out, C.c_float), C.byref(ms)))
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        err = np.abs(out - ref).max()
+        scale = np.abs(ref).max()
+        print('tc gemm %dx%dx%d: max abs err %.3e (max |C| %.2f, rel %.2e), %.3f ms' % (M, N, K, err, scale, err / scale, ms.value))
+        assert err / scale < 2e-6, (M, N, K, err, scale)
+
+
+@pytest.mark.parametrize('name', ['small_tied', 'small_untied', 'small_dsoftmax', 'small_dsoftmax_star',
+                                  'small_tied_selfnorm', 'small_tied_beam50', 'small_tied_vs', 'small_tied_dyn_top'])
+def test_decode_tc_small(name, tmp_path_factory):
+    check_decode(name, TC, tmp_path_factory)
+
+
+@pytest.mark.parametrize('name', ['cfg2_tied', 'cfg3_dsoftmax_star', 'cfg4_tied_dyn'])
+def test_decode_tc_full_size(name, tmp_path_factory):
+    check_decode(name, TC, tmp_path_factory)
+
+
+def test_tc_matches_exact_on_a_lockstep_batch(tmp_path_factory):
+    """configs[1] shape, 64 sentences decoded in lock-step: tensor-core beams == float64 beams."""
+    from jlm_b200 import synth
+    dec, case, _ = get_decoder('cfg2_tied', tmp_path_factory)
+    _, _, _, lexicon, _, _ = build_case('cfg2_tied')
+    sents = synth.make_sentences(lexicon, 64, min_len=20, seed=77, vocab_size=case['vocab_size'])
+    dec._want_trace = False
+    try:
+        a = dec.decode_batch(sents, topN=10, beam_width=10, backend=EXACT)
+        b = dec.decode_batch(sents, topN=10, beam_width=10, backend=TC)
+    finally:
+        dec._want_trace = True
+    same = sum([w for _, w in x] == [w for _, w in y] for x, y in zip(a, b))
+    top1 = sum(x[0][1] == y[0][1] for x, y in zip(a, b))
+    worst = max(abs(p[0] - q[0]) for x, y in zip(a, b) for p, q in zip(x, y))
+    print('lock-step 64: identical n-best %d/64, identical top-1 %d/64, worst score diff %.3e' % (same, top1, worst))
+    assert top1 == 64
+    assert same == 64
+    assert worst < 1e-3

@@ -1,0 +1,149 @@
+"""CPU-side checks (no GPU): host lattice / vocabulary logic against the reference-generated golden
+fixtures, the packed CSR layout, and that the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from jlm_b200 import _lib, lattice
+from jlm_b200.vocab import Vocab
+from oracle import jlm_oracle as O
+from tests.golden.cases import CASES
+from tests.helpers import build_case, load_golden
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('name', ['small_tied', 'small_tied_beam50', 'cfg2_tied'])
+def test_lattice_matches_reference(name):
+    case, cfg, weights, lexicon, reading_dict, sentences = build_case(name)
+    meta, _ = load_golden(name)
+    vocab = Vocab(cfg['vocab_size'], lexicon=lexicon)
+    builder = lattice.LatticeBuilder(vocab.w2i, lexicon, reading_dict)
+    for si, sent in enumerate(sentences):
+        frames = builder.build(sent)
+        g = meta['decode'][si]['lattice']
+        assert len(frames) == len(sent) + 1
+        for t, fr in enumerate(frames):
+            assert [[n[0], n[1], n[2]] for n in fr] == g[str(t)], (name, si, t)
+        # and against the oracle's independent restatement
+        w2i, _ = O.make_vocab(lexicon, cfg['vocab_size'])
+        assert frames == O.build_lattice(sent, w2i, lexicon, reading_dict)
+
+
+def test_lattice_unk_fallback_and_oov_skip():
+    # 3 in-vocab words + one OOV word (beyond vocab_size); kana 'ウ' has no reading at all
+    lexicon = [('<eos>', 100), ('a/ア/P', 50), ('b/アイ/P', 40), ('c/イ/P', 30), ('oov/ア/P', 1)]
+    reading = {'ア': [1, 4], 'アイ': [2], 'イ': [3]}
+    vocab = Vocab(5, lexicon=lexicon)          # <unk>, <eos>, a, b, c  -> 'oov' is out of vocabulary
+    frames = lattice.LatticeBuilder(vocab.w2i, lexicon, reading).build('アイウ')
+    assert frames[0] == [(-1, 1, '<eos>')]
+    assert frames[1] == [(0, 2, 'a/ア/P')]
+    assert frames[2] == [(0, 3, 'b/アイ/P'), (1, 4, 'c/イ/P')]
+    assert frames[3] == [(2, 0, 'ウ')]          # <unk> node carries the raw kana (quirk 8)
+    bl = lattice.to_backward_lookup(frames)
+    assert bl[2][0].start_idx == 0 and bl[2][0].reading_length == 2 and bl[0][0].reading_length == 1
+
+
+@pytest.mark.parametrize('name', ['small_tied_vs', 'small_tied_vs_top', 'small_tied_vs_rand'])
+def test_static_vocab_matches_reference(name):
+    case, cfg, weights, lexicon, reading_dict, sentences = build_case(name)
+    meta, _ = load_golden(name)
+    vocab = Vocab(cfg['vocab_size'], lexicon=lexicon)
+    builder = lattice.LatticeBuilder(vocab.w2i, lexicon, reading_dict)
+    kw = case['decode_kwargs']
+    for si, sent in enumerate(sentences):
+        if kw.get('random_sampling'):
+            np.random.seed(1234 + si)
+        lv = lattice.static_vocab(builder.build(sent), len(vocab.w2i), kw.get('samples', 0),
+                                  kw.get('top_sampling', False), kw.get('random_sampling', False))
+        # the fixture stores the list as left after the LAST sentence only
+        if si == len(sentences) - 1:
+            assert lv == meta['decode'][si]['lattice_vocab']
+        assert lv == sorted(set(lv))
+
+
+@pytest.mark.parametrize('name', ['small_tied_dyn', 'small_tied_dyn_top', 'small_tied_dyn_rand'])
+def test_dynamic_vocab_matches_reference(name):
+    case, cfg, weights, lexicon, reading_dict, sentences = build_case(name)
+    meta, _ = load_golden(name)
+    vocab = Vocab(cfg['vocab_size'], lexicon=lexicon)
+    builder = lattice.LatticeBuilder(vocab.w2i, lexicon, reading_dict)
+    kw = case['decode_kwargs']
+    for si, sent in enumerate(sentences):
+        if kw.get('random_sampling'):
+            np.random.seed(1234 + si)
+        frames = builder.build(sent)
+        lv0, news = lattice.dynamic_vocab(frames, len(vocab.w2i), kw.get('samples', 0),
+                                          kw.get('top_sampling', False), kw.get('random_sampling', False))
+        final = lattice.dynamic_vocab_final(lv0, news)
+        assert {str(k): v for k, v in final.items()} == meta['decode'][si]['lattice_vocab']
+        packed = lattice.PackedLattices([frames], dynamic=[(lv0, news)])
+        # columns ordered by first appearance; lattice_vocab[i] == set(cols[:vfp[i+1]])
+        cum = set(lv0)
+        for i in range(len(frames)):
+            if i:
+                cum |= set(news[i])
+            assert set(packed.vocab_ids[:packed.vocab_frame_ptr[i + 1]].tolist()) == cum
+        ndup = len(lv0) - len(set(lv0))
+        assert int(packed.dup_ptr[1]) == ndup
+
+
+def test_packed_lattice_csr_layout():
+    f0 = [[(-1, 1, '<eos>')], [(0, 5, 'x')], [(0, 6, 'y'), (1, 7, 'z')]]
+    f1 = [[(-1, 1, '<eos>')], [(0, 9, 'q')]]
+    p = lattice.PackedLattices([f0, f1])
+    assert p.sent_len.tolist() == [2, 1]
+    assert p.frame_ptr_off.tolist() == [0, 4]
+    assert p.frame_ptr.tolist() == [0, 1, 2, 4, 4, 5, 6]
+    assert p.node_start.tolist() == [-1, 0, 0, 1, -1, 0]
+    assert p.node_word.tolist() == [1, 5, 6, 7, 1, 9]
+    assert p.node_words(1) == ['<eos>', 'q']
+    lb = p.c_struct()
+    assert lb.n_sent == 2 and not lb.vocab_ptr
+
+
+def test_library_exports_every_declared_symbol():
+    """include/jlm_b200.h is the contract: every function it declares must be exported, with the
+    binding table in jlm_b200/_lib.py covering exactly the same set."""
+    hdr = open(os.path.join(REPO, 'include', 'jlm_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(jlm_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().jlm_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by include/jlm_b200.h on LP64
+    assert ctypes.sizeof(_lib.Config) == 4 * (6 + 3 * 8)
+    assert ctypes.sizeof(_lib.Weights) == 8 * (4 + 4 + 4 + 4 + 8 + 8)
+    assert ctypes.sizeof(_lib.LatticeBatch) == 8 * 11
+    assert ctypes.sizeof(_lib.NBest) == 8 + 8 * 4
+    assert ctypes.sizeof(_lib.BatchInfo) == 8 * 3 + 4 * 2 + 8 * 3 + 4 * 3 + 4 * 4 + 4
+
+
+def test_product_fails_loudly_without_gpu(tmp_path):
+    """No CPU fallback: constructing the model without a CUDA device must raise, not degrade."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from jlm_b200 import synth, config, LSTM_Model
+    synth.make_experiment(str(tmp_path), 3, 200, 64, 32, 'tied', seed=0)
+    config.set_root(str(tmp_path))
+    with pytest.raises(_lib.JlmError, match='no usable CUDA device'):
+        LSTM_Model(3)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure; nothing under jlm_b200/ may reference it."""
+    pkg = os.path.join(REPO, 'jlm_b200')
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(root, fn), encoding='utf-8').read()
+                assert 'oracle' not in src.replace('test infrastructure', ''), os.path.join(root, fn)

@@ -132,6 +132,7 @@ def main():
     ap.add_argument('--ref-sentences', type=int, default=8)
     ap.add_argument('--cpu-baseline-sentences', type=int, default=12)
     ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
+    ap.add_argument('--profile', action='store_true', help='1 warm-up + K plain steps only (for ncu); prints no JSON')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -201,6 +202,12 @@ def main():
     batch = C.c_void_p()
     _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(batch)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
+    if args.profile:
+        for _ in range(1 + args.steps):
+            _lib.check(lib.jlm_batch_run(batch))
+        torch.cuda.synchronize()
+        _lib.check(lib.jlm_batch_destroy(batch))
+        return
     for _ in range(max(args.warmup, 3)):
         _lib.check(lib.jlm_batch_run(batch))
     barrier()

@@ -259,7 +259,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
-            if (n0 + 32 <= g.N) {
+            if (n0 + 32 <= g.N && (g.ldc & 3) == 0) {
               if (g.C32) {
                 float4* dst = reinterpret_cast<float4*>(g.C32 + (int64_t)row * g.ldc + n0);
 #pragma unroll

@@ -31,77 +31,149 @@ __global__ void k_init_frame0(BeamDev d, int S) {
   if (d.slot_cumy) d.slot_cumy[s0] = 0.0;
 }
 
-// One warp per sentence: expand (decoder.py:172-182), score (Path.append_node, decoder.py:43-49)
-// and keep the beam_width best under the reference's stable sort (decoder.py:227-229): candidates
-// are visited in the reference's enumeration order (node order, then parent rank) and a candidate
-// only displaces kept entries that are strictly worse, so equal scores keep the earlier ordinal.
-// The kept list lives in registers, sorted, entry e at (lane e%32, register e/32); a warp ballot
-// finds the few candidates that beat the current k-th score.
+// Score: Path.append_node (decoder.py:43-49) for every lattice node that STARTS at the frame that
+// was just stepped.  One warp per node: the node's word row of the output block is read once and
+// dotted (float64 accumulation) with the stage-1 projection row of each kept path of the start frame;
+// the result lands in the node's slice of its END frame's candidate list, so the prune kernel of
+// that later frame scans one contiguous, coalesced array.
+//   static : cand_val = parent score + (LSE(parent row) - y[word])      (-y when self-normalised)
+//   dynamic: cand_val = y[word]; scores depend on the end frame's vocabulary and are formed at prune time
+constexpr int SC_RC = 8;       // rows accumulated per pass
+constexpr int SC_WARPS = 8;    // warps (= nodes) per CTA
+
+template <typename TT, bool DYN>
+__global__ void __launch_bounds__(SC_WARPS * 32)
+k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
+              int64_t item0, int n_items, int64_t row0, int use_lse) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int n = d.start_items[item0 + item];
+  const int w = d.node_word[n];
+  const int pf = d.node_pfid[n];
+  const int rows = d.bc[pf];
+  const int64_t ps0 = d.slot0[pf];
+  const int64_t cpos = d.cand_pos[n];
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
+    if (i < seg.n && w >= seg.start[i]) s = i;
+  const int kpad = seg.kpad[s];
+  const float* wrow = seg.W[s] + (int64_t)(w - seg.start[s]) * kpad;
+  const TT* trow = T + (ps0 - row0) * ldt + seg.koff[s];
+  const double bias = (double)b2[w];
+  for (int r0 = 0; r0 < rows; r0 += SC_RC) {
+    double acc[SC_RC];
+#pragma unroll
+    for (int r = 0; r < SC_RC; ++r) acc[r] = 0.0;
+    for (int k = lane * 4; k < kpad; k += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+#pragma unroll
+      for (int r = 0; r < SC_RC; ++r) {
+        if (r0 + r < rows) {
+          const TT* tp = trow + (int64_t)(r0 + r) * ldt + k;
+          acc[r] = fma((double)tp[0], (double)wv.x, acc[r]);
+          acc[r] = fma((double)tp[1], (double)wv.y, acc[r]);
+          acc[r] = fma((double)tp[2], (double)wv.z, acc[r]);
+          acc[r] = fma((double)tp[3], (double)wv.w, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SC_RC; ++r) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < SC_RC; ++r) {
+      if (lane == r && r0 + r < rows) {
+        const double y = acc[r] + bias;
+        const int64_t ps = ps0 + r0 + r;
+        d.cand_val[cpos + r0 + r] = DYN ? y : d.slot_score[ps] + ((use_lse ? d.slot_lse[ps] : 0.0) - y);
+      }
+    }
+  }
+}
+
+// Prune: one warp per sentence keeps the beam_width best candidates of the frame under the
+// reference's stable sort (decoder.py:227-229).  The frame's candidates are one contiguous array in
+// the reference's enumeration order (node order, then parent rank), read 128 per iteration with
+// coalesced loads; a warp ballot picks the few that beat the current k-th score and a candidate only
+// displaces kept entries that are strictly worse, so equal scores keep the earlier ordinal.  The kept
+// list lives in registers, sorted, entry e at (lane e%32, register e/32), as (score, ordinal); the
+// (node, parent) of the survivors is recovered at the end by a binary search over the frame's nodes.
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
-k_expand_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
+k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= nact) return;
   const unsigned FULL = 0xffffffffu;
   const int fid = (int)d.fbase[warp] + t;
   const int lo = d.frame_lo[fid], hi = d.frame_hi[fid];
+  const int64_t c0 = d.frame_cand_lo[fid];
+  const int nc = d.frame_ncand[fid];
+  const double* val = d.cand_val + c0;
 
-  if (DYN && use_lse) {
+  if (DYN) {
     // _fix_neg_log (decoder_dynamic.py:150-175): every ancestor transition is re-scored with the
-    // softmax over lattice_vocab[t]; sum the ancestors' LSEs once per potential parent.
-    for (int pf = d.frame_minpf[fid]; pf < fid; ++pf) {
+    // softmax over lattice_vocab[t]; sum the ancestors' LSEs once per potential parent ...
+    if (use_lse) {
+      for (int pf = d.frame_minpf[fid]; pf < fid; ++pf) {
+        const int pc = d.bc[pf];
+        const int64_t ps0 = d.slot0[pf];
+        for (int r = lane; r < pc; r += 32) {
+          double sum = 0.0;
+          int a = (int)(ps0 + r);
+          while (a >= 0) {
+            sum += d.dyn_lse[(int64_t)a * tstride + t];
+            a = d.slot_parent[a];
+          }
+          d.dyn_chain[ps0 + r] = sum;
+        }
+      }
+      __syncwarp();
+    }
+    // ... then the candidates' scores: sum of LSEs minus sum of logits along the path
+    for (int n = lo; n < hi; ++n) {
+      const int pf = d.node_pfid[n];
       const int pc = d.bc[pf];
       const int64_t ps0 = d.slot0[pf];
-      for (int r = lane; r < pc; r += 32) {
-        double sum = 0.0;
-        int a = (int)(ps0 + r);
-        while (a >= 0) {
-          sum += d.dyn_lse[(int64_t)a * tstride + t];
-          a = d.slot_parent[a];
-        }
-        d.dyn_chain[ps0 + r] = sum;
-      }
+      const int64_t cp = d.cand_pos[n];
+      for (int r = lane; r < pc; r += 32)
+        d.cand_sc[cp + r] = (use_lse ? d.dyn_chain[ps0 + r] : 0.0) - (d.slot_cumy[ps0 + r] + d.cand_val[cp + r]);
     }
     __syncwarp();
+    val = d.cand_sc + c0;
   }
 
-  double es[L], ey[L];
-  int ep[L], en[L];
+  double es[L];
+  int ec[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     es[l] = INFINITY;
-    ey[l] = 0.0;
-    ep[l] = -1;
-    en[l] = -1;
+    ec[l] = -1;
   }
   const int kl = (W - 1) >> 5, klane = (W - 1) & 31;
   double kth = INFINITY;
 
-  for (int n = lo; n < hi; ++n) {
-    const int pf = d.node_pfid[n];
-    const int pc = d.bc[pf];
-    const int64_t ps0 = d.slot0[pf];
-    const int64_t loff = d.logit_off[n];
-    for (int base = 0; base < pc; base += 32) {
-      const int r = base + lane;
-      const bool valid = r < pc;
-      double y = 0.0, sc = INFINITY;
-      if (valid) {
-        y = d.node_logit[loff + r];
-        if (DYN)
-          sc = (use_lse ? d.dyn_chain[ps0 + r] : 0.0) - (d.slot_cumy[ps0 + r] + y);
-        else
-          sc = d.slot_score[ps0 + r] + ((use_lse ? d.slot_lse[ps0 + r] : 0.0) - y);
-      }
-      unsigned m = __ballot_sync(FULL, valid && sc < kth);
+  constexpr int U = 4;   // 32-candidate groups in flight per iteration
+  for (int base = 0; base < nc; base += 32 * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = base + u * 32 + lane;
+      v[u] = c < nc ? val[c] : INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned m = __ballot_sync(FULL, v[u] < kth);
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const double x = __shfl_sync(FULL, sc, b);
-        const double xy = __shfl_sync(FULL, y, b);
+        const double x = __shfl_sync(FULL, v[u], b);
         if (!(x < kth)) continue;
-        const int xp = (int)(ps0 + base + b);
+        const int xc = base + u * 32 + b;
         int pos = 0;
 #pragma unroll
         for (int l = 0; l < L; ++l) pos += __popc(__ballot_sync(FULL, es[l] <= x));
@@ -109,31 +181,21 @@ k_expand_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
         for (int l = L - 1; l >= 0; --l) {
           const int idx = l * 32 + lane;
           double us = __shfl_up_sync(FULL, es[l], 1);
-          double uy = __shfl_up_sync(FULL, ey[l], 1);
-          int up = __shfl_up_sync(FULL, ep[l], 1);
-          int un = __shfl_up_sync(FULL, en[l], 1);
+          int uc = __shfl_up_sync(FULL, ec[l], 1);
           if (l > 0) {
             const double cs = __shfl_sync(FULL, es[l > 0 ? l - 1 : 0], 31);
-            const double cy = __shfl_sync(FULL, ey[l > 0 ? l - 1 : 0], 31);
-            const int cp = __shfl_sync(FULL, ep[l > 0 ? l - 1 : 0], 31);
-            const int cn = __shfl_sync(FULL, en[l > 0 ? l - 1 : 0], 31);
+            const int cc = __shfl_sync(FULL, ec[l > 0 ? l - 1 : 0], 31);
             if (lane == 0) {
               us = cs;
-              uy = cy;
-              up = cp;
-              un = cn;
+              uc = cc;
             }
           }
           if (idx > pos) {
             es[l] = us;
-            ey[l] = uy;
-            ep[l] = up;
-            en[l] = un;
+            ec[l] = uc;
           } else if (idx == pos) {
             es[l] = x;
-            ey[l] = xy;
-            ep[l] = xp;
-            en[l] = n;
+            ec[l] = xc;
           }
         }
         double kv = es[0];
@@ -151,11 +213,19 @@ k_expand_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
   for (int l = 0; l < L; ++l) {
     const int idx = l * 32 + lane;
     if (idx < cnt) {
+      const int64_t c = c0 + ec[l];
+      // last node of the frame whose first candidate is <= c
+      int a = lo, b = hi - 1;
+      while (a < b) {
+        const int mid = (a + b + 1) >> 1;
+        if (d.cand_pos[mid] <= c) a = mid; else b = mid - 1;
+      }
+      const int par = (int)(d.slot0[d.node_pfid[a]] + (c - d.cand_pos[a]));
       d.slot_score[s0 + idx] = es[l];
-      d.slot_parent[s0 + idx] = ep[l];
-      d.slot_node[s0 + idx] = en[l];
-      d.slot_word[s0 + idx] = en[l] >= 0 ? d.node_word[en[l]] : 0;
-      if (DYN) d.slot_cumy[s0 + idx] = (ep[l] >= 0 ? d.slot_cumy[ep[l]] : 0.0) + ey[l];
+      d.slot_parent[s0 + idx] = par;
+      d.slot_node[s0 + idx] = a;
+      d.slot_word[s0 + idx] = d.node_word[a];
+      if (DYN) d.slot_cumy[s0 + idx] = d.slot_cumy[par] + d.cand_val[c];
     }
   }
 }
@@ -247,9 +317,9 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
 // host: plan
 // ------------------------------------------------------------------------------------------------
 struct HostPlan {
-  std::vector<int32_t> node_word, node_pfid, frame_lo, frame_hi, frame_minpf, bc, sent_T, start_words;
-  std::vector<int64_t> logit_off, slot0, fbase;
-  std::vector<SubsetJob> node_jobs, vocab_jobs;
+  std::vector<int32_t> node_word, node_pfid, frame_lo, frame_hi, frame_ncand, frame_minpf, bc, sent_T, start_items;
+  std::vector<int64_t> cand_pos, frame_cand_lo, slot0, fbase;
+  std::vector<SubsetJob> vocab_jobs;
   std::vector<DynJobInfo> dyn_info;
   std::vector<int32_t> vocab_cols, vfp;
 };
@@ -296,9 +366,11 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
   b->N = N;
   P.node_word.assign(lat->node_word, lat->node_word + N);
   P.node_pfid.assign(N, -1);
-  P.logit_off.assign(N, 0);
+  P.cand_pos.assign(N, 0);
   P.frame_lo.assign(F, 0);
   P.frame_hi.assign(F, 0);
+  P.frame_cand_lo.assign(F, 0);
+  P.frame_ncand.assign(F, 0);
   P.frame_minpf.assign(F, 0);
   P.bc.assign(F, 0);
   P.slot0.assign(F, 0);
@@ -320,6 +392,7 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
       P.frame_hi[fb + t] = (int32_t)fp[t + 1];
       int64_t ncand = 0;
       int minpf = (int)(fb + t);
+      P.frame_cand_lo[fb + t] = n_cand_total;
       for (int64_t n = fp[t]; n < fp[t + 1]; ++n) {
         const int w = lat->node_word[n];
         JLM_REQUIRE(w >= 0 && w < h->V, "decode: word id %d out of range", w);
@@ -328,10 +401,13 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
         JLM_REQUIRE(st >= 0 && st < t, "decode: node %lld of sentence %d has start %d at frame %d", (long long)n, s, st, t);
         P.node_pfid[n] = (int32_t)(fb + st);
         nstart[fb + st] += 1;
+        P.cand_pos[n] = n_cand_total + ncand;
         ncand += P.bc[fb + st];
         minpf = std::min(minpf, (int)(fb + st));
       }
       P.frame_minpf[fb + t] = minpf;
+      JLM_REQUIRE(ncand < (int64_t)1 << 31, "decode: too many candidates in one frame");
+      P.frame_ncand[fb + t] = (int32_t)ncand;
       P.bc[fb + t] = t == 0 ? 1 : (int32_t)std::min<int64_t>(b->W, ncand);
       n_cand_total += ncand;
     }
@@ -362,25 +438,26 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
   b->n_slots = slot;
   b->slot0 = P.slot0;
 
-  // nodes grouped by start frame; node logits are stored [start frame][node][parent rank]
-  std::vector<int64_t> start_ptr(F + 1, 0);
-  for (int64_t f = 0; f < F; ++f) start_ptr[f + 1] = start_ptr[f] + nstart[f];
-  P.start_words.assign(std::max<int64_t>(start_ptr[F], 1), 0);
-  std::vector<int64_t> cand_base(F, 0);
+  // lattice nodes grouped by the lock-step frame they START at (sentence position, then node order):
+  // the work list of the scoring kernel that follows that frame's LM step
   {
-    int64_t base = 0;
-    for (int64_t f = 0; f < F; ++f) {
-      cand_base[f] = base;
-      base += (int64_t)nstart[f] * P.bc[f];
+    std::vector<int64_t> item_base(F + 1, 0);
+    int64_t item = 0;
+    for (int t = 0; t < b->n_steps; ++t) {
+      StepPlan& sp = b->steps[t];
+      sp.item0 = item;
+      for (int p = 0; p < sp.nact; ++p) {
+        const int64_t fid = b->fbase[p] + t;
+        item_base[fid] = item;
+        item += nstart[fid];
+      }
+      JLM_REQUIRE(item - sp.item0 < (int64_t)1 << 31, "decode: too many nodes start at one frame");
+      sp.n_items = (int)(item - sp.item0);
     }
-    JLM_REQUIRE(base == n_cand_total, "decode: internal candidate count mismatch");
-    std::vector<int64_t> fill(start_ptr.begin(), start_ptr.end() - 1);
+    P.start_items.assign(std::max<int64_t>(item, 1), 0);
     for (int64_t n = 0; n < N; ++n) {
       const int pf = P.node_pfid[n];
-      if (pf < 0) continue;
-      const int64_t q = fill[pf]++;
-      P.start_words[q] = P.node_word[n];
-      P.logit_off[n] = cand_base[pf] + (q - start_ptr[pf]) * P.bc[pf];
+      if (pf >= 0) P.start_items[item_base[pf]++] = (int32_t)n;
     }
   }
 
@@ -427,9 +504,6 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
     int64_t yv = 0;
     for (int p = 0; p < sp.nstep; ++p) {
       const int64_t fid = b->fbase[p] + t;
-      SubsetJob nj{P.slot0[fid] - sp.row0, P.bc[fid], start_ptr[fid], nstart[fid], cand_base[fid]};
-      P.node_jobs.push_back(nj);
-      sp.max_node_cols = std::max(sp.max_node_cols, nstart[fid]);
       if (vocab_mode) {
         const int s = b->order[p];
         const int nc = (int)(col_ptr[s + 1] - col_ptr[s]);
@@ -458,16 +532,17 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   BeamDev& d = b->d;
   d.node_word = place(a, P.node_word);
   d.node_pfid = place(a, P.node_pfid);
-  d.logit_off = place(a, P.logit_off);
+  d.cand_pos = place(a, P.cand_pos);
   d.frame_lo = place(a, P.frame_lo);
   d.frame_hi = place(a, P.frame_hi);
+  d.frame_cand_lo = place(a, P.frame_cand_lo);
+  d.frame_ncand = place(a, P.frame_ncand);
   d.frame_minpf = place(a, P.frame_minpf);
   d.bc = place(a, P.bc);
   d.slot0 = place(a, P.slot0);
   d.fbase = place(a, P.fbase);
   d.sent_T = place(a, P.sent_T);
-  d.start_words = place(a, P.start_words);
-  d.node_jobs = place(a, P.node_jobs);
+  d.start_items = place(a, P.start_items);
   d.vocab_jobs = place(a, P.vocab_jobs);
   d.dyn_info = place(a, P.dyn_info);
   d.vocab_cols = place(a, P.vocab_cols);
@@ -478,13 +553,15 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   d.slot_parent = a.take<int32_t>(ns);
   d.slot_node = a.take<int32_t>(ns);
   d.slot_word = a.take<int32_t>(ns);
-  d.slot_cumy = d.dyn_lse = d.dyn_chain = nullptr;
+  d.slot_cumy = d.dyn_lse = d.dyn_chain = d.cand_sc = nullptr;
+  const size_t ncd = (size_t)std::max<int64_t>(b->n_cand, 1);
   if (b->dynamic) {
+    d.cand_sc = a.take<double>(ncd);
     d.slot_cumy = a.take<double>(ns);
     d.dyn_chain = a.take<double>(ns);
     d.dyn_lse = a.take<double>(ns * (size_t)(b->Tmax + 1));
   }
-  d.node_logit = a.take<double>((size_t)std::max<int64_t>(b->n_cand, 1));
+  d.cand_val = a.take<double>(ncd);
   d.out_score = a.take<double>((size_t)b->S * b->topN);
   d.out_npaths = a.take<int32_t>((size_t)b->S);
   d.out_len = a.take<int32_t>((size_t)b->S * b->topN);
@@ -529,9 +606,16 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
     JLM_CUDA(cudaGetLastError());
     b->launches += 2;
   }
-  if (sp.max_node_cols > 0) {
-    JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.node_jobs + sp.job0, sp.nstep, sp.max_node_cols, d.start_words, nullptr,
-                              d.node_logit, 0));
+  if (sp.n_items > 0) {
+    const int grid = ceil_div(sp.n_items, SC_WARPS);
+    const int ul = b->use_lse ? 1 : 0;
+    if (b->dynamic)
+      k_score_nodes<TT, true><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, d, h->b2, sp.item0, sp.n_items,
+                                                             sp.row0, ul);
+    else
+      k_score_nodes<TT, false><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, d, h->b2, sp.item0, sp.n_items,
+                                                              sp.row0, ul);
+    JLM_CUDA(cudaGetLastError());
     b->launches += 1;
   }
   return 0;
@@ -587,11 +671,11 @@ int32_t launch_prune(jlm_batch* b, int t) {
   const int ul = b->use_lse ? 1 : 0;
   cudaStream_t st = b->h->stream;
   if (L <= 1)
-    k_expand_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+    k_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
   else if (L <= 2)
-    k_expand_prune<2, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+    k_prune<2, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
   else
-    k_expand_prune<4, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+    k_prune<4, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   return 0;
@@ -652,16 +736,17 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
       memset(host, 0, plan_bytes);
       stage(host, base, b->d.node_word, P.node_word);
       stage(host, base, b->d.node_pfid, P.node_pfid);
-      stage(host, base, b->d.logit_off, P.logit_off);
+      stage(host, base, b->d.cand_pos, P.cand_pos);
       stage(host, base, b->d.frame_lo, P.frame_lo);
       stage(host, base, b->d.frame_hi, P.frame_hi);
+      stage(host, base, b->d.frame_cand_lo, P.frame_cand_lo);
+      stage(host, base, b->d.frame_ncand, P.frame_ncand);
       stage(host, base, b->d.frame_minpf, P.frame_minpf);
       stage(host, base, b->d.bc, P.bc);
       stage(host, base, b->d.slot0, P.slot0);
       stage(host, base, b->d.fbase, P.fbase);
       stage(host, base, b->d.sent_T, P.sent_T);
-      stage(host, base, b->d.start_words, P.start_words);
-      stage(host, base, b->d.node_jobs, P.node_jobs);
+      stage(host, base, b->d.start_items, P.start_items);
       stage(host, base, b->d.vocab_jobs, P.vocab_jobs);
       stage(host, base, b->d.dyn_info, P.dyn_info);
       stage(host, base, b->d.vocab_cols, P.vocab_cols);

@@ -3,41 +3,43 @@
 #include "jlm_common.cuh"
 
 struct StepPlan {
-  int64_t row0;      // first beam slot of this lock-step frame (slots are frame-major)
-  int rows_step;     // rows that take an LM step (sentences that continue past this frame)
-  int rows_all;      // all beam entries of the frame
-  int nact;          // sentences (sorted positions 0..nact) that have this frame
-  int nstep;         // sentences that continue (prefix of the active ones)
-  int64_t job0;      // first SubsetJob of the step (one per stepped sentence)
-  int max_node_cols; // largest number of nodes starting at this frame in one sentence
+  int64_t row0;       // first beam slot of this lock-step frame (slots are frame-major)
+  int rows_step;      // rows that take an LM step (sentences that continue past this frame)
+  int rows_all;       // all beam entries of the frame
+  int nact;           // sentences (sorted positions 0..nact) that have this frame
+  int nstep;          // sentences that continue (prefix of the active ones)
+  int64_t item0;      // first entry of start_items: lattice nodes that START at this frame
+  int n_items;
+  int64_t job0;       // first vocabulary SubsetJob of the step (one per stepped sentence)
   int max_vocab_cols;
-  int64_t yv_elems;  // elements of the per-step vocab-logit scratch
+  int64_t yv_elems;   // elements of the per-step vocab-logit scratch
 };
 
 struct DynJobInfo {
-  int64_t vfp_off;   // into d_vfp (sentence's vocab_frame_ptr, T+2 entries)
+  int64_t vfp_off;    // into d_vfp (sentence's vocab_frame_ptr, T+2 entries)
   int32_t nv, nd, T, pad;
 };
 
 struct BeamDev {
-  // plan (read-only on the device)
+  // ---- plan (read-only on the device) ----
   int32_t* node_word = nullptr;
   int32_t* node_pfid = nullptr;     // frame id of the node's start frame, -1 for <eos>
-  int64_t* logit_off = nullptr;     // first node-logit slot of the node
+  int64_t* cand_pos = nullptr;      // first candidate slot of the node (candidates are END-frame major)
   int32_t* frame_lo = nullptr;      // per frame id: nodes ending here [lo, hi)
   int32_t* frame_hi = nullptr;
-  int32_t* frame_minpf = nullptr;   // smallest parent frame id among them (dynamic chain sums)
+  int64_t* frame_cand_lo = nullptr; // per frame id: first candidate
+  int32_t* frame_ncand = nullptr;   // per frame id: candidates (sum over its nodes of the parents' beam counts)
+  int32_t* frame_minpf = nullptr;   // smallest parent frame id (dynamic chain sums)
   int32_t* bc = nullptr;            // beam count per frame id
   int64_t* slot0 = nullptr;         // first slot per frame id
   int64_t* fbase = nullptr;         // first frame id per sorted sentence
   int32_t* sent_T = nullptr;
-  int32_t* start_words = nullptr;   // words of nodes grouped by start frame
-  SubsetJob* node_jobs = nullptr;
+  int32_t* start_items = nullptr;   // node ids grouped by the lock-step frame they start at
   SubsetJob* vocab_jobs = nullptr;
   DynJobInfo* dyn_info = nullptr;
   int32_t* vocab_cols = nullptr;
   int32_t* vfp = nullptr;
-  // beam state
+  // ---- beam state ----
   double* slot_score = nullptr;
   double* slot_lse = nullptr;
   double* slot_cumy = nullptr;      // dynamic: sum of the path's logits
@@ -46,8 +48,11 @@ struct BeamDev {
   int32_t* slot_parent = nullptr;   // global slot of the parent, -1 for <eos>
   int32_t* slot_node = nullptr;
   int32_t* slot_word = nullptr;
-  double* node_logit = nullptr;
-  // n-best output
+  // candidates, contiguous per (sentence, frame) in the reference's enumeration order
+  // (node order, then parent rank): candidate cand_pos[n] + r extends parent rank r with node n
+  double* cand_val = nullptr;       // static: full path score ; dynamic: the transition's logit
+  double* cand_sc = nullptr;        // dynamic only: score under the current frame's softmaxes
+  // ---- n-best output ----
   double* out_score = nullptr;
   int32_t* out_npaths = nullptr;
   int32_t* out_len = nullptr;

@@ -144,6 +144,25 @@ struct jlm_handle {
   cudaEvent_t ev[4] = {};
 };
 
+// Segment table passed by value to kernels that look a word's output block up.
+struct SegTable {
+  int n;
+  int start[JLM_MAX_SEGMENTS], end[JLM_MAX_SEGMENTS], koff[JLM_MAX_SEGMENTS], kpad[JLM_MAX_SEGMENTS];
+  const float* W[JLM_MAX_SEGMENTS];
+};
+static inline SegTable make_seg_table(const jlm_handle* h) {
+  SegTable t{};
+  t.n = h->n_seg;
+  for (int i = 0; i < h->n_seg; ++i) {
+    t.start[i] = h->seg[i].start;
+    t.end[i] = h->seg[i].end;
+    t.koff[i] = h->seg[i].koff;
+    t.kpad[i] = h->seg[i].kpad;
+    t.W[i] = h->seg[i].W;
+  }
+  return t;
+}
+
 // ---------------------------------------------------------------- exact back end (jlm_exact.cu)
 // C[M,N] (+bias) = A[M,K] . B[N,K]^T, float64 accumulation.  K % 32 == 0, lda/ldb % 4 == 0.
 // part != nullptr: also emit per-(row, 64-column tile) (max, sum exp) partials, tile index offset

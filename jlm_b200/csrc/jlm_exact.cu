@@ -201,12 +201,6 @@ __global__ void k_lstm_pointwise(const double* __restrict__ gates, const double*
   }
 }
 
-struct SegTable {
-  int n;
-  int start[JLM_MAX_SEGMENTS], end[JLM_MAX_SEGMENTS], koff[JLM_MAX_SEGMENTS], kpad[JLM_MAX_SEGMENTS];
-  const float* W[JLM_MAX_SEGMENTS];
-};
-
 constexpr int SUB_RC = 8;        // rows accumulated per pass
 constexpr int SUB_WARPS = 8;     // warps per CTA, one column per warp per iteration
 
@@ -260,19 +254,6 @@ k_subset_logits(SegTable seg, const TT* __restrict__ T, int64_t ldt, const Subse
       }
     }
   }
-}
-
-SegTable make_seg_table(const jlm_handle* h) {
-  SegTable t{};
-  t.n = h->n_seg;
-  for (int i = 0; i < h->n_seg; ++i) {
-    t.start[i] = h->seg[i].start;
-    t.end[i] = h->seg[i].end;
-    t.koff[i] = h->seg[i].koff;
-    t.kpad[i] = h->seg[i].kpad;
-    t.W[i] = h->seg[i].W;
-  }
-  return t;
 }
 
 int grid_1d(int64_t total, int block, int cap) {

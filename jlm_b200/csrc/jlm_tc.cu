@@ -7,8 +7,9 @@
 // per operand.  One product is three MMAs (hi.lo + lo.hi + hi.hi; lo.lo ~ 2^-22 is dropped) into
 // one fp32 TMEM accumulator, un-scaled in the epilogue.
 //
-// Kernel.  One persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one
-// elected lane) + TMEM owner, warps 2-5 = epilogue (one TMEM lane quarter each).  128 x BN x 64
+// Kernel.  One persistent CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane)
+// + TMEM owner, then 4 epilogue warps (one TMEM lane quarter each; the LSTM epilogue runs 8, two per
+// quarter splitting the tile's columns, because its math is what paces that kernel).  128 x BN x 64
 // tiles, smem ring of {A_hi, A_lo, B_hi, B_lo} stages in SWIZZLE_128B layout, two TMEM accumulator
 // stages so the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogues:
 //   EPI_LSTM  : gate bias + sigmoid/tanh + cell update (decoder/model.py:132-139), writes h, c and
@@ -37,6 +38,21 @@ constexpr int A_TILE = BM * BK * 2;  // bytes of one fp16 A tile
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum { EPI_LSE = 0, EPI_STORE = 1, EPI_LSTM = 2 };
+
+template <int EPI>
+struct EpiCfg {
+  static constexpr int WARPS = (EPI == EPI_LSTM) ? 8 : 4;   // epilogue warps
+  static constexpr int THREADS = 64 + 32 * WARPS;
+};
+
+// sigmoid / tanh on the MUFU pipe (ex2.approx + rcp.approx, ~2e-7 absolute): the gate epilogue is
+// MUFU-paced, and these stay an order of magnitude inside the split-fp16 GEMM's own error.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  // 1 - 2/(e^{2x}+1); clamped so e^{2x} stays finite (tanh(15) == 1 in float)
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  return fmaf(-2.f, __frcp_rn(__expf(2.f * xc) + 1.f), 1.f);
+}
 
 template <int BN>
 struct TileCfg {
@@ -92,7 +108,7 @@ __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const floa
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
           const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const GemmArgs g) {
   using C = TileCfg<BN>;
@@ -126,7 +142,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);
-        ptx::mbar_init(tempty_bar(a), 4);
+        ptx::mbar_init(tempty_bar(a), EpiCfg<EPI>::WARPS);
       }
       ptx::fence_barrier_init();
     }
@@ -202,26 +218,49 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..) =====================
+    constexpr int ET = 32 * EpiCfg<EPI>::WARPS;
     const int q = warp & 3;               // TMEM lane quarter this warp may read
-    const int te = threadIdx.x - 64;      // 0..127
+    const int te = threadIdx.x - 64;      // 0..ET-1
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
       float* bs = bias_s + acc * BN;
-      for (int c = te; c < BN; c += 128) {
+      for (int c = te; c < BN; c += ET) {
         const int n = n_blk * BN + c;
         float v = (EPI == EPI_LSE) ? -INFINITY : 0.f;
         if (n < g.N) v = g.bias ? g.bias[n] : 0.f;
         bs[c] = v;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
-      ptx::tc_fence_after();
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
+      // LSTM: the parent's cell row does not depend on the MMAs - fetch it while they run
+      constexpr int UPT = BN / 4;                       // hidden units per tile
+      constexpr int UPW = UPT / (EpiCfg<EPI>::WARPS / 4);   // units per epilogue warp
+      const int ubase = ((warp - 2) >> 2) * UPW;        // this warp's first unit inside the tile
+      float cprev[EPI == EPI_LSTM ? UPW : 1];
+      if (EPI == EPI_LSTM) {
+        const int par = row_ok ? g.parent[row] : -1;
+        if (par >= 0) {
+          const float4* src = reinterpret_cast<const float4*>(g.c_src + (int64_t)par * g.ld_state + n_blk * UPT + ubase);
+#pragma unroll
+          for (int j = 0; j < UPW / 4; ++j) {
+            const float4 t = src[j];
+            cprev[4 * j] = t.x;
+            cprev[4 * j + 1] = t.y;
+            cprev[4 * j + 2] = t.z;
+            cprev[4 * j + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < UPW; ++j) cprev[j] = 0.f;
+        }
+      }
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
 
       if (EPI == EPI_LSE) {
         float m_run = -INFINITY, c_run = -INFINITY, s_run = 0.f;
@@ -277,47 +316,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
           }
         }
       } else {
-        // EPI_LSTM: tile columns are [i | f | o | g] x (BN/4) units (weights permuted on the host)
-        constexpr int UPT = BN / 4;
-        for (int uc = 0; uc < UPT / 16; ++uc) {
+        // EPI_LSTM: tile columns are [i | f | o | g] x (BN/4) units (weights permuted on the host);
+        // decoder/model.py:132-139
+#pragma unroll
+        for (int uc = 0; uc < UPW / 16; ++uc) {
+          const int ul = ubase + uc * 16;               // first unit of the chunk inside the tile
           uint32_t ri[16], rf[16], ro[16], rg[16];
-          ptx::tmem_ld_x16(taddr + uc * 16, ri);
-          ptx::tmem_ld_x16(taddr + UPT + uc * 16, rf);
-          ptx::tmem_ld_x16(taddr + 2 * UPT + uc * 16, ro);
-          ptx::tmem_ld_x16(taddr + 3 * UPT + uc * 16, rg);
+          ptx::tmem_ld_x16(taddr + ul, ri);
+          ptx::tmem_ld_x16(taddr + UPT + ul, rf);
+          ptx::tmem_ld_x16(taddr + 2 * UPT + ul, ro);
+          ptx::tmem_ld_x16(taddr + 3 * UPT + ul, rg);
           ptx::tmem_ld_wait();
           if (row_ok) {
-            const int u0 = n_blk * UPT + uc * 16;
-            const int par = g.parent[row];
-            float cp[16];
-            if (par >= 0) {
-              const float4* src = reinterpret_cast<const float4*>(g.c_src + (int64_t)par * g.ld_state + u0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 t = src[j];
-                cp[4 * j] = t.x;
-                cp[4 * j + 1] = t.y;
-                cp[4 * j + 2] = t.z;
-                cp[4 * j + 3] = t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) cp[j] = 0.f;
-            }
+            const int u0 = n_blk * UPT + ul;
             float hv[16], cv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float pi = fmaf(__uint_as_float(ri[j]), g.inv_scale, bs[uc * 16 + j]);
-              const float pf = fmaf(__uint_as_float(rf[j]), g.inv_scale, bs[UPT + uc * 16 + j]);
-              const float po = fmaf(__uint_as_float(ro[j]), g.inv_scale, bs[2 * UPT + uc * 16 + j]);
-              const float pg = fmaf(__uint_as_float(rg[j]), g.inv_scale, bs[3 * UPT + uc * 16 + j]);
-              const float gi = 1.f / (expf(-pi) + 1.f);
-              const float gf = 1.f / (expf(-pf) + 1.f);
-              const float go = 1.f / (expf(-po) + 1.f);
-              const float gg = tanhf(pg);
-              const float c = fmaf(cp[j], gf, gg * gi);
+              const float pi = fmaf(__uint_as_float(ri[j]), g.inv_scale, bs[ul + j]);
+              const float pf = fmaf(__uint_as_float(rf[j]), g.inv_scale, bs[UPT + ul + j]);
+              const float po = fmaf(__uint_as_float(ro[j]), g.inv_scale, bs[2 * UPT + ul + j]);
+              const float pg = fmaf(__uint_as_float(rg[j]), g.inv_scale, bs[3 * UPT + ul + j]);
+              const float c = fmaf(cprev[uc * 16 + j], fast_sigmoid(pf), fast_tanh(pg) * fast_sigmoid(pi));
               cv[j] = c;
-              hv[j] = tanhf(c) * go;
+              hv[j] = fast_tanh(c) * fast_sigmoid(po);
             }
             float4* dc = reinterpret_cast<float4*>(g.c_out + (int64_t)row * g.ld_state + u0);
             float4* dh = reinterpret_cast<float4*>(g.h_out + (int64_t)row * g.ld_state + u0);
@@ -489,7 +510,7 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   if (tiles <= 0) return 0;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  k_tc_gemm<BN, EPI><<<grid, 192, C::SMEM, h->stream>>>(Ah, Al, Bh, Bl, g);
+  k_tc_gemm<BN, EPI><<<grid, EpiCfg<EPI>::THREADS, C::SMEM, h->stream>>>(Ah, Al, Bh, Bl, g);
   JLM_CUDA(cudaGetLastError());
   return 0;
 }

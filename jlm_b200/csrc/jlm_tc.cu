@@ -45,13 +45,22 @@ struct EpiCfg {
   static constexpr int THREADS = 64 + 32 * WARPS;
 };
 
-// sigmoid / tanh on the MUFU pipe (ex2.approx + rcp.approx, ~2e-7 absolute): the gate epilogue is
-// MUFU-paced, and these stay an order of magnitude inside the split-fp16 GEMM's own error.
-__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
+// sigmoid / tanh straight on the MUFU pipe (ex2.approx + rcp.approx, ~2e-7 absolute): the gate
+// epilogue is instruction-paced, and these stay an order of magnitude inside the split-fp16 GEMM's
+// own error.  Saturation needs no clamps: ex2 -> +inf gives rcp -> 0.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(-LOG2E * x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
-  // 1 - 2/(e^{2x}+1); clamped so e^{2x} stays finite (tanh(15) == 1 in float)
-  const float xc = fminf(fmaxf(x, -15.f), 15.f);
-  return fmaf(-2.f, __frcp_rn(__expf(2.f * xc) + 1.f), 1.f);
+  return fmaf(-2.f, rcp_approx(ex2_approx((2.f * LOG2E) * x) + 1.f), 1.f);   // 1 - 2/(e^{2x}+1)
 }
 
 template <int BN>
@@ -88,16 +97,17 @@ struct GemmArgs {
   int64_t ld_state;
 };
 
+// 16 consecutive values -> two 32-byte runs (hi, lo): x*scale = hi + lo in fp16
 __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* v, float scale) {
-  // 16 consecutive values -> two 32-byte runs (hi, lo)
   uint32_t ph[8], pl[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float a = v[2 * j] * scale, b = v[2 * j + 1] * scale;
-    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-    ph[j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-    pl[j] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+    const __half2 h2 = __floats2half2_rn(a, b);          // one F2FP.PACK_AB
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+    ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
   }
   uint4* dh = reinterpret_cast<uint4*>(hi);
   uint4* dl = reinterpret_cast<uint4*>(lo);
@@ -392,10 +402,11 @@ __global__ void k_tc_gather_split(const float* __restrict__ h_src, const int32_t
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float x = v[2 * j] * scale, y = v[2 * j + 1] * scale;
-      const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
-      const __half lx = __float2half_rn(x - __half2float(hx)), ly = __float2half_rn(y - __half2float(hy));
-      ph[j] = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
-      pl[j] = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
+      const __half2 h2 = __floats2half2_rn(x, y);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(x - hf.x, y - hf.y);
+      ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
     }
     *reinterpret_cast<uint4*>(A_hi + (int64_t)m * Kg + k) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     *reinterpret_cast<uint4*>(A_lo + (int64_t)m * Kg + k) = make_uint4(pl[0], pl[1], pl[2], pl[3]);

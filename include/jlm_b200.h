@@ -137,6 +137,33 @@ typedef struct {
   const int32_t* dup_ids;
 } jlm_lattice_batch;
 
+/* ------------------------------------------------------------------------------------------------
+ * Native lattice builder (host code): Decoder._build_lattice (decoder.py:79-135) and the vocabulary
+ * selection lists (decoder.py:137-151, decoder_dynamic.py:30-46) for a batch of sentences, emitted as
+ * the CSR arrays above.  Needs no GPU.
+ *
+ * jlm_lexicon_create takes the dictionary side as the reference prepares it in Decoder.__init__
+ * (decoder.py:55-74): for every key of reading_dict.pkl its UTF-32 code points and the ids (w2i) of its
+ * in-vocabulary words in `sorted(lexicon ids)` order (decoder.py:97-103; out-of-vocabulary words
+ * already skipped).  Entry e of word_ids is "lexicon entry e"; node_entry reports it per lattice node so
+ * the host can recover the word string (-1: '<eos>', -2: the '<unk>' fallback whose word is the kana
+ * at node_start, decoder.py:129-130). */
+typedef struct jlm_lexicon jlm_lexicon;
+typedef struct jlm_lattice jlm_lattice;
+int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading_ptr /* [n+1] */,
+                           const uint32_t* reading_chars, const int64_t* word_ptr /* [n+1] */,
+                           const int32_t* word_ids, int32_t eos_id, int32_t unk_id, jlm_lexicon** out);
+int32_t jlm_lexicon_destroy(jlm_lexicon* lex);
+/* Sentence s is text[text_ptr[s] .. text_ptr[s+1]) (UTF-32).  mode = JLM_DECODE_*: which vocabulary
+ * lists to emit.  extra_ids [n_sent, n_extra] are the `samples` word ids of each sentence
+ * (top_sampling: 0..samples-1; random_sampling: the host's np.random.randint draw). */
+int32_t jlm_lattice_build(const jlm_lexicon* lex, int32_t n_sent, const int64_t* text_ptr, const uint32_t* text,
+                          int32_t mode, int32_t n_extra, const int32_t* extra_ids, jlm_lattice** out);
+/* Borrowed pointers into the lattice object (valid until jlm_lattice_destroy). */
+int32_t jlm_lattice_view(const jlm_lattice* lat, jlm_lattice_batch* view, const int32_t** node_entry,
+                         int64_t* n_nodes);
+int32_t jlm_lattice_destroy(jlm_lattice* lat);
+
 /* n-best output of Decoder.decode (decoder.py:237-241) for every sentence. */
 typedef struct {
   int32_t top_n;        /* capacity per sentence */

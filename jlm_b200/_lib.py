@@ -16,6 +16,7 @@ _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
 
 
 class Config(C.Structure):
@@ -72,6 +73,11 @@ SYMBOLS = {
     'jlm_batch_get_info': (C.c_int32, [_VP, C.POINTER(BatchInfo)]),
     'jlm_batch_enable_timers': (C.c_int32, [_VP, C.c_int32]),
     'jlm_batch_get_beams': (C.c_int32, [_VP, C.c_int32, _i32p, _f64p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p]),
+    'jlm_lexicon_create': (C.c_int32, [C.c_int32, _i64p, _u32p, _i64p, _i32p, C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    'jlm_lexicon_destroy': (C.c_int32, [_VP]),
+    'jlm_lattice_build': (C.c_int32, [_VP, C.c_int32, _i64p, _u32p, C.c_int32, C.c_int32, _i32p, C.POINTER(_VP)]),
+    'jlm_lattice_view': (C.c_int32, [_VP, C.POINTER(LatticeBatch), C.POINTER(_i32p), C.POINTER(C.c_int64)]),
+    'jlm_lattice_destroy': (C.c_int32, [_VP]),
     'jlm_tc_gemm_selftest': (C.c_int32, [_VP, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p]),
 }
 

@@ -37,6 +37,7 @@ class Decoder(object):
         self.perf_log_lstm = []
         self.perf_log_softmax = []
         self._builder = lattice.LatticeBuilder(self.w2i, self.full_lexicon, self.full_reading_dict)
+        self._native_lexicon = None
         self._lib = _lib.load()
         self.last_info = None
 
@@ -110,12 +111,9 @@ class Decoder(object):
             lib.jlm_batch_destroy(batch)
         out = []
         for s in range(S):
-            words = packed.node_words(s)
-            off = int(packed.node_off[s])
             res = []
             for k in range(int(n_paths[s])):
-                ids = path_nodes[s, k, :path_len[s, k]]
-                ws = [words[i - off] for i in ids]
+                ws = packed.path_words(s, path_nodes[s, k, :path_len[s, k]].tolist())
                 res.append((float(scores[s, k]), [w for w in ws if w != '<eos>']))   # decoder.py:237
             out.append(res[:topN])
         return out
@@ -168,9 +166,35 @@ class Decoder(object):
         self.perf_sen += 1
         return out
 
+    def _native(self):
+        if self._native_lexicon is None:
+            self._native_lexicon = lattice.NativeLexicon(self.w2i, self.full_lexicon, self.full_reading_dict)
+        return self._native_lexicon
+
+    def _sample_ids(self, n_sent, samples, top_sampling, random_sampling):
+        """The `samples` extra word ids of every sentence, drawn exactly as the reference does per
+        sentence (decoder.py:144-149): np.random.randint from the global stream, or range(samples)."""
+        if not samples or not (top_sampling or random_sampling):
+            return None
+        if random_sampling:
+            return np.stack([np.random.randint(len(self.w2i), size=samples) for _ in range(n_sent)]).astype(np.int32)
+        return np.tile(np.arange(samples, dtype=np.int32), (n_sent, 1))
+
     def decode_batch(self, inputs, topN=10, beam_width=10, vocab_select=False, samples=0, top_sampling=False,
-                     random_sampling=False, backend=_lib.BACKEND_AUTO):
-        """decode() for many independent sentences decoded in lock-step; returns one n-best list per input."""
+                     random_sampling=False, backend=_lib.BACKEND_AUTO, native_lattice=True):
+        """decode() for many independent sentences decoded in lock-step; returns one n-best list per input.
+        The lattices are built by the native builder (jlm_lattice_build) unless native_lattice=False or a
+        vocabulary left by an earlier decode() call has to be honoured (quirk 6)."""
+        inputs = list(inputs)
+        if native_lattice and inputs and (vocab_select or not self.lattice_vocab):
+            mode = _lib.DECODE_STATIC_VOCAB if vocab_select else _lib.DECODE_FULL
+            extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling) if vocab_select else None
+            packed = lattice.NativeLattices(self._native(), inputs, mode, extra)
+            out = self._run(packed, mode, topN, beam_width, backend, timers=False)
+            if vocab_select:
+                self.lattice_vocab = packed.vocab_list(len(inputs) - 1)
+            self.perf_sen += len(inputs)
+            return out
         all_frames, vocabs = [], []
         for text in inputs:
             frames = self._build_lattice(text, vocab_select=vocab_select, samples=samples,

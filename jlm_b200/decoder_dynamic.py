@@ -57,8 +57,14 @@ class DynamicDecoder(Decoder):
         return out[0]
 
     def decode_batch(self, inputs, topN=10, beam_width=10, vocab_select=True, samples=0, top_sampling=False,
-                     random_sampling=False, backend=_lib.BACKEND_AUTO):
-        _, out = self._decode_many(list(inputs), topN, beam_width, vocab_select, samples, top_sampling,
-                                   random_sampling, backend, timers=False)
+                     random_sampling=False, backend=_lib.BACKEND_AUTO, native_lattice=True):
+        inputs = list(inputs)
+        if native_lattice and inputs and vocab_select:
+            extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling)
+            packed = lattice.NativeLattices(self._native(), inputs, _lib.DECODE_DYNAMIC, extra)
+            out = self._run(packed, _lib.DECODE_DYNAMIC, topN, beam_width, backend, timers=False)
+        else:
+            _, out = self._decode_many(inputs, topN, beam_width, vocab_select, samples, top_sampling,
+                                       random_sampling, backend, timers=False)
         self.perf_sen += len(out)
         return out

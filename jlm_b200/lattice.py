@@ -202,3 +202,122 @@ class PackedLattices(object):
     def node_words(self, s):
         """Flat list of word strings of sentence s, indexed by (absolute node index - node_off[s])."""
         return [n[2] for f in self.frames[s] for n in f]
+
+    def path_words(self, s, node_ids):
+        """Word strings of the given absolute node indices of sentence s."""
+        words = self._words_cache.get(s) if hasattr(self, '_words_cache') else None
+        if words is None:
+            if not hasattr(self, '_words_cache'):
+                self._words_cache = {}
+            words = self._words_cache[s] = self.node_words(s)
+        off = int(self.node_off[s])
+        return [words[i - off] for i in node_ids]
+
+
+class NativeLexicon(object):
+    """Dictionary side of the lattice builder handed to libjlm_b200 once (jlm_lexicon_create):
+    reading -> in-vocabulary (word id, word) pairs in `sorted(lexicon ids)` order (decoder.py:97-103)."""
+
+    def __init__(self, w2i, full_lexicon, full_reading_dict):
+        self._lib = _lib.load()
+        rptr, wptr, chars, wids, self.entry_words = [0], [0], [], [], []
+        for reading, ids in full_reading_dict.items():
+            cps = [ord(ch) for ch in reading]
+            for lex_id in sorted(ids):
+                word = full_lexicon[lex_id][0]
+                idx = w2i.get(word)
+                if idx is not None:
+                    wids.append(idx)
+                    self.entry_words.append(word)
+            chars += cps
+            rptr.append(len(chars))
+            wptr.append(len(wids))
+        self._arrays = (np.array(rptr, dtype=np.int64), np.array(chars if chars else [0], dtype=np.uint32),
+                        np.array(wptr, dtype=np.int64), np.array(wids if wids else [0], dtype=np.int32))
+        a = self._arrays
+        self.handle = C.c_void_p()
+        _lib.check(self._lib.jlm_lexicon_create(len(rptr) - 1, _lib.ptr(a[0], C.c_int64), _lib.ptr(a[1], C.c_uint32),
+                                                _lib.ptr(a[2], C.c_int64), _lib.ptr(a[3], C.c_int32),
+                                                int(w2i['<eos>']), int(w2i['<unk>']), C.byref(self.handle)))
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h is not None and h.value:
+            self._lib.jlm_lexicon_destroy(h)
+            self.handle = None
+
+
+class NativeLattices(object):
+    """A batch of lattices built by jlm_lattice_build; same interface as PackedLattices for the decode
+    call (c_struct, n_sent, sent_len, path_words), arrays owned by the native object."""
+
+    def __init__(self, lexicon, texts, mode=_lib.DECODE_FULL, extra_ids=None):
+        self._lib = lexicon._lib
+        self._lexicon = lexicon
+        self.texts = list(texts)
+        self.n_sent = len(self.texts)
+        lens = np.fromiter((len(t) for t in self.texts), dtype=np.int64, count=self.n_sent)
+        tptr = np.zeros(self.n_sent + 1, dtype=np.int64)
+        np.cumsum(lens, out=tptr[1:])
+        joined = ''.join(self.texts)
+        cps = np.frombuffer(joined.encode('utf-32-le'), dtype=np.uint32) if joined else np.zeros(1, dtype=np.uint32)
+        n_extra = 0
+        if extra_ids is not None:
+            extra_ids = np.ascontiguousarray(extra_ids, dtype=np.int32).reshape(self.n_sent, -1)
+            n_extra = extra_ids.shape[1]
+        self.handle = C.c_void_p()
+        _lib.check(self._lib.jlm_lattice_build(lexicon.handle, self.n_sent, _lib.ptr(tptr, C.c_int64),
+                                               _lib.ptr(cps, C.c_uint32), int(mode), n_extra,
+                                               _lib.ptr(extra_ids, C.c_int32) if n_extra else None,
+                                               C.byref(self.handle)))
+        self._view = _lib.LatticeBatch()
+        entry = C.POINTER(C.c_int32)()
+        n_nodes = C.c_int64(0)
+        _lib.check(self._lib.jlm_lattice_view(self.handle, C.byref(self._view), C.byref(entry), C.byref(n_nodes)))
+        self.n_nodes = int(n_nodes.value)
+        v = self._view
+        self.sent_len = np.ctypeslib.as_array(v.sent_len, shape=(self.n_sent,))
+        self.frame_ptr_off = np.ctypeslib.as_array(v.frame_ptr_off, shape=(self.n_sent,))
+        n_fp = int(self.sent_len.astype(np.int64).sum()) + 2 * self.n_sent
+        self.frame_ptr = np.ctypeslib.as_array(v.frame_ptr, shape=(n_fp,))
+        self.node_start = np.ctypeslib.as_array(v.node_start, shape=(self.n_nodes,))
+        self.node_word = np.ctypeslib.as_array(v.node_word, shape=(self.n_nodes,))
+        self.node_entry = np.ctypeslib.as_array(entry, shape=(self.n_nodes,))
+        self.node_off = np.append(self.frame_ptr[self.frame_ptr_off], self.n_nodes).astype(np.int64)
+        self.mode = mode
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h is not None and h.value:
+            self._lib.jlm_lattice_destroy(h)
+            self.handle = None
+
+    def c_struct(self):
+        return self._view
+
+    def path_words(self, s, node_ids):
+        words, ew = [], self._lexicon.entry_words
+        for i in node_ids:
+            e = int(self.node_entry[i])
+            if e >= 0:
+                words.append(ew[e])
+            elif e == -1:
+                words.append('<eos>')
+            else:
+                words.append(self.texts[s][int(self.node_start[i])])     # '<unk>' node carries the raw kana
+        return words
+
+    def frames_of(self, s):
+        """Sentence s as the Python builder's frames (list over t of [(start, word_idx, word)])."""
+        fp = self.frame_ptr[int(self.frame_ptr_off[s]):int(self.frame_ptr_off[s]) + int(self.sent_len[s]) + 2]
+        out = []
+        for t in range(len(fp) - 1):
+            ids = range(int(fp[t]), int(fp[t + 1]))
+            ws = self.path_words(s, ids)
+            out.append([(int(self.node_start[i]), int(self.node_word[i]), w) for i, w in zip(ids, ws)])
+        return out
+
+    def vocab_list(self, s):
+        v = self._view
+        a, b = int(v.vocab_ptr[s]), int(v.vocab_ptr[s + 1])
+        return [int(v.vocab_ids[k]) for k in range(a, b)]

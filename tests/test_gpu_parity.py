@@ -223,3 +223,40 @@ def test_tc_matches_exact_on_a_lockstep_batch(tmp_path_factory):
     assert top1 == 64
     assert same == 64
     assert worst < 1e-3
+
+
+def test_full_size_batch_properties(tmp_path_factory):
+    """configs[1] at full model size, a 256-sentence lock-step batch on the tensor-core back end, checked
+    through size-independent properties: (a) the result of a sentence does not depend on its batch
+    neighbours or position (bit-identical under a permutation of the batch), (b) n-best scores ascend,
+    (c) the best path's score equals the sum of -log softmax re-computed step by step through the
+    model-level API (LSTM_Model.predict_with_context, exact back end) along that path."""
+    from jlm_b200 import synth
+    dec, case, _ = get_decoder('cfg2_tied', tmp_path_factory)
+    _, _, _, lexicon, _, _ = build_case('cfg2_tied')
+    sents = synth.make_sentences(lexicon, 256, min_len=20, seed=4242, vocab_size=case['vocab_size'])
+    dec._want_trace = False
+    try:
+        a = dec.decode_batch(sents, topN=10, beam_width=10, backend=TC)
+        perm = np.random.default_rng(5).permutation(len(sents))
+        b = dec.decode_batch([sents[i] for i in perm], topN=10, beam_width=10, backend=TC)
+    finally:
+        dec._want_trace = True
+    for k, i in enumerate(perm):
+        assert a[i] == b[k], i                                           # (a) bit-identical
+    for res in a:
+        sc = [s for s, _ in res]
+        assert sc == sorted(sc) and 1 <= len(res) <= 10                 # (b)
+    # (c) re-score the best path of a few sentences with the model API
+    eos = dec.w2i['<eos>']
+    for si in (0, 17, 255):
+        best_score, best_words = a[si][0]
+        h = np.zeros((1, dec.model.hidden_size))
+        c = np.zeros((1, dec.model.hidden_size))
+        prev, total = eos, 0.0
+        for w in best_words:
+            wid = dec.w2i.get(w, 0)                                      # '<unk>' nodes carry the raw kana
+            (pred, _, _, _), h, c = dec.model.predict_with_context([prev], h, c)
+            total += -np.log(pred[0, wid])
+            prev = wid
+        assert abs(total - best_score) < 1e-3, (si, total, best_score)

@@ -147,3 +147,80 @@ def test_product_does_not_import_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(root, fn), encoding='utf-8').read()
                 assert 'oracle' not in src.replace('test infrastructure', ''), os.path.join(root, fn)
+
+
+# ---------------------------------------------------------------------------------------------------
+# native lattice builder (jlm_lattice_build, host C++; no GPU needed) vs the Python restatement of
+# decoder.py:79-151 / decoder_dynamic.py:30-46 that is itself pinned to the reference fixtures above
+# ---------------------------------------------------------------------------------------------------
+def _native_setup(name):
+    case, cfg, weights, lexicon, reading_dict, sentences = build_case(name)
+    vocab = Vocab(cfg['vocab_size'], lexicon=lexicon)
+    builder = lattice.LatticeBuilder(vocab.w2i, lexicon, reading_dict)
+    nlex = lattice.NativeLexicon(vocab.w2i, lexicon, reading_dict)
+    return case, vocab, builder, nlex, sentences
+
+
+@pytest.mark.parametrize('name', ['small_tied', 'small_tied_beam50', 'cfg2_tied'])
+def test_native_lattice_matches_python_builder(name):
+    case, vocab, builder, nlex, sentences = _native_setup(name)
+    texts = list(sentences) + [sentences[0][:1], sentences[-1][:3], 'ヰヱヰ']     # ragged + kana with no reading
+    frames = [builder.build(t) for t in texts]
+    want = lattice.PackedLattices(frames)
+    got = lattice.NativeLattices(nlex, texts)
+    for key in ('sent_len', 'frame_ptr_off', 'frame_ptr', 'node_start', 'node_word'):
+        assert np.array_equal(getattr(got, key), getattr(want, key)), key
+    for s in range(len(texts)):
+        assert got.frames_of(s) == frames[s]
+    lb = got.c_struct()
+    assert lb.n_sent == len(texts) and not lb.vocab_ptr
+
+
+@pytest.mark.parametrize('name,mode', [('small_tied_vs', 1), ('small_tied_vs_top', 1), ('small_tied_vs_rand', 1),
+                                       ('small_tied_dyn', 2), ('small_tied_dyn_top', 2), ('small_tied_dyn_rand', 2),
+                                       ('cfg4_tied_dyn', 2)])
+def test_native_vocab_lists_match_python(name, mode):
+    case, vocab, builder, nlex, sentences = _native_setup(name)
+    kw = case['decode_kwargs']
+    samples, top, rnd = kw.get('samples', 0), kw.get('top_sampling', False), kw.get('random_sampling', False)
+    frames = [builder.build(t) for t in sentences]
+    np.random.seed(99)
+    if mode == 1:
+        lists = [lattice.static_vocab(fr, len(vocab.w2i), samples, top, rnd) for fr in frames]
+        want = lattice.PackedLattices(frames, vocab_lists=lists)
+    else:
+        dyn = [lattice.dynamic_vocab(fr, len(vocab.w2i), samples, top, rnd) for fr in frames]
+        want = lattice.PackedLattices(frames, dynamic=dyn)
+    # the same draws, in the same per-sentence order, for the native builder
+    np.random.seed(99)
+    extra = None
+    if samples and rnd:
+        extra = np.stack([np.random.randint(len(vocab.w2i), size=samples) for _ in sentences]).astype(np.int32)
+    elif samples and top:
+        extra = np.tile(np.arange(samples, dtype=np.int32), (len(sentences), 1))
+    got = lattice.NativeLattices(nlex, sentences, mode, extra)
+    v = got.c_struct()
+    S = len(sentences)
+    assert [int(v.vocab_ptr[i]) for i in range(S + 1)] == want.vocab_ptr.tolist()
+    n = int(want.vocab_ptr[-1])
+    assert [int(v.vocab_ids[i]) for i in range(n)] == want.vocab_ids.tolist()
+    if mode == 2:
+        nf = len(want.vocab_frame_ptr)
+        assert [int(v.vocab_frame_ptr[i]) for i in range(nf)] == want.vocab_frame_ptr.tolist()
+        assert [int(v.dup_ptr[i]) for i in range(S + 1)] == want.dup_ptr.tolist()
+        nd = int(want.dup_ptr[-1])
+        assert [int(v.dup_ids[i]) for i in range(nd)] == want.dup_ids.tolist()[:nd]
+    else:
+        assert got.vocab_list(S - 1) == lists[-1]
+
+
+def test_native_lexicon_rejects_bad_input():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rptr = np.array([0, 1, 2], dtype=np.int64)
+    chars = np.array([0x30A2, 0x30A2], dtype=np.uint32)          # the same reading twice
+    wptr = np.array([0, 1, 2], dtype=np.int64)
+    wids = np.array([2, 3], dtype=np.int32)
+    rc = lib.jlm_lexicon_create(2, _lib.ptr(rptr, ctypes.c_int64), _lib.ptr(chars, ctypes.c_uint32),
+                                _lib.ptr(wptr, ctypes.c_int64), _lib.ptr(wids, ctypes.c_int32), 1, 0, ctypes.byref(h))
+    assert rc != 0 and b'duplicate reading' in lib.jlm_last_error()

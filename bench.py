@@ -31,9 +31,34 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-WORKLOAD = 'cfg2: V=50000 H=512 E=256 tied standard softmax, beam=10, topN=10, >=20 kana/sentence'
-V, H, E, BEAM, TOPN, MIN_LEN = 50000, 512, 256, 10, 10, 20
 METRIC = 'kana chars/sec decoded at V=50k H=512 beam=10'
+MIN_LEN = 20
+# BASELINE.json configs[1..4]; configs[1] (cfg2) is the one the metric is quoted on and the default.
+WORKLOADS = {
+    'cfg2': dict(desc='cfg2: V=50000 H=512 E=256 tied standard softmax, beam=10, topN=10, >=20 kana/sentence',
+                 V=50000, H=512, E=256, mode='tied', segments=None, beam=10, topn=10, dynamic=False),
+    'cfg3': dict(desc='cfg3: V=50000 H=512 D-softmax* segs (200,0,12k)/(100,12k,30k)/(50,30k,50k), beam=10',
+                 V=50000, H=512, E=256, mode='dsoftmax_star',
+                 segments=[[200, 0, 12000], [100, 12000, 30000], [50, 30000, None]], beam=10, topn=10, dynamic=False),
+    'cfg4': dict(desc='cfg4: V=50000 H=512 E=256 tied, DynamicDecoder (incremental vocab, samples=200 top), beam=20',
+                 V=50000, H=512, E=256, mode='tied', segments=None, beam=20, topn=10, dynamic=True, samples=200),
+    'cfg5': dict(desc='cfg5: V=100000 H=1024 D-softmax* segs (256,0,4k)/(128,4k,12k)/(64,12k,100k), beam=50',
+                 V=100000, H=1024, E=256, mode='dsoftmax_star',
+                 segments=[[256, 0, 4000], [128, 4000, 12000], [64, 12000, None]], beam=50, topn=10, dynamic=False),
+}
+
+
+def flops_per_row(wl):
+    """Algorithmic flops of one LM row: (gate GEMM, full-vocabulary output GEMMs)."""
+    V, H = wl['V'], wl['H']
+    if wl['mode'] == 'dsoftmax_star':
+        segs = [(sz, s, V if e is None else e) for sz, s, e in wl['segments']]
+        e_in = segs[0][0]
+        proj = sum(2.0 * sz * (e - s) for sz, s, e in segs)
+    else:
+        e_in = wl['E']
+        proj = 2.0 * wl['E'] * V
+    return 2.0 * (e_in + H) * 4 * H, proj
 
 
 def peaks():
@@ -44,11 +69,33 @@ def peaks():
     return 1400.0, 1590.0, 6650.0, 'fallback'
 
 
-def make_inputs(root, n_sent, seed):
+def make_inputs(root, wl, n_sent, seed):
     from jlm_b200 import synth
-    cfg, weights, lexicon, reading_dict = synth.make_experiment(root, 1, V, H, E, 'tied', seed=0)
-    sents = synth.make_sentences(lexicon, n_sent, min_len=MIN_LEN, seed=seed, vocab_size=V)
+    cfg, weights, lexicon, reading_dict = synth.make_experiment(root, 1, wl['V'], wl['H'], wl['E'], wl['mode'],
+                                                                segments=wl['segments'], seed=0)
+    sents = synth.make_sentences(lexicon, n_sent, min_len=MIN_LEN, seed=seed, vocab_size=wl['V'])
     return cfg, weights, lexicon, reading_dict, sents
+
+
+def oracle_decoder(wl, cfg, weights, lexicon, reading_dict):
+    """(prepare(text) -> state, run(state) -> n-best): the CPU oracle split so that only the
+    lattice -> n-best region is timed (decode() minus _build_lattice)."""
+    from oracle import jlm_oracle as O
+    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict, dynamic=wl['dynamic'])
+
+    def prepare(text):
+        fr = O.build_lattice(text, ora.w2i, lexicon, reading_dict)
+        if wl['dynamic']:
+            return fr, O.dynamic_lattice_vocab(fr, len(ora.w2i), wl['samples'], True, False)
+        return fr, None
+
+    def run(state):
+        fr, lv = state
+        if wl['dynamic']:
+            return O.decode_dynamic(ora.model, fr, {k: list(v) for k, v in lv.items()}, wl['topn'], wl['beam'])
+        return O.decode_static(ora.model, fr, wl['topn'], wl['beam'], None)
+
+    return prepare, run
 
 
 class ClockSampler(threading.Thread):
@@ -94,17 +141,19 @@ def run_reference(args, rank, world):
     itself cannot travel to the GPU box) on the host cores, bounded sample of the same workload."""
     if rank != 0:
         return
-    from oracle import jlm_oracle as O
+    wl = WORKLOADS[args.workload]
+    TOPN, BEAM = wl['topn'], wl['beam']
+    WORKLOAD = wl['desc']
     root = tempfile.mkdtemp(prefix='jlm_bench_ref_')
     n = max(1, args.ref_sentences)
-    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, n, seed=1)
-    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict)
-    frames = [O.build_lattice(s, ora.w2i, lexicon, reading_dict) for s in sents]
+    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, wl, n, seed=100)
+    prepare, run = oracle_decoder(wl, cfg, weights, lexicon, reading_dict)
+    states = [prepare(s) for s in sents]
     chars = sum(len(s) for s in sents)
 
     def step():
-        for fr in frames:
-            O.decode_static(ora.model, fr, TOPN, BEAM, None)
+        for st in states:
+            run(st)
 
     for _ in range(args.warmup if args.warmup < 2 else 1):
         step()
@@ -134,6 +183,7 @@ def main():
     ap.add_argument('--ref-sentences', type=int, default=8)
     ap.add_argument('--cpu-baseline-sentences', type=int, default=32)
     ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--profile', action='store_true', help='1 warm-up + K plain steps only (for ncu); prints no JSON')
     args = ap.parse_args()
 
@@ -156,16 +206,21 @@ def main():
     import jlm_b200
     from jlm_b200 import _lib, config, lattice
     lib = _lib.load()
+    wl = WORKLOADS[args.workload]
+    TOPN, BEAM, WORKLOAD = wl['topn'], wl['beam'], wl['desc']
+    MODE = _lib.DECODE_DYNAMIC if wl['dynamic'] else _lib.DECODE_FULL
     root = tempfile.mkdtemp(prefix='jlm_bench_r%d_' % rank)
-    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, args.sentences, seed=100 + rank)
+    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, wl, args.sentences, seed=100 + rank)
     config.set_root(root)
-    dec = jlm_b200.Decoder(1, device=local)
+    dec = (jlm_b200.DynamicDecoder if wl['dynamic'] else jlm_b200.Decoder)(1, device=local)
+    extra = np.tile(np.arange(wl['samples'], dtype=np.int32), (len(sents), 1)) if wl['dynamic'] else None
+    n_extra = wl['samples'] if wl['dynamic'] else 0
     hdl = dec.model._handle
     stream = torch.cuda.current_stream()
     _lib.check(lib.jlm_set_stream(hdl, C.c_void_p(stream.cuda_stream)))
     nlex = dec._native()
     t_lat = time.perf_counter()
-    packed = lattice.NativeLattices(nlex, sents)          # jlm_lattice_build (host C++)
+    packed = lattice.NativeLattices(nlex, sents, MODE, extra)          # jlm_lattice_build (host C++)
     t_lat = time.perf_counter() - t_lat
     lb = packed.c_struct()
     chars = sum(len(s) for s in sents)
@@ -202,7 +257,7 @@ def main():
 
     # ---------------- device-resident arm: lattices uploaded once, K timed runs ----------------
     batch = C.c_void_p()
-    _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(batch)))
+    _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(batch)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
     if args.profile:
         for _ in range(1 + args.steps):
@@ -264,10 +319,10 @@ def main():
     def e2e_step():
         lat = C.c_void_p()
         _lib.check(lib.jlm_lattice_build(nlex.handle, len(sents), _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
-                                         _lib.DECODE_FULL, 0, None, C.byref(lat)))
+                                         MODE, n_extra, _lib.ptr(extra, C.c_int32) if n_extra else None, C.byref(lat)))
         view = _lib.LatticeBatch()
         _lib.check(lib.jlm_lattice_view(lat, C.byref(view), None, None))
-        _lib.check(lib.jlm_decode_batch(hdl, C.byref(view), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(nb)))
+        _lib.check(lib.jlm_decode_batch(hdl, C.byref(view), BEAM, TOPN, MODE, args.backend, C.byref(nb)))
         _lib.check(lib.jlm_lattice_destroy(lat))
 
     ref_nodes = path_nodes.copy()
@@ -285,7 +340,7 @@ def main():
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
     # one more upload to read the byte counters of a single call
     b2 = C.c_void_p()
-    _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, _lib.DECODE_FULL, args.backend, C.byref(b2)))
+    _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(b2)))
     _lib.check(lib.jlm_batch_run(b2))
     _lib.check(lib.jlm_batch_fetch(b2, C.byref(nb)))
     i2 = _lib.BatchInfo()
@@ -298,9 +353,8 @@ def main():
         return
 
     sus, burst, hbm, src = peaks()
-    # algorithmic flops per LM row: gate 2*(E+H)*4H ; projection 2*H*E + 2*E*V
-    f_gate_row = 2.0 * (E + H) * 4 * H
-    f_proj_row = 2.0 * E * V
+    # algorithmic flops per LM row: gate 2*(E+H)*4H ; full-vocabulary output GEMMs
+    f_gate_row, f_proj_row = flops_per_row(wl)
     rows_total = rows_stepped * args.steps
     traffic = None
     tp = os.path.join(REPO, 'profiles', 'traffic.json')
@@ -318,17 +372,23 @@ def main():
         roof['gate'] = {'kernel': 'k_tc_gemm<256,EPI_LSTM> (gate GEMM + LSTM epilogue)', 'achieved': g_ach,
                         'frac': g_ach / sus if g_ach else None, 'issued_frac': 3 * g_ach / sus if g_ach else None,
                         'avg_launch_ms': gate_ms / max(n_gate, 1), 'launches': n_gate}
+    elif gate_ms > 0 and args.backend == 2:
+        # vocabulary-selection workloads have no full-vocabulary GEMM: the gate GEMM is the tensor kernel
+        g_ach = f_gate_row * rows_total / (gate_ms * 1e-3) / 1e12
+        roof.update({'kernel': 'k_tc_gemm<256,EPI_LSTM> (gate GEMM + LSTM epilogue)', 'achieved': g_ach,
+                     'frac': g_ach / sus, 'issued_frac': 3 * g_ach / sus, 'traffic': None,
+                     'flops_per_launch': f_gate_row * rows_total / max(n_gate, 1),
+                     'avg_launch_ms': gate_ms / max(n_gate, 1), 'launches': n_gate})
     else:
         roof.update({'achieved': None, 'frac': None})
 
     # ---------------- CPU baseline: oracle port on a bounded sample of the same workload ----------------
-    from oracle import jlm_oracle as O
     nb_cpu = max(1, min(args.cpu_baseline_sentences, len(sents)))
-    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict)
+    prepare, run_cpu = oracle_decoder(wl, cfg, weights, lexicon, reading_dict)
     sub = sents[:nb_cpu]
-    ofr = [O.build_lattice(s, ora.w2i, lexicon, reading_dict) for s in sub]
+    states = [prepare(s) for s in sub]
     t0 = time.perf_counter()
-    cpu_out = [O.decode_static(ora.model, fr, TOPN, BEAM, None) for fr in ofr]
+    cpu_out = [run_cpu(st) for st in states]
     cpu_s = time.perf_counter() - t0
     cpu_chars = sum(len(s) for s in sub)
     # parity spot-check of the timed GPU output against the oracle on the same sentences

@@ -12,7 +12,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/jlm_b200.h"
@@ -36,6 +38,8 @@ struct jlm_lexicon {
   std::vector<int64_t> word_ptr;      // [n+1] into word_ids; entry index == position in word_ids
   std::vector<int32_t> word_ids;
   std::vector<int32_t> table;         // open addressing, -1 = empty, else reading index
+  std::vector<uint32_t> tag;          // high hash bits of the slot's reading: rejects most misses without
+                                      // touching the reading itself
   uint64_t mask = 0;
 };
 
@@ -81,6 +85,7 @@ extern "C" int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading
   while (cap < (uint64_t)n_readings * 2 + 2) cap <<= 1;
   L->mask = cap - 1;
   L->table.assign(cap, -1);
+  L->tag.assign(cap, 0);
   for (int32_t r = 0; r < n_readings; ++r) {
     const int64_t a = L->reading_ptr[r], b = L->reading_ptr[r + 1];
     if (b < a || L->word_ptr[r + 1] < L->word_ptr[r]) {
@@ -103,6 +108,7 @@ extern "C" int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading
       s = (s + 1) & L->mask;
     }
     L->table[s] = r;
+    L->tag[s] = (uint32_t)(h >> 32);
   }
   *out = L;
   return 0;
@@ -113,29 +119,27 @@ extern "C" int32_t jlm_lexicon_destroy(jlm_lexicon* lex) {
   return 0;
 }
 
-extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const int64_t* text_ptr,
-                                     const uint32_t* text, int32_t mode, int32_t n_extra, const int32_t* extra_ids,
-                                     jlm_lattice** out) {
-  LAT_REQUIRE(L && out && n_sent > 0 && text_ptr, "jlm_lattice_build: bad argument");
-  LAT_REQUIRE(mode >= JLM_DECODE_FULL && mode <= JLM_DECODE_DYNAMIC, "jlm_lattice_build: bad mode %d", mode);
-  LAT_REQUIRE(n_extra >= 0 && (n_extra == 0 || extra_ids), "jlm_lattice_build: extra ids missing");
-  *out = nullptr;
-  jlm_lattice* lat = new jlm_lattice();
-  lat->n_sent = n_sent;
-  lat->mode = mode;
-  lat->sent_len.resize(n_sent);
-  lat->frame_ptr_off.resize(n_sent);
-  if (mode != JLM_DECODE_FULL) lat->vocab_ptr.assign(1, 0);
-  if (mode == JLM_DECODE_DYNAMIC) lat->dup_ptr.assign(1, 0);
+namespace {
 
+// Builds sentences [s_lo, s_hi) into `lat` with node / vocabulary offsets relative to this chunk.
+int32_t build_range(const jlm_lexicon* L, int32_t s_lo, int32_t s_hi, const int64_t* text_ptr, const uint32_t* text,
+                    int32_t mode, int32_t n_extra, const int32_t* extra_ids, jlm_lattice* lat, char* err, size_t errn) {
   struct Tmp { int32_t start, word, entry; };
   std::vector<std::vector<Tmp>> frames;
   std::vector<int32_t> scratch, seen_sorted, fresh;
-  for (int32_t s = 0; s < n_sent; ++s) {
+  if (mode != JLM_DECODE_FULL) lat->vocab_ptr.assign(1, 0);
+  if (mode == JLM_DECODE_DYNAMIC) lat->dup_ptr.assign(1, 0);
+  {
+    const size_t chars = (size_t)(text_ptr[s_hi] - text_ptr[s_lo]);
+    lat->node_start.reserve(chars * 12);
+    lat->node_word.reserve(chars * 12);
+    lat->node_entry.reserve(chars * 12);
+    lat->frame_ptr.reserve(chars + 2 * (size_t)(s_hi - s_lo));
+  }
+  for (int32_t s = s_lo; s < s_hi; ++s) {
     const int64_t t0 = text_ptr[s], t1 = text_ptr[s + 1];
     if (t1 < t0 || t1 - t0 > (int64_t)1 << 24) {
-      delete lat;
-      jlm_set_error("jlm_lattice_build: bad text offsets for sentence %d", s);
+      snprintf(err, errn, "jlm_lattice_build: bad text offsets for sentence %d", s);
       return 1;
     }
     const int32_t T = (int32_t)(t1 - t0);
@@ -149,10 +153,12 @@ extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const
       for (int32_t j = 0; j < jmax; ++j) {
         h = fnv_step(h, tx[i + j]);
         uint64_t slot = h & L->mask;
+        const uint32_t tg = (uint32_t)(h >> 32);
         while (L->table[slot] >= 0) {
           const int32_t q = L->table[slot];
-          const int64_t qa = L->reading_ptr[q];
-          if (L->reading_ptr[q + 1] - qa == j + 1 && memcmp(&L->chars[qa], tx + i, sizeof(uint32_t) * (j + 1)) == 0) {
+          const int64_t qa = L->tag[slot] == tg ? L->reading_ptr[q] : 0;
+          if (L->tag[slot] == tg && L->reading_ptr[q + 1] - qa == j + 1 &&
+              memcmp(&L->chars[qa], tx + i, sizeof(uint32_t) * (j + 1)) == 0) {
             std::vector<Tmp>& end = frames[i + j + 1];
             for (int64_t e = L->word_ptr[q]; e < L->word_ptr[q + 1]; ++e)   // lexicon-id order, OOV already dropped
               end.push_back({i, L->word_ids[e], (int32_t)e});
@@ -165,8 +171,8 @@ extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const
       if (jmax == 0 && frames[i + 1].empty()) frames[i + 1].push_back({i, L->unk_id, -2});
     }
     // CSR
-    lat->sent_len[s] = T;
-    lat->frame_ptr_off[s] = (int64_t)lat->frame_ptr.size();
+    lat->sent_len.push_back(T);
+    lat->frame_ptr_off.push_back((int64_t)lat->frame_ptr.size());
     lat->frame_ptr.push_back((int64_t)lat->node_word.size());
     for (int32_t t = 0; t <= T; ++t) {
       for (const Tmp& n : frames[t]) {
@@ -197,16 +203,13 @@ extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const
       for (int32_t k = 0; k < n_extra; ++k) scratch.push_back(extra[k]);
       seen_sorted = scratch;
       std::sort(seen_sorted.begin(), seen_sorted.end());
-      // duplicates: every occurrence beyond the first, in list order
-      {
-        std::vector<int32_t> uniq = seen_sorted;
-        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-        std::vector<char> used(uniq.size(), 0);
+      seen_sorted.erase(std::unique(seen_sorted.begin(), seen_sorted.end()), seen_sorted.end());
+      {  // duplicates: every occurrence beyond the first, in list order
+        std::vector<char> used(seen_sorted.size(), 0);
         for (int32_t v : scratch) {
-          const size_t k = std::lower_bound(uniq.begin(), uniq.end(), v) - uniq.begin();
+          const size_t k = std::lower_bound(seen_sorted.begin(), seen_sorted.end(), v) - seen_sorted.begin();
           if (used[k]) lat->dup_ids.push_back(v); else used[k] = 1;
         }
-        seen_sorted.swap(uniq);
       }
       const int64_t base = (int64_t)lat->vocab_ids.size();
       lat->vocab_ids.insert(lat->vocab_ids.end(), seen_sorted.begin(), seen_sorted.end());
@@ -228,6 +231,76 @@ extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const
       lat->dup_ptr.push_back((int64_t)lat->dup_ids.size());
     }
   }
+  return 0;
+}
+
+template <class T>
+void append(std::vector<T>& dst, const std::vector<T>& src, T add, size_t skip = 0) {
+  const size_t o = dst.size();
+  dst.resize(o + src.size() - skip);
+  for (size_t i = skip; i < src.size(); ++i) dst[o + i - skip] = src[i] + add;
+}
+
+}  // namespace
+
+extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const int64_t* text_ptr,
+                                     const uint32_t* text, int32_t mode, int32_t n_extra, const int32_t* extra_ids,
+                                     jlm_lattice** out) {
+  LAT_REQUIRE(L && out && n_sent > 0 && text_ptr, "jlm_lattice_build: bad argument");
+  LAT_REQUIRE(mode >= JLM_DECODE_FULL && mode <= JLM_DECODE_DYNAMIC, "jlm_lattice_build: bad mode %d", mode);
+  LAT_REQUIRE(n_extra >= 0 && (n_extra == 0 || extra_ids), "jlm_lattice_build: extra ids missing");
+  *out = nullptr;
+  // sentences are independent: build contiguous chunks on host threads, then concatenate
+  int nthreads = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("JLM_HOST_THREADS")) nthreads = atoi(e);
+  nthreads = std::max(1, std::min(std::min(nthreads, 8), n_sent / 512));
+  std::vector<jlm_lattice> part(nthreads);
+  std::vector<int32_t> rc(nthreads, 0);
+  std::vector<std::vector<char>> err(nthreads, std::vector<char>(256, 0));
+  auto work = [&](int k) {
+    const int32_t lo = (int32_t)((int64_t)n_sent * k / nthreads), hi = (int32_t)((int64_t)n_sent * (k + 1) / nthreads);
+    rc[k] = build_range(L, lo, hi, text_ptr, text, mode, n_extra, extra_ids, &part[k], err[k].data(), err[k].size());
+  };
+  if (nthreads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nthreads; ++k) th.emplace_back(work, k);
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < nthreads; ++k)
+    if (rc[k]) {
+      jlm_set_error("%s", err[k].data());
+      return 1;
+    }
+  jlm_lattice* lat = new jlm_lattice();
+  if (nthreads == 1) {
+    *lat = std::move(part[0]);
+  } else {
+    if (mode != JLM_DECODE_FULL) lat->vocab_ptr.assign(1, 0);
+    if (mode == JLM_DECODE_DYNAMIC) lat->dup_ptr.assign(1, 0);
+    for (int k = 0; k < nthreads; ++k) {
+      const jlm_lattice& p = part[k];
+      const int64_t node0 = (int64_t)lat->node_word.size(), fp0 = (int64_t)lat->frame_ptr.size();
+      append(lat->sent_len, p.sent_len, 0);
+      append(lat->frame_ptr_off, p.frame_ptr_off, fp0);
+      append(lat->frame_ptr, p.frame_ptr, node0);
+      append(lat->node_start, p.node_start, 0);
+      append(lat->node_word, p.node_word, 0);
+      append(lat->node_entry, p.node_entry, 0);
+      if (mode != JLM_DECODE_FULL) {
+        append(lat->vocab_ptr, p.vocab_ptr, (int64_t)lat->vocab_ids.size(), 1);
+        append(lat->vocab_ids, p.vocab_ids, 0);
+      }
+      if (mode == JLM_DECODE_DYNAMIC) {
+        append(lat->vocab_frame_ptr, p.vocab_frame_ptr, 0);
+        append(lat->dup_ptr, p.dup_ptr, (int64_t)lat->dup_ids.size(), 1);
+        append(lat->dup_ids, p.dup_ids, 0);
+      }
+    }
+  }
+  lat->n_sent = n_sent;
+  lat->mode = mode;
   if (mode == JLM_DECODE_DYNAMIC && lat->dup_ids.empty()) lat->dup_ids.push_back(0);   // keep the pointer non-null
   *out = lat;
   return 0;

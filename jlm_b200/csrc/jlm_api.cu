@@ -282,7 +282,7 @@ int32_t dev_project(jlm_handle* h, const double* d_hidden, int B, const int32_t*
     JLM_TRY(h->scratch[S_PART].reserve(sizeof(SubsetJob)));
     SubsetJob* d_job = h->scratch[S_PART].as<SubsetJob>();
     JLM_CUDA(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, h->stream));
-    JLM_TRY(subset_logits<double>(h->stream, h, T, ldt, d_job, 1, n_cols, d_cols, d_bias, d_y, 1));
+    JLM_TRY(subset_logits<double>(h->stream, h, T, ldt, d_job, 1, n_cols, d_cols, d_bias, d_y));
     if (d_lse) JLM_TRY(exact_rows_lse(h->stream, d_y, n_cols, B, n_cols, d_lse));
   }
   return 0;

@@ -90,6 +90,7 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
         const double y = acc[r] + bias;
         const int64_t ps = ps0 + r0 + r;
         d.cand_val[cpos + r0 + r] = DYN ? y : d.slot_score[ps] + ((use_lse ? d.slot_lse[ps] : 0.0) - y);
+        if (DYN) d.cand_parent[cpos + r0 + r] = (int32_t)ps;
       }
     }
   }
@@ -115,37 +116,11 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
   const int nc = d.frame_ncand[fid];
   const double* val = d.cand_val + c0;
 
-  if (DYN) {
-    // _fix_neg_log (decoder_dynamic.py:150-175): every ancestor transition is re-scored with the
-    // softmax over lattice_vocab[t]; sum the ancestors' LSEs once per potential parent ...
-    if (use_lse) {
-      for (int pf = d.frame_minpf[fid]; pf < fid; ++pf) {
-        const int pc = d.bc[pf];
-        const int64_t ps0 = d.slot0[pf];
-        for (int r = lane; r < pc; r += 32) {
-          double sum = 0.0;
-          int a = (int)(ps0 + r);
-          while (a >= 0) {
-            sum += d.dyn_lse[(int64_t)a * tstride + t];
-            a = d.slot_parent[a];
-          }
-          d.dyn_chain[ps0 + r] = sum;
-        }
-      }
-      __syncwarp();
-    }
-    // ... then the candidates' scores: sum of LSEs minus sum of logits along the path
-    for (int n = lo; n < hi; ++n) {
-      const int pf = d.node_pfid[n];
-      const int pc = d.bc[pf];
-      const int64_t ps0 = d.slot0[pf];
-      const int64_t cp = d.cand_pos[n];
-      for (int r = lane; r < pc; r += 32)
-        d.cand_sc[cp + r] = (use_lse ? d.dyn_chain[ps0 + r] : 0.0) - (d.slot_cumy[ps0 + r] + d.cand_val[cp + r]);
-    }
-    __syncwarp();
-    val = d.cand_sc + c0;
-  }
+  // DYN, _fix_neg_log (decoder_dynamic.py:150-175): every ancestor transition is re-scored with the
+  // softmax over lattice_vocab[t].  dyn_chain[slot][t] already holds the sum of the path's LSEs under
+  // that vocabulary (accumulated parent-to-child by k_dyn_prefix_lse), so a candidate's score is
+  // (sum of LSEs) - (sum of logits) along its path, formed here from its parent slot.
+  const int32_t* cpar = DYN ? d.cand_parent + c0 : nullptr;
 
   double es[L];
   int ec[L];
@@ -163,7 +138,15 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int c = base + u * 32 + lane;
-      v[u] = c < nc ? val[c] : INFINITY;
+      v[u] = INFINITY;
+      if (c < nc) {
+        if (DYN) {
+          const int par = cpar[c];
+          v[u] = (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + val[c]);
+        } else {
+          v[u] = val[c];
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -279,7 +262,7 @@ k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv
 __global__ void __launch_bounds__(128)
 k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restrict__ info,
                  const int32_t* __restrict__ vfp, const double* __restrict__ yv, double* __restrict__ dyn_lse,
-                 int64_t slot_base, int k, int tstride) {
+                 double* dyn_chain, const int32_t* __restrict__ slot_parent, int64_t slot_base, int k, int tstride) {
   const SubsetJob job = jobs[blockIdx.y];
   const DynJobInfo inf = info[blockIdx.y];
   const int lane = threadIdx.x & 31;
@@ -287,6 +270,7 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
   if (r >= job.rows) return;
   const double* p = yv + job.out0 + (int64_t)r * job.ncols;
   const int64_t slot = slot_base + job.row0 + r;
+  const int par = slot_parent[slot];
   double M = -INFINITY, Ssum = 0.0;
   int pos = 0;
   for (int i = k + 1; i <= inf.T; ++i) {
@@ -309,7 +293,12 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
       M = nm;
     }
     pos = end;
-    if (lane == 0) dyn_lse[slot * tstride + i] = M + log(Ssum);
+    if (lane == 0) {
+      const double lse = M + log(Ssum);
+      dyn_lse[slot * tstride + i] = lse;
+      // sum of this path's LSEs under lattice_vocab[i]; the parent was stepped at an earlier frame
+      dyn_chain[slot * tstride + i] = (par >= 0 ? dyn_chain[(int64_t)par * tstride + i] : 0.0) + lse;
+    }
   }
 }
 
@@ -553,12 +542,13 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   d.slot_parent = a.take<int32_t>(ns);
   d.slot_node = a.take<int32_t>(ns);
   d.slot_word = a.take<int32_t>(ns);
-  d.slot_cumy = d.dyn_lse = d.dyn_chain = d.cand_sc = nullptr;
+  d.slot_cumy = d.dyn_lse = d.dyn_chain = nullptr;
+  d.cand_parent = nullptr;
   const size_t ncd = (size_t)std::max<int64_t>(b->n_cand, 1);
   if (b->dynamic) {
-    d.cand_sc = a.take<double>(ncd);
+    d.cand_parent = a.take<int32_t>(ncd);
     d.slot_cumy = a.take<double>(ns);
-    d.dyn_chain = a.take<double>(ns);
+    d.dyn_chain = a.take<double>(ns * (size_t)(b->Tmax + 1));
     d.dyn_lse = a.take<double>(ns * (size_t)(b->Tmax + 1));
   }
   d.cand_val = a.take<double>(ncd);
@@ -596,11 +586,11 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
   BeamDev& d = b->d;
   if (b->use_lse && b->mode != JLM_DECODE_FULL) {
     JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.vocab_jobs + sp.job0, sp.nstep, sp.max_vocab_cols, d.vocab_cols, nullptr,
-                              b->yv, 1));
+                              b->yv));
     dim3 grid(ceil_div(b->W, 4), sp.nstep);
     if (b->dynamic)
       k_dyn_prefix_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse,
-                                             sp.row0, t, b->Tmax + 1);
+                                             d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1);
     else
       k_job_rows_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0);
     JLM_CUDA(cudaGetLastError());

@@ -44,14 +44,14 @@ struct BeamDev {
   double* slot_lse = nullptr;
   double* slot_cumy = nullptr;      // dynamic: sum of the path's logits
   double* dyn_lse = nullptr;        // dynamic: [slot, Tmax+1] LSE over lattice_vocab[i]
-  double* dyn_chain = nullptr;      // dynamic: per-slot chain sums for the frame being expanded
+  double* dyn_chain = nullptr;      // dynamic: [slot, Tmax+1] sum of the path's LSEs over lattice_vocab[i]
   int32_t* slot_parent = nullptr;   // global slot of the parent, -1 for <eos>
   int32_t* slot_node = nullptr;
   int32_t* slot_word = nullptr;
   // candidates, contiguous per (sentence, frame) in the reference's enumeration order
   // (node order, then parent rank): candidate cand_pos[n] + r extends parent rank r with node n
   double* cand_val = nullptr;       // static: full path score ; dynamic: the transition's logit
-  double* cand_sc = nullptr;        // dynamic only: score under the current frame's softmaxes
+  int32_t* cand_parent = nullptr;   // dynamic only: global slot of the candidate's parent path
   // ---- n-best output ----
   double* out_score = nullptr;
   int32_t* out_npaths = nullptr;

@@ -188,8 +188,7 @@ int32_t exact_gather_gate_input(cudaStream_t st, const jlm_handle* h, const doub
 int32_t exact_lstm_pointwise(cudaStream_t st, const jlm_handle* h, const double* gates, const double* c_src,
                              const int32_t* parent, int M, double* h_out, double* c_out);
 
-// y[r, j] for selected words: out[job.out0 + j*job.rows + r] (col-major per job, "node logits")
-// or row-major [r, j] when row_major != 0.
+// y[r, j] for selected words, row-major per job: out[job.out0 + r*job.ncols + j]
 struct SubsetJob {
   int64_t row0;      // first T row
   int32_t rows;
@@ -199,8 +198,7 @@ struct SubsetJob {
 };
 template <typename TT>
 int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t ldt, const SubsetJob* jobs,
-                      int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out,
-                      int row_major);
+                      int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out);
 
 // ---------------------------------------------------------------- tensor-core back end (jlm_tc.cu)
 int32_t tc_prepare_weights(jlm_handle* h);

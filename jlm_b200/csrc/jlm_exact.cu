@@ -201,57 +201,91 @@ __global__ void k_lstm_pointwise(const double* __restrict__ gates, const double*
   }
 }
 
-constexpr int SUB_RC = 8;        // rows accumulated per pass
-constexpr int SUB_WARPS = 8;     // warps per CTA, one column per warp per iteration
+// Logits of a word subset for the rows of a job (LSTM_Model.project with `vocab`, decoder/model.py:
+// 144-193): out[job.out0 + r*ncols + j] = T[row0+r] . W[cols[j]] + b2[bias_idx[j]], float64
+// accumulation.  One CTA = 128 columns of one job: thread = column (its word row of the output block
+// staged in shared memory, K in chunks of 32), all rows of the job accumulate in registers against
+// broadcast reads of the shared T chunk - no cross-lane reduction.  Columns of different segments
+// (different K slice of T) are handled in separate passes.
+constexpr int VL_COLS = 128;    // columns (= threads) per CTA
+constexpr int VL_KC = 32;       // K chunk (float4 per row: VL_KC/4)
+constexpr int VL_RC = 32;       // rows accumulated per pass
 
 template <typename TT>
-__global__ void __launch_bounds__(SUB_WARPS * 32)
-k_subset_logits(SegTable seg, const TT* __restrict__ T, int64_t ldt, const SubsetJob* __restrict__ jobs,
-                const int32_t* __restrict__ cols, const int32_t* __restrict__ bias_idx,
-                const float* __restrict__ b2, double* __restrict__ out, int row_major) {
+__global__ void __launch_bounds__(VL_COLS)
+k_vocab_logits(SegTable seg, const TT* __restrict__ T, int64_t ldt, const SubsetJob* __restrict__ jobs,
+               const int32_t* __restrict__ cols, const int32_t* __restrict__ bias_idx,
+               const float* __restrict__ b2, double* __restrict__ out) {
+  __shared__ __align__(16) double Ts[VL_RC][VL_KC];
+  __shared__ __align__(16) float Ws[VL_COLS][VL_KC + 2];
+  __shared__ int32_t Wid[VL_COLS];
   const SubsetJob job = jobs[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  for (int j = blockIdx.x * SUB_WARPS + warp; j < job.ncols; j += gridDim.x * SUB_WARPS) {
-    const int w = cols[job.col0 + j];
-    const int bw = bias_idx ? bias_idx[job.col0 + j] : w;
-    int s = 0;
+  const int c0 = blockIdx.x * VL_COLS;
+  if (c0 >= job.ncols) return;
+  const int tid = threadIdx.x;
+  const int j = c0 + tid;
+  const bool valid = j < job.ncols;
+  const int w = valid ? cols[job.col0 + j] : -1;
+  int myseg = -1;
+  if (valid) {
+    myseg = 0;
 #pragma unroll
     for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
-      if (i < seg.n && w >= seg.start[i]) s = i;
-    const int kpad = seg.kpad[s];
-    const float* wrow = seg.W[s] + (int64_t)(w - seg.start[s]) * kpad;
-    const double bias = (double)b2[bw];
-    for (int r0 = 0; r0 < job.rows; r0 += SUB_RC) {
-      double acc[SUB_RC];
+      if (i < seg.n && w >= seg.start[i]) myseg = i;
+  }
+  Wid[tid] = w;
+  const double bias = valid ? (double)b2[bias_idx ? bias_idx[job.col0 + j] : w] : 0.0;
+  for (int r0 = 0; r0 < job.rows; r0 += VL_RC) {
+    const int nr = min(VL_RC, job.rows - r0);
+    double acc[VL_RC];
 #pragma unroll
-      for (int r = 0; r < SUB_RC; ++r) acc[r] = 0.0;
-      for (int k = lane * 4; k < kpad; k += 128) {
-        const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+    for (int r = 0; r < VL_RC; ++r) acc[r] = 0.0;
+    for (int s = 0; s < seg.n; ++s) {
+      if (!__syncthreads_or(myseg == s)) continue;
+      const int kpad = seg.kpad[s];
+      const int sstart = seg.start[s], send = seg.end[s];
+      const float* Wseg = seg.W[s];
+      for (int k0 = 0; k0 < kpad; k0 += VL_KC) {
+        for (int i = tid; i < nr * VL_KC; i += VL_COLS) {
+          const int r = i / VL_KC, k = i % VL_KC;
+          Ts[r][k] = (double)T[(job.row0 + r0 + r) * ldt + seg.koff[s] + k0 + k];
+        }
+        constexpr int QPR = VL_KC / 4;              // float4 per staged row
+        constexpr int RPI = VL_COLS / QPR;          // rows staged per iteration
+#pragma unroll 4
+        for (int it = 0; it < VL_COLS / RPI; ++it) {
+          const int c = it * RPI + tid / QPR, q = tid % QPR;
+          const int wc = Wid[c];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (wc >= sstart && wc < send)
+            v = *reinterpret_cast<const float4*>(Wseg + (int64_t)(wc - sstart) * kpad + k0 + q * 4);
+          float2* dst = reinterpret_cast<float2*>(&Ws[c][q * 4]);
+          dst[0] = make_float2(v.x, v.y);
+          dst[1] = make_float2(v.z, v.w);
+        }
+        __syncthreads();
+        if (myseg == s) {
+#pragma unroll 2
+          for (int k = 0; k < VL_KC; k += 2) {
+            const float2 wv = *reinterpret_cast<const float2*>(&Ws[tid][k]);
+            const double w0 = (double)wv.x, w1 = (double)wv.y;
 #pragma unroll
-        for (int r = 0; r < SUB_RC; ++r) {
-          if (r0 + r < job.rows) {
-            const TT* t = T + (job.row0 + r0 + r) * ldt + seg.koff[s] + k;
-            acc[r] = fma((double)t[0], (double)wv.x, acc[r]);
-            acc[r] = fma((double)t[1], (double)wv.y, acc[r]);
-            acc[r] = fma((double)t[2], (double)wv.z, acc[r]);
-            acc[r] = fma((double)t[3], (double)wv.w, acc[r]);
+            for (int r = 0; r < VL_RC; ++r) {
+              if (r < nr) {
+                const double2 t = *reinterpret_cast<const double2*>(&Ts[r][k]);
+                acc[r] = fma(t.x, w0, acc[r]);
+                acc[r] = fma(t.y, w1, acc[r]);
+              }
+            }
           }
         }
+        __syncthreads();
       }
+    }
+    if (valid) {
 #pragma unroll
-      for (int r = 0; r < SUB_RC; ++r) {
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-      }
-#pragma unroll
-      for (int r = 0; r < SUB_RC; ++r) {
-        if (lane == r && r0 + r < job.rows) {
-          const int64_t o = row_major ? job.out0 + (int64_t)(r0 + r) * job.ncols + j
-                                      : job.out0 + (int64_t)j * job.rows + (r0 + r);
-          out[o] = acc[r] + bias;
-        }
-      }
+      for (int r = 0; r < VL_RC; ++r)
+        if (r < nr) out[job.out0 + (int64_t)(r0 + r) * job.ncols + j] = acc[r] + bias;
     }
   }
 }
@@ -340,22 +374,19 @@ int32_t exact_lstm_pointwise(cudaStream_t st, const jlm_handle* h, const double*
 
 template <typename TT>
 int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t ldt, const SubsetJob* jobs,
-                      int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out,
-                      int row_major) {
+                      int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out) {
   if (n_jobs <= 0 || max_cols <= 0) return 0;
-  int gx = ceil_div(max_cols, SUB_WARPS);
-  if (gx > 64) gx = 64;
+  const int gx = ceil_div(max_cols, VL_COLS);
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
-    int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+    const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid(gx, nj);
-    k_subset_logits<TT><<<grid, SUB_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, jobs + j0, cols, bias_idx, h->b2,
-                                                         out, row_major);
+    k_vocab_logits<TT><<<grid, VL_COLS, 0, st>>>(make_seg_table(h), T, ldt, jobs + j0, cols, bias_idx, h->b2, out);
   }
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
 
 template int32_t subset_logits<double>(cudaStream_t, const jlm_handle*, const double*, int64_t, const SubsetJob*, int,
-                                       int, const int32_t*, const int32_t*, double*, int);
+                                       int, const int32_t*, const int32_t*, double*);
 template int32_t subset_logits<float>(cudaStream_t, const jlm_handle*, const float*, int64_t, const SubsetJob*, int,
-                                      int, const int32_t*, const int32_t*, double*, int);
+                                      int, const int32_t*, const int32_t*, double*);

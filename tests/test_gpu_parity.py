@@ -260,3 +260,20 @@ def test_full_size_batch_properties(tmp_path_factory):
             total += -np.log(pred[0, wid])
             prev = wid
         assert abs(total - best_score) < 1e-3, (si, total, best_score)
+
+
+def test_empty_and_all_unknown_inputs(tmp_path_factory):
+    """decode('') keeps only the <eos> path (decoder.py:224-241 with T=0); kana without any reading fall
+    back to '<unk>' nodes that carry the raw kana (decoder.py:129-130)."""
+    from oracle import jlm_oracle as O
+    dec, case, sentences = get_decoder('small_tied', tmp_path_factory)
+    _, cfg, weights, lexicon, reading_dict, _ = build_case('small_tied')
+    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict)
+    assert dec.decode('', backend=EXACT) == [(0.0, [])]
+    assert dec.decode_batch(['', sentences[0], ''], topN=2, beam_width=3, backend=EXACT)[0] == [(0.0, [])]
+    for text in ('ヰ', 'ヰヱヰ'):
+        got = dec.decode(text, topN=3, beam_width=3, backend=EXACT)
+        want = ora.decode(text, topN=3, beam_width=3)
+        assert [w for _, w in got] == [w for _, w in want] == [list(text)]
+        np.testing.assert_allclose([s for s, _ in got], [s for s, _ in want], rtol=0, atol=2e-5)
+        assert dec.decode_batch([text], topN=3, beam_width=3, backend=EXACT)[0] == got

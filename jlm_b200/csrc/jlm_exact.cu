@@ -108,6 +108,95 @@ k_gemm_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int 
   }
 }
 
+// Few rows in flight (one sentence: M <= beam rows): the GEMM is a weight stream.  One CTA = one
+// 64-column tile; thread = (column, quarter of K): it streams its quarter of the column's weight row
+// (every weight byte is read once) and accumulates all M rows in float64 registers against broadcast
+// reads of A, which sits in shared memory as doubles - no cross-lane reduction in the K loop.  The four
+// K-quarters are then summed through shared memory and the tile's (max, sum exp) partial is formed in
+// the CTA.  HBM/L2-bound: algorithmic bytes = N*K*sizeof(weight) per launch.
+// Two shapes: COLS=64, KG=4 when LSE partials are wanted (their tile is 64 columns) or N is large;
+// COLS=32, KG=16 for the small gate / stage-1 GEMMs, which need more CTAs and shorter K loops.
+template <typename TB, int MT, int COLS, int KG>
+__global__ void __launch_bounds__(COLS * KG)
+k_skinny_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
+             const float* __restrict__ bias, double* __restrict__ C, int64_t ldc, int M, int N, int K,
+             double2* __restrict__ part, int part_ld, int part_tile0) {
+  extern __shared__ __align__(16) double smem_sk[];
+  double* As = smem_sk;                                  // [M][K]
+  double* Ps = smem_sk + (size_t)M * K;                  // [KG][MT][COLS] partial sums, then values
+  constexpr int SK_THREADS = COLS * KG;
+  constexpr int VEC = 16 / sizeof(TB);                   // weights per 16-byte load: 4 floats or 2 doubles
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid * 2; i < M * K; i += SK_THREADS * 2) {
+    const int m = i / K, k = i % K;
+    *reinterpret_cast<double2*>(&As[i]) = *reinterpret_cast<const double2*>(A + (int64_t)m * lda + k);
+  }
+  __syncthreads();
+  const int g = warp / (COLS / 32);                      // K slice
+  const int c = (warp % (COLS / 32)) * 32 + lane;        // column inside the tile
+  const int n = blockIdx.x * COLS + c;
+  const int kq = K / KG;
+  double acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+  if (n < N) {
+    const TB* brow = B + (int64_t)n * ldb + g * kq;
+    const double* arow = As + g * kq;
+#pragma unroll 8
+    for (int k = 0; k < kq; k += VEC) {
+      double w[VEC];
+      if (sizeof(TB) == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(brow + k);
+        w[0] = v.x; w[1] = v.y; w[VEC - 2] = v.z; w[VEC - 1] = v.w;
+      } else {
+        const double2 v = *reinterpret_cast<const double2*>(brow + k);
+        w[0] = v.x; w[1] = v.y;
+      }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+#pragma unroll
+          for (int i = 0; i < VEC; i += 2) {
+            const double2 a2 = *reinterpret_cast<const double2*>(arow + m * K + k + i);
+            acc[m] = fma(a2.x, w[i], acc[m]);
+            acc[m] = fma(a2.y, w[i + 1], acc[m]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) Ps[(g * MT + m) * COLS + c] = acc[m];
+  __syncthreads();
+  // sum the K slices (fixed order): value (m, c) lands in Ps[m][c] of slice 0
+  for (int i = tid; i < M * COLS; i += SK_THREADS) {
+    const int m = i / COLS, cc = i % COLS;
+    const int nn = blockIdx.x * COLS + cc;
+    double v = -INFINITY;
+    if (nn < N) {
+      v = 0.0;
+#pragma unroll
+      for (int q = 0; q < KG; ++q) v += Ps[(q * MT + m) * COLS + cc];
+      if (bias) v += (double)bias[nn];
+      if (C) C[(int64_t)m * ldc + nn] = v;
+    }
+    if (COLS == BN) Ps[m * COLS + cc] = v;
+  }
+  if (COLS == BN && part) {
+    __syncthreads();
+    for (int m = warp; m < M; m += SK_THREADS / 32) {      // one warp per row: 64 columns, 2 per lane
+      const double v0 = Ps[m * BN + lane], v1 = Ps[m * BN + 32 + lane];
+      double mx = fmax(v0, v1);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      double sm = (v0 == -INFINITY ? 0.0 : exp(v0 - mx)) + (v1 == -INFINITY ? 0.0 : exp(v1 - mx));
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      if (lane == 0) part[(int64_t)m * part_ld + part_tile0 + blockIdx.x] = make_double2(mx, sm);
+    }
+  }
+}
+
 __global__ void k_lse_merge(const double2* __restrict__ part, int part_ld, int n_tiles, int M,
                             double* __restrict__ lse, int self_norm) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -297,12 +386,38 @@ int grid_1d(int64_t total, int block, int cap) {
   return (int)g;
 }
 
+template <typename TB, int MT>
+int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* bias, double* C,
+                      int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
+  static bool configured = false;
+  if (!configured) {
+    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const size_t smem = ((size_t)M * K + (size_t)64 * MT * 4) * sizeof(double);   // KG*COLS == 256 for both shapes... x2 below
+  if (part || N > 8192 || K % (16 * 4) != 0) {
+    k_skinny_f64<TB, MT, 64, 4><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld,
+                                                                   part_tile0);
+  } else {
+    const size_t smem2 = ((size_t)M * K + (size_t)16 * MT * 32) * sizeof(double);
+    k_skinny_f64<TB, MT, 32, 16><<<ceil_div(N, 32), 512, smem2, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, nullptr, 0, 0);
+  }
+  return 0;
+}
+
 template <typename TB>
 int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* bias, double* C,
                     int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
   JLM_REQUIRE(K % BK == 0 && lda % 2 == 0 && ldb % 4 == 0, "exact gemm: unaligned K=%d lda=%d ldb=%d", K, lda, ldb);
   if (M <= 0 || N <= 0) return 0;
-  if (M <= 16) {
+  if (M <= 16 && ((size_t)M * K + (size_t)16 * 16 * 32) * sizeof(double) <= 200 * 1024 && K % 16 == 0) {
+    // weight-streaming path for one sentence's rows
+    if (M <= 4) JLM_TRY((launch_skinny<TB, 4>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
+    else if (M <= 8) JLM_TRY((launch_skinny<TB, 8>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
+    else if (M <= 12) JLM_TRY((launch_skinny<TB, 12>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
+    else JLM_TRY((launch_skinny<TB, 16>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
+  } else if (M <= 16) {
     dim3 grid(ceil_div(N, BN), ceil_div(M, 16));
     k_gemm_f64<TB, 1><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
   } else if (M <= 32) {

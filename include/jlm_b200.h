@@ -89,6 +89,13 @@ int32_t jlm_abi_version(void);
  * `device`.  Fails (no fallback) when no CUDA device is usable. */
 int32_t jlm_create(const jlm_config* cfg, const jlm_weights* w, int32_t device, jlm_handle** out);
 int32_t jlm_destroy(jlm_handle* h);
+/* Optional 8-bit form of one output block (train/comp.py:20-48,69-80: k-means code + codebook, the
+ * reference's `comp_N/lstm_weights_comp_dump.pkl`): code is [seg_end-seg_start, seg_width] row-major,
+ * codebook has n_codes (<= 256) float32 centroids.  codebook[code] must reproduce the float32 block
+ * given to jlm_create bit for bit (checked), so results do not change; the few-rows-in-flight path then
+ * streams 1 byte per weight instead of 4 (decoder/model.py:74-76 only ever sees the decoded floats). */
+int32_t jlm_set_quantized_block(jlm_handle* h, int32_t segment, const uint8_t* code, const float* codebook,
+                                int32_t n_codes);
 /* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*), e.g.
  * torch.cuda.current_stream().cuda_stream so torch.cuda.Event timing sees the kernels. */
 int32_t jlm_set_stream(jlm_handle* h, void* cuda_stream);

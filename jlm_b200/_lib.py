@@ -57,6 +57,7 @@ SYMBOLS = {
     'jlm_abi_version': (C.c_int32, []),
     'jlm_create': (C.c_int32, [C.POINTER(Config), C.POINTER(Weights), C.c_int32, C.POINTER(_VP)]),
     'jlm_destroy': (C.c_int32, [_VP]),
+    'jlm_set_quantized_block': (C.c_int32, [_VP, C.c_int32, C.POINTER(C.c_uint8), _f32p, C.c_int32]),
     'jlm_set_stream': (C.c_int32, [_VP, _VP]),
     'jlm_synchronize': (C.c_int32, [_VP]),
     'jlm_lstm_step': (C.c_int32, [_VP, _i32p, _f64p, _f64p, C.c_int32, _f64p, _f64p]),

@@ -185,6 +185,8 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
   cudaFree(h->LM_in);
   cudaFree(h->P1);
   for (auto& p : h->Wseg_store) cudaFree(p);
+  for (auto& p : h->Wq_store) cudaFree(p);
+  for (auto& p : h->cb_store) cudaFree(p);
   for (auto& b : h->scratch) b.release();
   h->batch_cache.release();
   for (auto& b : h->pinned) b.release();
@@ -192,6 +194,40 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
     if (ev) cudaEventDestroy(ev);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return 0;
+}
+
+extern "C" int32_t jlm_set_quantized_block(jlm_handle* h, int32_t segment, const uint8_t* code, const float* codebook,
+                                           int32_t n_codes) {
+  JLM_REQUIRE(h && code && codebook, "jlm_set_quantized_block: null argument");
+  JLM_REQUIRE(segment >= 0 && segment < h->n_seg, "jlm_set_quantized_block: segment %d out of range", segment);
+  JLM_REQUIRE(n_codes >= 1 && n_codes <= 256, "jlm_set_quantized_block: n_codes %d not in [1,256]", n_codes);
+  JLM_CUDA(cudaSetDevice(h->device));
+  SegDev& s = h->seg[segment];
+  const int64_t Vi = s.end - s.start;
+  // the codes must decode to exactly the float32 block already on the device
+  std::vector<float> W((size_t)Vi * s.kpad);
+  JLM_CUDA(cudaMemcpy(W.data(), s.W, W.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> q((size_t)Vi * s.kpad, 0);
+  for (int64_t v = 0; v < Vi; ++v)
+    for (int k = 0; k < s.width; ++k) {
+      const uint8_t c = code[v * s.width + k];
+      JLM_REQUIRE(c < n_codes, "jlm_set_quantized_block: code %d >= n_codes %d", (int)c, n_codes);
+      JLM_REQUIRE(memcmp(&codebook[c], &W[(size_t)v * s.kpad + k], sizeof(float)) == 0,
+                  "jlm_set_quantized_block: codebook[code] differs from the float32 weight at row %lld col %d",
+                  (long long)v, k);
+      q[(size_t)v * s.kpad + k] = c;
+    }
+  std::vector<float> cb(256, 0.f);
+  memcpy(cb.data(), codebook, sizeof(float) * n_codes);
+  if (h->Wq_store[segment]) cudaFree(h->Wq_store[segment]);
+  if (h->cb_store[segment]) cudaFree(h->cb_store[segment]);
+  h->Wq_store[segment] = nullptr;
+  h->cb_store[segment] = nullptr;
+  JLM_TRY(upload(&h->Wq_store[segment], q));
+  JLM_TRY(upload(&h->cb_store[segment], cb));
+  s.Wq = h->Wq_store[segment];
+  s.cb = h->cb_store[segment];
   return 0;
 }
 
@@ -272,8 +308,12 @@ int32_t dev_project(jlm_handle* h, const double* d_hidden, int B, const int32_t*
     for (int i = 0; i < h->n_seg; ++i) {
       const SegDev& s = h->seg[i];
       const int Vi = s.end - s.start;
-      JLM_TRY(exact_gemm_f32w(h->stream, T + s.koff, ldt, s.W, s.kpad, h->b2 + s.start, d_y ? d_y + s.start : nullptr, V,
-                              B, Vi, s.kpad, part, tiles, tile0));
+      if (s.Wq && B <= 16)
+        JLM_TRY(exact_gemm_q8w(h->stream, T + s.koff, ldt, s.Wq, s.kpad, s.cb, h->b2 + s.start,
+                               d_y ? d_y + s.start : nullptr, V, B, Vi, s.kpad, part, tiles, tile0));
+      else
+        JLM_TRY(exact_gemm_f32w(h->stream, T + s.koff, ldt, s.W, s.kpad, h->b2 + s.start, d_y ? d_y + s.start : nullptr, V,
+                                B, Vi, s.kpad, part, tiles, tile0));
       tile0 += exact_tiles_n(Vi);
     }
     if (d_lse) JLM_TRY(exact_lse_merge(h->stream, part, tiles, tiles, B, d_lse, 0));

@@ -641,8 +641,12 @@ int32_t exact_lm_step(jlm_batch* b, int t) {
     for (int i = 0; i < h->n_seg; ++i) {
       const SegDev& s = h->seg[i];
       const int Vi = s.end - s.start;
-      JLM_TRY(exact_gemm_f32w(st, T + s.koff, ldt, s.W, s.kpad, h->b2 + s.start, nullptr, 0, M, Vi, s.kpad, b->part,
-                              b->part_tiles, tile0));
+      if (s.Wq && M <= 16)
+        JLM_TRY(exact_gemm_q8w(st, T + s.koff, ldt, s.Wq, s.kpad, s.cb, h->b2 + s.start, nullptr, 0, M, Vi, s.kpad,
+                               b->part, b->part_tiles, tile0));
+      else
+        JLM_TRY(exact_gemm_f32w(st, T + s.koff, ldt, s.W, s.kpad, h->b2 + s.start, nullptr, 0, M, Vi, s.kpad, b->part,
+                                b->part_tiles, tile0));
       tile0 += exact_tiles_n(Vi);
       b->launches += 1;
     }

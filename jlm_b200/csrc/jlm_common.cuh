@@ -112,6 +112,8 @@ struct SegDev {
   int koff;    // column offset of the segment's slice inside the stage-1 output T (padded layout)
   int start, end;
   const float* W;   // [end-start, kpad] K-major, zero padded (exact back end + needed-word dots)
+  const uint8_t* Wq = nullptr;   // optional 8-bit codes, same layout (pad columns hold code 0; A is zero there)
+  const float* cb = nullptr;     // its 256-entry codebook (unused entries zero)
 };
 
 struct TcWeights;  // tensor-core operand copies (jlm_tc.cu)
@@ -136,6 +138,8 @@ struct jlm_handle {
   float* LM_in = nullptr;   // [V, Ep] zero padded
   double* P1 = nullptr;     // [Kt, Hp] stage-1 weight, K-major, float64 (NULL when untied)
   float* Wseg_store[JLM_MAX_SEGMENTS] = {};
+  uint8_t* Wq_store[JLM_MAX_SEGMENTS] = {};
+  float* cb_store[JLM_MAX_SEGMENTS] = {};
   TcWeights* tc = nullptr;
   // scratch for the model-level API and the batch engine
   DevBuf scratch[8];
@@ -170,6 +174,10 @@ static inline SegTable make_seg_table(const jlm_handle* h) {
 int32_t exact_gemm_f32w(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias,
                         double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
                         int part_tile0);
+// same contraction with the weights given as 8-bit codes + codebook; M <= 16 only (weight streaming)
+int32_t exact_gemm_q8w(cudaStream_t st, const double* A, int lda, const uint8_t* Bq, int ldb, const float* codebook,
+                       const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                       int part_tile0);
 int32_t exact_gemm_f64w(cudaStream_t st, const double* A, int lda, const double* B, int ldb,
                         double* C, int64_t ldc, int M, int N, int K);
 int exact_tiles_n(int N);

@@ -197,6 +197,89 @@ k_skinny_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, in
   }
 }
 
+// The same weight stream with the block stored as 8-bit k-means codes (train/comp.py): 16 weights per
+// 16-byte load, decoded through the 256-entry codebook held in shared memory as doubles.  Results are
+// bit-identical to k_skinny_f64<float, MT, 64, 4> on the decoded floats (same products, same order).
+template <int MT>
+__global__ void __launch_bounds__(256)
+k_skinny_q8(const double* __restrict__ A, int lda, const uint8_t* __restrict__ Bq, int ldb,
+            const float* __restrict__ codebook, const float* __restrict__ bias, double* __restrict__ C, int64_t ldc,
+            int M, int N, int K, double2* __restrict__ part, int part_ld, int part_tile0) {
+  extern __shared__ __align__(16) double smem_sk[];
+  constexpr int COLS = 64, KG = 4, SK_THREADS = 256;
+  double* As = smem_sk;                                  // [M][K]
+  double* Ps = smem_sk + (size_t)M * K;                  // [KG][MT][COLS]
+  __shared__ double cb[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cb[tid] = (double)codebook[tid];
+  for (int i = tid * 2; i < M * K; i += SK_THREADS * 2) {
+    const int m = i / K, k = i % K;
+    *reinterpret_cast<double2*>(&As[i]) = *reinterpret_cast<const double2*>(A + (int64_t)m * lda + k);
+  }
+  __syncthreads();
+  const int g = warp / (COLS / 32);
+  const int c = (warp % (COLS / 32)) * 32 + lane;
+  const int n = blockIdx.x * COLS + c;
+  const int kq = K / KG;
+  double acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+  if (n < N) {
+    const uint8_t* brow = Bq + (int64_t)n * ldb + g * kq;
+    const double* arow = As + g * kq;
+#pragma unroll 2
+    for (int k = 0; k < kq; k += 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(brow + k);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double w0 = cb[wv[j] & 0xff], w1 = cb[(wv[j] >> 8) & 0xff], w2 = cb[(wv[j] >> 16) & 0xff],
+                     w3 = cb[wv[j] >> 24];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < M) {
+            const double2 a01 = *reinterpret_cast<const double2*>(arow + m * K + k + 4 * j);
+            const double2 a23 = *reinterpret_cast<const double2*>(arow + m * K + k + 4 * j + 2);
+            acc[m] = fma(a01.x, w0, acc[m]);
+            acc[m] = fma(a01.y, w1, acc[m]);
+            acc[m] = fma(a23.x, w2, acc[m]);
+            acc[m] = fma(a23.y, w3, acc[m]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) Ps[(g * MT + m) * COLS + c] = acc[m];
+  __syncthreads();
+  for (int i = tid; i < M * COLS; i += SK_THREADS) {
+    const int m = i / COLS, cc = i % COLS;
+    const int nn = blockIdx.x * COLS + cc;
+    double v = -INFINITY;
+    if (nn < N) {
+      v = 0.0;
+#pragma unroll
+      for (int q = 0; q < KG; ++q) v += Ps[(q * MT + m) * COLS + cc];
+      if (bias) v += (double)bias[nn];
+      if (C) C[(int64_t)m * ldc + nn] = v;
+    }
+    Ps[m * COLS + cc] = v;
+  }
+  if (part) {
+    __syncthreads();
+    for (int m = warp; m < M; m += SK_THREADS / 32) {
+      const double v0 = Ps[m * COLS + lane], v1 = Ps[m * COLS + 32 + lane];
+      double mx = fmax(v0, v1);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      double sm = (v0 == -INFINITY ? 0.0 : exp(v0 - mx)) + (v1 == -INFINITY ? 0.0 : exp(v1 - mx));
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      if (lane == 0) part[(int64_t)m * part_ld + part_tile0 + blockIdx.x] = make_double2(mx, sm);
+    }
+  }
+}
+
 __global__ void k_lse_merge(const double2* __restrict__ part, int part_ld, int n_tiles, int M,
                             double* __restrict__ lse, int self_norm) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -431,6 +514,22 @@ int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int 
   return 0;
 }
 
+template <int MT>
+int32_t launch_skinny_q8(cudaStream_t st, const double* A, int lda, const uint8_t* Bq, int ldb, const float* codebook,
+                         const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                         int part_tile0) {
+  static bool configured = false;
+  if (!configured) {
+    JLM_CUDA(cudaFuncSetAttribute(k_skinny_q8<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const size_t smem = ((size_t)M * K + (size_t)64 * MT * 4) * sizeof(double);
+  k_skinny_q8<MT><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld,
+                                                      part_tile0);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 int exact_tiles_n(int N) { return ceil_div(N, BN); }
@@ -439,6 +538,18 @@ int32_t exact_gemm_f32w(cudaStream_t st, const double* A, int lda, const float* 
                         double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
                         int part_tile0) {
   return launch_gemm<float>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+}
+
+int32_t exact_gemm_q8w(cudaStream_t st, const double* A, int lda, const uint8_t* Bq, int ldb, const float* codebook,
+                       const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                       int part_tile0) {
+  JLM_REQUIRE(M >= 1 && M <= 16 && K % 64 == 0 && ldb % 16 == 0, "q8 gemm: unsupported shape M=%d K=%d ldb=%d", M, K, ldb);
+  JLM_REQUIRE(((size_t)M * K + 64 * 16 * 4) * sizeof(double) <= 200 * 1024, "q8 gemm: K=%d too large", K);
+  if (N <= 0) return 0;
+  if (M <= 4) return launch_skinny_q8<4>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  if (M <= 8) return launch_skinny_q8<8>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  if (M <= 12) return launch_skinny_q8<12>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  return launch_skinny_q8<16>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
 }
 
 int32_t exact_gemm_f64w(cudaStream_t st, const double* A, int lda, const double* B, int ldb, double* C,

@@ -109,6 +109,41 @@ class LSTM_Model(object):
         self._handle = C.c_void_p()
         _lib.check(self._lib.jlm_create(C.byref(c), C.byref(cw), int(device), C.byref(self._handle)))
         del keep
+        self.quantized_blocks = self._attach_codes(experiment_id, comp) if (comp and weights is None) else []
+
+    def _attach_codes(self, experiment_id, comp):
+        """Hands the k-means (code, codebook) form of the output blocks to the device when the reference's
+        comp dump is present (train/comp.py:79-80: weights/comp_N/lstm_weights_comp_dump.pkl).  The codes
+        must decode to the floats already loaded (jlm_set_quantized_block verifies), so results are
+        unchanged; only the bytes streamed per LM step by the few-rows-in-flight path shrink 4x."""
+        path = os.path.join(config.experiment_path, str(experiment_id), 'weights', 'comp_{}'.format(comp),
+                            'lstm_weights_comp_dump.pkl')
+        if comp > 8 or not os.path.exists(path):
+            return []
+        with open(path, 'rb') as f:
+            dump = pickle.load(f)
+        if not self.share_embedding:
+            keys = [('UM', True)]
+        elif self.config.get('V_table'):
+            keys = [('LM{}'.format(i), False) for i in range(len(self._segs))]
+        elif self.config.get('D_softmax'):
+            return []                      # comp.py cannot compress the block list of a D-softmax dump
+        else:
+            keys = [('LM', False)]
+        done = []
+        for seg, (key, transposed) in enumerate(keys):
+            if key not in dump:
+                continue
+            code, codebook = dump[key]
+            code = np.asarray(code)
+            if code.dtype != np.uint8:
+                continue
+            code = np.ascontiguousarray(code.T if transposed else code)
+            cb = np.ascontiguousarray(np.asarray(codebook, dtype=np.float32).reshape(-1))
+            _lib.check(self._lib.jlm_set_quantized_block(self._handle, seg, _lib.ptr(code, C.c_uint8),
+                                                         _lib.ptr(cb, C.c_float), int(cb.shape[0])))
+            done.append(key)
+        return done
 
     def __del__(self):
         h = getattr(self, '_handle', None)

@@ -226,3 +226,42 @@ def make_experiment(root, experiment_id, vocab_size, hidden_size, embed_size, mo
         lexicon, reading_dict = make_lexicon(vocab_size, seed=seed)
     write_experiment(root, experiment_id, cfg, weights, lexicon, reading_dict)
     return cfg, weights, lexicon, reading_dict
+
+
+def compress_weights(weights, bits=8, seed=0):
+    """Stand-in for train/comp.py:20-80 with the same outputs: per tensor a (code uint8, codebook
+    [2**bits, 1] float32) pair and the decoded tensor np.take(codebook, code).  Centroids are quantiles
+    refined by two Lloyd iterations instead of sklearn's full k-means (the formats, not the clustering
+    quality, are what the inference path depends on)."""
+    n = 2 ** bits
+    dump, decoded = {}, {}
+    for key, value in weights.items():
+        if isinstance(value, list):
+            raise ValueError('comp.py cannot compress the block list of a D-softmax dump')
+        flat = np.asarray(value, dtype=np.float32).reshape(-1).astype(np.float64)
+        cent = np.unique(np.quantile(flat, (np.arange(n) + 0.5) / n))
+        for _ in range(2):
+            edges = (cent[1:] + cent[:-1]) / 2
+            code = np.searchsorted(edges, flat)
+            sums = np.bincount(code, weights=flat, minlength=len(cent))
+            cnt = np.bincount(code, minlength=len(cent))
+            cent = np.where(cnt > 0, sums / np.maximum(cnt, 1), cent)
+            cent = np.sort(cent)
+        edges = (cent[1:] + cent[:-1]) / 2
+        code = np.searchsorted(edges, flat).astype(np.uint8).reshape(np.asarray(value).shape)
+        codebook = cent.astype(np.float32).reshape(-1, 1)
+        dump[key] = (code, codebook)
+        decoded[key] = np.take(codebook, code)
+    return dump, decoded
+
+
+def write_compressed(root, experiment_id, weights, bits=8):
+    """Writes lstm_weights_comp_N.pkl and comp_N/lstm_weights_comp_dump.pkl (train/comp.py:52-80 layout)."""
+    wdir = os.path.join(root, 'train', 'experiments', str(experiment_id), 'weights')
+    os.makedirs(os.path.join(wdir, 'comp_{}'.format(bits)), exist_ok=True)
+    dump, decoded = compress_weights(weights, bits)
+    with open(os.path.join(wdir, 'lstm_weights_comp_{}.pkl'.format(bits)), 'wb') as f:
+        pickle.dump(decoded, f)
+    with open(os.path.join(wdir, 'comp_{}'.format(bits), 'lstm_weights_comp_dump.pkl'), 'wb') as f:
+        pickle.dump(dump, f)
+    return dump, decoded

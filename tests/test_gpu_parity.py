@@ -277,3 +277,39 @@ def test_empty_and_all_unknown_inputs(tmp_path_factory):
         assert [w for _, w in got] == [w for _, w in want] == [list(text)]
         np.testing.assert_allclose([s for s, _ in got], [s for s, _ in want], rtol=0, atol=2e-5)
         assert dec.decode_batch([text], topN=3, beam_width=3, backend=EXACT)[0] == got
+
+
+@pytest.mark.parametrize('mode', ['tied', 'untied', 'dsoftmax_star'])
+def test_quantized_blocks_match_decoded_floats(mode, tmp_path_factory):
+    """train/comp.py format: with the (code, codebook) dump present the output blocks are streamed as 8-bit
+    codes (jlm_set_quantized_block); results must equal the run on the decoded float pickle the reference
+    itself loads (decoder/model.py:74-76)."""
+    import jlm_b200
+    from jlm_b200 import config, synth
+    root = str(tmp_path_factory.mktemp('comp_' + mode))
+    cfg, weights, lexicon, reading_dict = synth.make_experiment(root, 1, 1000, 64, 32, mode, seed=3)
+    dump, decoded = synth.write_compressed(root, 1, weights, bits=8)
+    synth.write_experiment(root, 2, cfg, decoded)                 # experiment 2: the decoded floats, no codes
+    sents = synth.make_sentences(lexicon, 3, min_len=10, seed=9, vocab_size=1000)
+    config.set_root(root)
+    dq = jlm_b200.Decoder(1, comp=8)
+    df = jlm_b200.Decoder(2)
+    assert dq.model.quantized_blocks == {'tied': ['LM'], 'untied': ['UM'], 'dsoftmax_star': ['LM0', 'LM1', 'LM2']}[mode]
+    assert df.model.quantized_blocks == []
+    for s in sents:
+        a = dq.decode(s, topN=5, beam_width=5, backend=EXACT)
+        b = df.decode(s, topN=5, beam_width=5, backend=EXACT)
+        assert [w for _, w in a] == [w for _, w in b]
+        np.testing.assert_allclose([x for x, _ in a], [x for x, _ in b], rtol=0, atol=1e-11)
+    (pa, ya, _, _), ha, ca = dq.model.predict_with_context([1, 5, 17], np.zeros((3, 64)), np.zeros((3, 64)))
+    (pb, yb, _, _), hb, cb = df.model.predict_with_context([1, 5, 17], np.zeros((3, 64)), np.zeros((3, 64)))
+    np.testing.assert_allclose(ya, yb, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-12)
+    # a codebook that does not reproduce the floats is rejected, not silently used
+    from jlm_b200 import _lib
+    import ctypes as C
+    code, cbk = dump['UM' if mode == 'untied' else ('LM0' if mode == 'dsoftmax_star' else 'LM')]
+    code = np.ascontiguousarray(code.T if mode == 'untied' else code)
+    bad = np.ascontiguousarray(cbk.reshape(-1) + np.float32(1e-3))
+    rc = dq._lib.jlm_set_quantized_block(dq.model._handle, 0, _lib.ptr(code, C.c_uint8), _lib.ptr(bad, C.c_float), len(bad))
+    assert rc != 0 and b'differs from the float32 weight' in dq._lib.jlm_last_error()

@@ -165,6 +165,7 @@ extern "C" int32_t jlm_create(const jlm_config* cfg, const jlm_weights* w, int32
     return 1;
   }
   h->own_stream = true;
+  if (const char* e = getenv("JLM_Q8")) h->q8_policy = atoi(e) ? 1 : 0;
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (build_weights(h, w)) {
     jlm_destroy(h);
@@ -308,7 +309,7 @@ int32_t dev_project(jlm_handle* h, const double* d_hidden, int B, const int32_t*
     for (int i = 0; i < h->n_seg; ++i) {
       const SegDev& s = h->seg[i];
       const int Vi = s.end - s.start;
-      if (s.Wq && B <= 16)
+      if (exact_use_q8(h, s, B))
         JLM_TRY(exact_gemm_q8w(h->stream, T + s.koff, ldt, s.Wq, s.kpad, s.cb, h->b2 + s.start,
                                d_y ? d_y + s.start : nullptr, V, B, Vi, s.kpad, part, tiles, tile0));
       else

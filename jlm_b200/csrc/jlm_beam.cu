@@ -641,7 +641,7 @@ int32_t exact_lm_step(jlm_batch* b, int t) {
     for (int i = 0; i < h->n_seg; ++i) {
       const SegDev& s = h->seg[i];
       const int Vi = s.end - s.start;
-      if (s.Wq && M <= 16)
+      if (exact_use_q8(h, s, M))
         JLM_TRY(exact_gemm_q8w(st, T + s.koff, ldt, s.Wq, s.kpad, s.cb, h->b2 + s.start, nullptr, 0, M, Vi, s.kpad,
                                b->part, b->part_tiles, tile0));
       else

@@ -140,6 +140,7 @@ struct jlm_handle {
   float* Wseg_store[JLM_MAX_SEGMENTS] = {};
   uint8_t* Wq_store[JLM_MAX_SEGMENTS] = {};
   float* cb_store[JLM_MAX_SEGMENTS] = {};
+  int q8_policy = -1;   // -1 auto, 0 never, 1 always (JLM_Q8)
   TcWeights* tc = nullptr;
   // scratch for the model-level API and the batch engine
   DevBuf scratch[8];
@@ -174,6 +175,10 @@ static inline SegTable make_seg_table(const jlm_handle* h) {
 int32_t exact_gemm_f32w(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias,
                         double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
                         int part_tile0);
+// true when the 8-bit code path can and should serve this call: codes attached, shape supported by the
+// streaming kernel, and (policy) the float32 block is too large to stay L2-resident between LM steps
+// (JLM_Q8=1 forces the codes, JLM_Q8=0 disables them; default: blocks > 96 MB)
+bool exact_use_q8(const jlm_handle* h, const SegDev& s, int M);
 // same contraction with the weights given as 8-bit codes + codebook; M <= 16 only (weight streaming)
 int32_t exact_gemm_q8w(cudaStream_t st, const double* A, int lda, const uint8_t* Bq, int ldb, const float* codebook,
                        const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,

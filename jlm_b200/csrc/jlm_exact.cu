@@ -108,65 +108,100 @@ k_gemm_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int 
   }
 }
 
-// Few rows in flight (one sentence: M <= beam rows): the GEMM is a weight stream.  One CTA = one
-// 64-column tile; thread = (column, quarter of K): it streams its quarter of the column's weight row
-// (every weight byte is read once) and accumulates all M rows in float64 registers against broadcast
-// reads of A, which sits in shared memory as doubles - no cross-lane reduction in the K loop.  The four
-// K-quarters are then summed through shared memory and the tile's (max, sum exp) partial is formed in
-// the CTA.  HBM/L2-bound: algorithmic bytes = N*K*sizeof(weight) per launch.
-// Two shapes: COLS=64, KG=4 when LSE partials are wanted (their tile is 64 columns) or N is large;
-// COLS=32, KG=16 for the small gate / stage-1 GEMMs, which need more CTAs and shorter K loops.
-template <typename TB, int MT, int COLS, int KG>
-__global__ void __launch_bounds__(COLS * KG)
+// Few rows in flight (one sentence: M <= beam rows): the GEMM is a weight stream.  One CTA = one tile of
+// COLS columns; thread = (CPT columns 32 apart, one K slice): it streams its slice of those weight rows
+// (every weight byte is read once) and accumulates all M rows in float64 registers against broadcast reads
+// of A, which sits in shared memory as doubles - no cross-lane reduction in the K loop.  The K slices are
+// then summed through shared memory (fixed order) and, for 64-column tiles, the tile's (max, sum exp)
+// partial is formed in the CTA.  HBM/L2-bound: algorithmic bytes = N*K*sizeof(weight) per launch.
+// Weights are float32, float64 (stage-1 matrix) or 8-bit k-means codes (train/comp.py) decoded through a
+// 256-entry codebook held in shared memory; the code path issues the same products in the same order as
+// the float32 path, so its results are bit-identical.
+// Shapes: <COLS=64, CPT=2, KG=8> when LSE partials are wanted or N is large; <32, 1, 16> for the small
+// gate / stage-1 GEMMs, which need more CTAs and shorter K loops.
+template <typename TB>
+struct SkLoad {                                           // one 16-byte weight load
+  static constexpr int VEC = 16 / sizeof(TB);
+  static __device__ __forceinline__ void load(const TB* p, const double* cb, double (&w)[VEC]) {
+    if constexpr (sizeof(TB) == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p);
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if constexpr (sizeof(TB) == 8) {
+      const double2 v = *reinterpret_cast<const double2*>(p);
+      w[0] = v.x; w[1] = v.y;
+    } else {
+      const uint4 v = *reinterpret_cast<const uint4*>(p);
+      const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        w[4 * j] = cb[q[j] & 0xff];
+        w[4 * j + 1] = cb[(q[j] >> 8) & 0xff];
+        w[4 * j + 2] = cb[(q[j] >> 16) & 0xff];
+        w[4 * j + 3] = cb[q[j] >> 24];
+      }
+    }
+  }
+};
+
+template <typename TB, int MT, int COLS, int CPT, int KG>
+__global__ void __launch_bounds__(COLS / CPT * KG)
 k_skinny_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
-             const float* __restrict__ bias, double* __restrict__ C, int64_t ldc, int M, int N, int K,
-             double2* __restrict__ part, int part_ld, int part_tile0) {
+             const float* __restrict__ codebook, const float* __restrict__ bias, double* __restrict__ C,
+             int64_t ldc, int M, int N, int K, double2* __restrict__ part, int part_ld, int part_tile0) {
   extern __shared__ __align__(16) double smem_sk[];
-  double* As = smem_sk;                                  // [M][K]
-  double* Ps = smem_sk + (size_t)M * K;                  // [KG][MT][COLS] partial sums, then values
-  constexpr int SK_THREADS = COLS * KG;
-  constexpr int VEC = 16 / sizeof(TB);                   // weights per 16-byte load: 4 floats or 2 doubles
+  constexpr int SK_THREADS = COLS / CPT * KG;
+  constexpr int VEC = SkLoad<TB>::VEC;
+  constexpr int WPG = COLS / CPT / 32;                    // warps per K slice
+  double* As = smem_sk;                                   // [M][K]
+  double* Ps = smem_sk + (size_t)M * K;                   // [KG][MT][COLS] partial sums, then values
+  double* cb = Ps + (size_t)KG * MT * COLS;               // [256] codebook (8-bit weights only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (sizeof(TB) == 1)
+    for (int i = tid; i < 256; i += SK_THREADS) cb[i] = (double)codebook[i];
   for (int i = tid * 2; i < M * K; i += SK_THREADS * 2) {
     const int m = i / K, k = i % K;
     *reinterpret_cast<double2*>(&As[i]) = *reinterpret_cast<const double2*>(A + (int64_t)m * lda + k);
   }
   __syncthreads();
-  const int g = warp / (COLS / 32);                      // K slice
-  const int c = (warp % (COLS / 32)) * 32 + lane;        // column inside the tile
+  const int g = warp / WPG;                               // K slice
+  const int c = (warp % WPG) * 32 * CPT + lane;           // first column inside the tile
   const int n = blockIdx.x * COLS + c;
   const int kq = K / KG;
-  double acc[MT];
+  double acc[CPT][MT];
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+  for (int j = 0; j < CPT; ++j)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[j][m] = 0.0;
   if (n < N) {
-    const TB* brow = B + (int64_t)n * ldb + g * kq;
+    const TB* brow[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) brow[j] = B + (int64_t)min(n + 32 * j, N - 1) * ldb + g * kq;
     const double* arow = As + g * kq;
-#pragma unroll 8
+#pragma unroll 2
     for (int k = 0; k < kq; k += VEC) {
-      double w[VEC];
-      if (sizeof(TB) == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(brow + k);
-        w[0] = v.x; w[1] = v.y; w[VEC - 2] = v.z; w[VEC - 1] = v.w;
-      } else {
-        const double2 v = *reinterpret_cast<const double2*>(brow + k);
-        w[0] = v.x; w[1] = v.y;
-      }
+      double w[CPT][VEC];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) SkLoad<TB>::load(brow[j] + k, cb, w[j]);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         if (m < M) {
 #pragma unroll
           for (int i = 0; i < VEC; i += 2) {
             const double2 a2 = *reinterpret_cast<const double2*>(arow + m * K + k + i);
-            acc[m] = fma(a2.x, w[i], acc[m]);
-            acc[m] = fma(a2.y, w[i + 1], acc[m]);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              acc[j][m] = fma(a2.x, w[j][i], acc[j][m]);
+              acc[j][m] = fma(a2.y, w[j][i + 1], acc[j][m]);
+            }
           }
         }
       }
     }
   }
 #pragma unroll
-  for (int m = 0; m < MT; ++m) Ps[(g * MT + m) * COLS + c] = acc[m];
+  for (int j = 0; j < CPT; ++j)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) Ps[(g * MT + m) * COLS + c + 32 * j] = acc[j][m];
   __syncthreads();
   // sum the K slices (fixed order): value (m, c) lands in Ps[m][c] of slice 0
   for (int i = tid; i < M * COLS; i += SK_THREADS) {
@@ -186,89 +221,6 @@ k_skinny_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, in
     __syncthreads();
     for (int m = warp; m < M; m += SK_THREADS / 32) {      // one warp per row: 64 columns, 2 per lane
       const double v0 = Ps[m * BN + lane], v1 = Ps[m * BN + 32 + lane];
-      double mx = fmax(v0, v1);
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      double sm = (v0 == -INFINITY ? 0.0 : exp(v0 - mx)) + (v1 == -INFINITY ? 0.0 : exp(v1 - mx));
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-      if (lane == 0) part[(int64_t)m * part_ld + part_tile0 + blockIdx.x] = make_double2(mx, sm);
-    }
-  }
-}
-
-// The same weight stream with the block stored as 8-bit k-means codes (train/comp.py): 16 weights per
-// 16-byte load, decoded through the 256-entry codebook held in shared memory as doubles.  Results are
-// bit-identical to k_skinny_f64<float, MT, 64, 4> on the decoded floats (same products, same order).
-template <int MT>
-__global__ void __launch_bounds__(256)
-k_skinny_q8(const double* __restrict__ A, int lda, const uint8_t* __restrict__ Bq, int ldb,
-            const float* __restrict__ codebook, const float* __restrict__ bias, double* __restrict__ C, int64_t ldc,
-            int M, int N, int K, double2* __restrict__ part, int part_ld, int part_tile0) {
-  extern __shared__ __align__(16) double smem_sk[];
-  constexpr int COLS = 64, KG = 4, SK_THREADS = 256;
-  double* As = smem_sk;                                  // [M][K]
-  double* Ps = smem_sk + (size_t)M * K;                  // [KG][MT][COLS]
-  __shared__ double cb[256];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  cb[tid] = (double)codebook[tid];
-  for (int i = tid * 2; i < M * K; i += SK_THREADS * 2) {
-    const int m = i / K, k = i % K;
-    *reinterpret_cast<double2*>(&As[i]) = *reinterpret_cast<const double2*>(A + (int64_t)m * lda + k);
-  }
-  __syncthreads();
-  const int g = warp / (COLS / 32);
-  const int c = (warp % (COLS / 32)) * 32 + lane;
-  const int n = blockIdx.x * COLS + c;
-  const int kq = K / KG;
-  double acc[MT];
-#pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
-  if (n < N) {
-    const uint8_t* brow = Bq + (int64_t)n * ldb + g * kq;
-    const double* arow = As + g * kq;
-#pragma unroll 2
-    for (int k = 0; k < kq; k += 16) {
-      const uint4 v = *reinterpret_cast<const uint4*>(brow + k);
-      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double w0 = cb[wv[j] & 0xff], w1 = cb[(wv[j] >> 8) & 0xff], w2 = cb[(wv[j] >> 16) & 0xff],
-                     w3 = cb[wv[j] >> 24];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          if (m < M) {
-            const double2 a01 = *reinterpret_cast<const double2*>(arow + m * K + k + 4 * j);
-            const double2 a23 = *reinterpret_cast<const double2*>(arow + m * K + k + 4 * j + 2);
-            acc[m] = fma(a01.x, w0, acc[m]);
-            acc[m] = fma(a01.y, w1, acc[m]);
-            acc[m] = fma(a23.x, w2, acc[m]);
-            acc[m] = fma(a23.y, w3, acc[m]);
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int m = 0; m < MT; ++m) Ps[(g * MT + m) * COLS + c] = acc[m];
-  __syncthreads();
-  for (int i = tid; i < M * COLS; i += SK_THREADS) {
-    const int m = i / COLS, cc = i % COLS;
-    const int nn = blockIdx.x * COLS + cc;
-    double v = -INFINITY;
-    if (nn < N) {
-      v = 0.0;
-#pragma unroll
-      for (int q = 0; q < KG; ++q) v += Ps[(q * MT + m) * COLS + cc];
-      if (bias) v += (double)bias[nn];
-      if (C) C[(int64_t)m * ldc + nn] = v;
-    }
-    Ps[m * COLS + cc] = v;
-  }
-  if (part) {
-    __syncthreads();
-    for (int m = warp; m < M; m += SK_THREADS / 32) {
-      const double v0 = Ps[m * COLS + lane], v1 = Ps[m * COLS + 32 + lane];
       double mx = fmax(v0, v1);
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -470,23 +422,42 @@ int grid_1d(int64_t total, int block, int cap) {
 }
 
 template <typename TB, int MT>
-int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* bias, double* C,
-                      int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
+int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* codebook,
+                      const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                      int part_tile0) {
   static bool configured = false;
   if (!configured) {
-    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 32, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  const size_t smem = ((size_t)M * K + (size_t)64 * MT * 4) * sizeof(double);   // KG*COLS == 256 for both shapes... x2 below
-  if (part || N > 8192 || K % (16 * 4) != 0) {
-    k_skinny_f64<TB, MT, 64, 4><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld,
-                                                                   part_tile0);
+  constexpr int VEC = 16 / (int)sizeof(TB);
+  if (part || N > 8192 || sizeof(TB) == 1 || K % (16 * VEC) != 0) {
+    const size_t smem = ((size_t)M * K + (size_t)8 * MT * 64 + 256) * sizeof(double);
+    k_skinny_f64<TB, MT, 64, 2, 8><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, B, ldb, codebook, bias, C, ldc, M, N, K,
+                                                                      part, part_ld, part_tile0);
   } else {
-    const size_t smem2 = ((size_t)M * K + (size_t)16 * MT * 32) * sizeof(double);
-    k_skinny_f64<TB, MT, 32, 16><<<ceil_div(N, 32), 512, smem2, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, nullptr, 0, 0);
+    const size_t smem = ((size_t)M * K + (size_t)16 * MT * 32 + 256) * sizeof(double);
+    k_skinny_f64<TB, MT, 32, 1, 16><<<ceil_div(N, 32), 512, smem, st>>>(A, lda, B, ldb, codebook, bias, C, ldc, M, N, K,
+                                                                       nullptr, 0, 0);
   }
+  JLM_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <typename TB>
+int32_t skinny_dispatch(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* codebook,
+                        const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
+                        int part_tile0) {
+  if (M <= 4) return launch_skinny<TB, 4>(st, A, lda, B, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  if (M <= 8) return launch_skinny<TB, 8>(st, A, lda, B, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  if (M <= 12) return launch_skinny<TB, 12>(st, A, lda, B, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  return launch_skinny<TB, 16>(st, A, lda, B, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+}
+
+// the skinny path needs M <= 16, K a multiple of 8 slices x 16 weights, and A + partial sums in shared memory
+bool skinny_ok(int M, int K) {
+  return M >= 1 && M <= 16 && K % 128 == 0 && ((size_t)M * K + 16 * 16 * 32 + 256) * sizeof(double) <= 200 * 1024;
 }
 
 template <typename TB>
@@ -494,12 +465,9 @@ int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int 
                     int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
   JLM_REQUIRE(K % BK == 0 && lda % 2 == 0 && ldb % 4 == 0, "exact gemm: unaligned K=%d lda=%d ldb=%d", K, lda, ldb);
   if (M <= 0 || N <= 0) return 0;
-  if (M <= 16 && ((size_t)M * K + (size_t)16 * 16 * 32) * sizeof(double) <= 200 * 1024 && K % 16 == 0) {
+  if (skinny_ok(M, K)) {
     // weight-streaming path for one sentence's rows
-    if (M <= 4) JLM_TRY((launch_skinny<TB, 4>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
-    else if (M <= 8) JLM_TRY((launch_skinny<TB, 8>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
-    else if (M <= 12) JLM_TRY((launch_skinny<TB, 12>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
-    else JLM_TRY((launch_skinny<TB, 16>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0)));
+    JLM_TRY(skinny_dispatch<TB>(st, A, lda, B, ldb, nullptr, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   } else if (M <= 16) {
     dim3 grid(ceil_div(N, BN), ceil_div(M, 16));
     k_gemm_f64<TB, 1><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
@@ -514,22 +482,6 @@ int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int 
   return 0;
 }
 
-template <int MT>
-int32_t launch_skinny_q8(cudaStream_t st, const double* A, int lda, const uint8_t* Bq, int ldb, const float* codebook,
-                         const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
-                         int part_tile0) {
-  static bool configured = false;
-  if (!configured) {
-    JLM_CUDA(cudaFuncSetAttribute(k_skinny_q8<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
-  const size_t smem = ((size_t)M * K + (size_t)64 * MT * 4) * sizeof(double);
-  k_skinny_q8<MT><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld,
-                                                      part_tile0);
-  JLM_CUDA(cudaGetLastError());
-  return 0;
-}
-
 }  // namespace
 
 int exact_tiles_n(int N) { return ceil_div(N, BN); }
@@ -540,16 +492,18 @@ int32_t exact_gemm_f32w(cudaStream_t st, const double* A, int lda, const float* 
   return launch_gemm<float>(st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
 }
 
+bool exact_use_q8(const jlm_handle* h, const SegDev& s, int M) {
+  if (!s.Wq || !skinny_ok(M, s.kpad) || h->q8_policy == 0) return false;
+  if (h->q8_policy == 1) return true;
+  return (size_t)(s.end - s.start) * s.kpad * sizeof(float) > ((size_t)96 << 20);
+}
+
 int32_t exact_gemm_q8w(cudaStream_t st, const double* A, int lda, const uint8_t* Bq, int ldb, const float* codebook,
                        const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
                        int part_tile0) {
-  JLM_REQUIRE(M >= 1 && M <= 16 && K % 64 == 0 && ldb % 16 == 0, "q8 gemm: unsupported shape M=%d K=%d ldb=%d", M, K, ldb);
-  JLM_REQUIRE(((size_t)M * K + 64 * 16 * 4) * sizeof(double) <= 200 * 1024, "q8 gemm: K=%d too large", K);
+  JLM_REQUIRE(skinny_ok(M, K) && ldb % 16 == 0, "q8 gemm: unsupported shape M=%d K=%d ldb=%d", M, K, ldb);
   if (N <= 0) return 0;
-  if (M <= 4) return launch_skinny_q8<4>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
-  if (M <= 8) return launch_skinny_q8<8>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
-  if (M <= 12) return launch_skinny_q8<12>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
-  return launch_skinny_q8<16>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  return skinny_dispatch<uint8_t>(st, A, lda, Bq, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
 }
 
 int32_t exact_gemm_f64w(cudaStream_t st, const double* A, int lda, const double* B, int ldb, double* C,

@@ -16,6 +16,7 @@ dump, decoded = synth.write_compressed(root, 1, {k: v for k, v in weights.items(
 synth.write_experiment(root, 2, cfg, decoded)
 config.set_root(root)
 sents = synth.make_sentences(lexicon, 8, min_len=20, seed=5, vocab_size=50000)
+os.environ['JLM_Q8'] = '1'      # read by jlm_create: stream the codes even though this block is L2-resident
 for name, dec in (('float32 blocks', jlm_b200.Decoder(2)), ('8-bit codes', jlm_b200.Decoder(1, comp=8))):
     out = [dec.decode_batch([s], backend=1) for s in sents]          # warm-up
     t0 = time.perf_counter()

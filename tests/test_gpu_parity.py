@@ -280,14 +280,17 @@ def test_empty_and_all_unknown_inputs(tmp_path_factory):
 
 
 @pytest.mark.parametrize('mode', ['tied', 'untied', 'dsoftmax_star'])
-def test_quantized_blocks_match_decoded_floats(mode, tmp_path_factory):
+def test_quantized_blocks_match_decoded_floats(mode, tmp_path_factory, monkeypatch):
     """train/comp.py format: with the (code, codebook) dump present the output blocks are streamed as 8-bit
     codes (jlm_set_quantized_block); results must equal the run on the decoded float pickle the reference
     itself loads (decoder/model.py:74-76)."""
     import jlm_b200
     from jlm_b200 import config, synth
     root = str(tmp_path_factory.mktemp('comp_' + mode))
-    cfg, weights, lexicon, reading_dict = synth.make_experiment(root, 1, 1000, 64, 32, mode, seed=3)
+    monkeypatch.setenv('JLM_Q8', '1')                 # use the codes whatever the block size
+    # E=128/H=128 so that the output blocks' K is a multiple of the streaming kernel's 128
+    segs = [[128, 0, 300], [128, 300, 700], [128, 700, None]] if mode == 'dsoftmax_star' else None
+    cfg, weights, lexicon, reading_dict = synth.make_experiment(root, 1, 1000, 128, 128, mode, segments=segs, seed=3)
     dump, decoded = synth.write_compressed(root, 1, weights, bits=8)
     synth.write_experiment(root, 2, cfg, decoded)                 # experiment 2: the decoded floats, no codes
     sents = synth.make_sentences(lexicon, 3, min_len=10, seed=9, vocab_size=1000)
@@ -301,8 +304,8 @@ def test_quantized_blocks_match_decoded_floats(mode, tmp_path_factory):
         b = df.decode(s, topN=5, beam_width=5, backend=EXACT)
         assert [w for _, w in a] == [w for _, w in b]
         np.testing.assert_allclose([x for x, _ in a], [x for x, _ in b], rtol=0, atol=1e-11)
-    (pa, ya, _, _), ha, ca = dq.model.predict_with_context([1, 5, 17], np.zeros((3, 64)), np.zeros((3, 64)))
-    (pb, yb, _, _), hb, cb = df.model.predict_with_context([1, 5, 17], np.zeros((3, 64)), np.zeros((3, 64)))
+    (pa, ya, _, _), ha, ca = dq.model.predict_with_context([1, 5, 17], np.zeros((3, 128)), np.zeros((3, 128)))
+    (pb, yb, _, _), hb, cb = df.model.predict_with_context([1, 5, 17], np.zeros((3, 128)), np.zeros((3, 128)))
     np.testing.assert_allclose(ya, yb, rtol=0, atol=1e-11)
     np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-12)
     # a codebook that does not reproduce the floats is rejected, not silently used

@@ -190,10 +190,10 @@ class Decoder(object):
             mode = _lib.DECODE_STATIC_VOCAB if vocab_select else _lib.DECODE_FULL
             extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling) if vocab_select else None
             packed = lattice.NativeLattices(self._native(), inputs, mode, extra)
-            out = self._run(packed, mode, topN, beam_width, backend, timers=False)
+            out = self._run(packed, mode, topN, beam_width, backend, timers=True)
             if vocab_select:
                 self.lattice_vocab = packed.vocab_list(len(inputs) - 1)
-            self.perf_sen += len(inputs)
+            self._log_batch_perf(len(inputs))
             return out
         all_frames, vocabs = [], []
         for text in inputs:
@@ -202,6 +202,16 @@ class Decoder(object):
             all_frames.append(frames)
             vocabs.append(list(self.lattice_vocab) if self.lattice_vocab else None)
         packed, mode = self._pack(all_frames, vocabs)
-        out = self._run(packed, mode, topN, beam_width, backend, timers=False)
-        self.perf_sen += len(inputs)
+        out = self._run(packed, mode, topN, beam_width, backend, timers=True)
+        self._log_batch_perf(len(inputs))
         return out
+
+    def _log_batch_perf(self, n_sent, last_frame_stepped=True):
+        """perf_log_* for a lock-step batch: one entry per lock-step LM step (decoder.py:211-212), the
+        CUDA-event time of that step for the whole batch."""
+        info = self.last_info
+        steps = max(int(info.n_steps) - (0 if last_frame_stepped else 1), 1)
+        self.perf_log_lstm += [info.ms_lstm * 1e-3 / steps] * steps
+        self.perf_log_softmax += [info.ms_softmax * 1e-3 / steps] * steps
+        self.perf_sen += n_sent
+        return steps

@@ -62,9 +62,11 @@ class DynamicDecoder(Decoder):
         if native_lattice and inputs and vocab_select:
             extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling)
             packed = lattice.NativeLattices(self._native(), inputs, _lib.DECODE_DYNAMIC, extra)
-            out = self._run(packed, _lib.DECODE_DYNAMIC, topN, beam_width, backend, timers=False)
+            out = self._run(packed, _lib.DECODE_DYNAMIC, topN, beam_width, backend, timers=True)
         else:
             _, out = self._decode_many(inputs, topN, beam_width, vocab_select, samples, top_sampling,
-                                       random_sampling, backend, timers=False)
-        self.perf_sen += len(out)
+                                       random_sampling, backend, timers=True)
+        steps = self._log_batch_perf(len(out), last_frame_stepped=False)
+        self.perf_log_fix_vocab += [0.0] * steps
+        self.perf_log_fix_lattice_path_prob += [self.last_info.ms_beam * 1e-3 / steps] * steps
         return out

@@ -265,3 +265,25 @@ def write_compressed(root, experiment_id, weights, bits=8):
     with open(os.path.join(wdir, 'comp_{}'.format(bits), 'lstm_weights_comp_dump.pkl'), 'wb') as f:
         pickle.dump(dump, f)
     return dump, decoded
+
+
+def make_test_corpus(lexicon, n_lines, seed=2, min_words=3, max_words=8):
+    """Lines of data/test.txt as eval.py reads them (decoder/eval.py:125-166): space separated
+    'display/reading/POS' tokens.  Words are drawn by frequency from the WHOLE lexicon, so some lines
+    contain out-of-vocabulary words and exercise the reference's has_oov filter."""
+    rng = np.random.default_rng(seed)
+    words = lexicon[1:]
+    freq = np.array([f for _, f in words], dtype=np.float64)
+    cdf = np.cumsum(freq / freq.sum())
+    lines = []
+    for _ in range(n_lines):
+        k = int(rng.integers(min_words, max_words + 1))
+        ids = np.minimum(np.searchsorted(cdf, rng.random(k)), len(words) - 1)
+        lines.append(' '.join(words[int(i)][0] for i in ids))
+    return lines
+
+
+def write_test_corpus(root, lines):
+    os.makedirs(os.path.join(root, 'data'), exist_ok=True)
+    with open(os.path.join(root, 'data', 'test.txt'), 'w', encoding='utf-8') as f:
+        f.write('\n'.join(lines) + '\n')

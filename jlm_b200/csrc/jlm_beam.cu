@@ -41,6 +41,15 @@ __global__ void k_init_frame0(BeamDev d, int S) {
 constexpr int SC_RC = 8;       // rows accumulated per pass
 constexpr int SC_WARPS = 8;    // warps (= nodes) per CTA
 
+__device__ __forceinline__ void load4(const float* p, double (&t)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double (&t)[4]) {
+  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+  t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y;
+}
+
 template <typename TT, bool DYN>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
@@ -68,30 +77,53 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
     for (int r = 0; r < SC_RC; ++r) acc[r] = 0.0;
     for (int k = lane * 4; k < kpad; k += 128) {
       const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+      const double w0 = (double)wv.x, w1 = (double)wv.y, w2 = (double)wv.z, w3 = (double)wv.w;
 #pragma unroll
       for (int r = 0; r < SC_RC; ++r) {
         if (r0 + r < rows) {
-          const TT* tp = trow + (int64_t)(r0 + r) * ldt + k;
-          acc[r] = fma((double)tp[0], (double)wv.x, acc[r]);
-          acc[r] = fma((double)tp[1], (double)wv.y, acc[r]);
-          acc[r] = fma((double)tp[2], (double)wv.z, acc[r]);
-          acc[r] = fma((double)tp[3], (double)wv.w, acc[r]);
+          double t[4];
+          load4(trow + (int64_t)(r0 + r) * ldt + k, t);
+          acc[r] = fma(t[0], w0, acc[r]);
+          acc[r] = fma(t[1], w1, acc[r]);
+          acc[r] = fma(t[2], w2, acc[r]);
+          acc[r] = fma(t[3], w3, acc[r]);
         }
       }
     }
+    // reduce-scatter over the warp: halve the rows a lane carries at xor 16 / 8 / 4, then finish the
+    // one remaining row over xor 2 / 1.  Lane l ends with row (l >> 2) & 7 (bits 4,3,2 -> row bits 2,1,0).
+    static_assert(SC_RC == 8, "the reduce-scatter below is written for 8 rows");
+    const unsigned FULL = 0xffffffffu;
+    double v4[4], v2[2], v1;
+    {
+      const bool up = (lane & 16) != 0;
 #pragma unroll
-    for (int r = 0; r < SC_RC; ++r) {
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-    }
-#pragma unroll
-    for (int r = 0; r < SC_RC; ++r) {
-      if (lane == r && r0 + r < rows) {
-        const double y = acc[r] + bias;
-        const int64_t ps = ps0 + r0 + r;
-        d.cand_val[cpos + r0 + r] = DYN ? y : d.slot_score[ps] + ((use_lse ? d.slot_lse[ps] : 0.0) - y);
-        if (DYN) d.cand_parent[cpos + r0 + r] = (int32_t)ps;
+      for (int i = 0; i < 4; ++i) {
+        const double send = up ? acc[i] : acc[i + 4], keep = up ? acc[i + 4] : acc[i];
+        v4[i] = keep + __shfl_xor_sync(FULL, send, 16);
       }
+    }
+    {
+      const bool up = (lane & 8) != 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double send = up ? v4[i] : v4[i + 2], keep = up ? v4[i + 2] : v4[i];
+        v2[i] = keep + __shfl_xor_sync(FULL, send, 8);
+      }
+    }
+    {
+      const bool up = (lane & 4) != 0;
+      const double send = up ? v2[0] : v2[1], keep = up ? v2[1] : v2[0];
+      v1 = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    v1 += __shfl_xor_sync(FULL, v1, 2);
+    v1 += __shfl_xor_sync(FULL, v1, 1);
+    const int r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    if ((lane & 3) == 0 && r0 + r < rows) {
+      const double y = v1 + bias;
+      const int64_t ps = ps0 + r0 + r;
+      d.cand_val[cpos + r0 + r] = DYN ? y : d.slot_score[ps] + ((use_lse ? d.slot_lse[ps] : 0.0) - y);
+      if (DYN) d.cand_parent[cpos + r0 + r] = (int32_t)ps;
     }
   }
 }

@@ -190,6 +190,7 @@ def main():
     ap.add_argument('--cpu-baseline-sentences', type=int, default=32)
     ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--chunks', type=int, default=0, help='e2e arm: pipeline chunks of jlm_decode_texts (0 = automatic)')
     ap.add_argument('--profile', action='store_true', help='1 warm-up + K plain steps only (for ncu); prints no JSON')
     args = ap.parse_args()
 
@@ -322,19 +323,31 @@ def main():
     np.cumsum(lens, out=tptr[1:])
     cps = np.frombuffer(''.join(sents).encode('utf-32-le'), dtype=np.uint32)
 
-    def e2e_step():
-        lat = C.c_void_p()
-        _lib.check(lib.jlm_lattice_build(nlex.handle, len(sents), _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
-                                         MODE, n_extra, _lib.ptr(extra, C.c_int32) if n_extra else None, C.byref(lat)))
-        view = _lib.LatticeBatch()
-        _lib.check(lib.jlm_lattice_view(lat, C.byref(view), None, None))
-        _lib.check(lib.jlm_decode_batch(hdl, C.byref(view), BEAM, TOPN, MODE, args.backend, C.byref(nb)))
-        _lib.check(lib.jlm_lattice_destroy(lat))
+    tmax = int(lens.max()) + 1
+    t_scores = np.empty((S, TOPN))
+    t_npaths = np.empty(S, dtype=np.int32)
+    t_len = np.empty((S, TOPN), dtype=np.int32)
+    t_entry = np.zeros((S, TOPN, tmax), dtype=np.int32)
+    t_start = np.zeros((S, TOPN, tmax), dtype=np.int32)
+    tnb = _lib.TextNBest()
+    tnb.top_n, tnb.max_len = TOPN, tmax
+    tnb.scores, tnb.n_paths = _lib.ptr(t_scores, C.c_double), _lib.ptr(t_npaths, C.c_int32)
+    tnb.path_len = _lib.ptr(t_len, C.c_int32)
+    tnb.path_entry, tnb.path_start = _lib.ptr(t_entry, C.c_int32), _lib.ptr(t_start, C.c_int32)
 
-    ref_nodes = path_nodes.copy()
+    def e2e_step():
+        # ONE public call: lattice build, plan, H2D, every frame, D2H, pipelined over chunks in the library
+        _lib.check(lib.jlm_decode_texts(hdl, nlex.handle, len(sents), _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
+                                        BEAM, TOPN, MODE, n_extra, _lib.ptr(extra, C.c_int32) if n_extra else None,
+                                        args.backend, args.chunks, C.byref(tnb), None))
+
     for _ in range(2):
         e2e_step()
-    assert np.array_equal(ref_nodes, path_nodes), 'e2e arm and device-resident arm disagree'
+    # the e2e arm must reproduce the device-resident arm: same scores, same paths (as lexicon entries)
+    assert np.array_equal(t_scores, scores) and np.array_equal(t_len, path_len), 'e2e arm and device-resident arm disagree'
+    for s_i in (0, S // 2, S - 1):
+        ids = path_nodes[s_i, 0, :path_len[s_i, 0]]
+        assert np.array_equal(packed.node_entry[ids], t_entry[s_i, 0, :t_len[s_i, 0]]), 'e2e paths differ'
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -435,7 +448,8 @@ def main():
                    'wall_s_timed_region': wall},
         'e2e': {'value': e2e, 'unit': 'chars/s', 'h2d_bytes_per_step': int(i2.h2d_bytes),
                 'd2h_bytes_per_step': int(i2.d2h_bytes),
-                'call': 'jlm_lattice_build + jlm_decode_batch (host UTF-32 kana -> host n-best node paths)'},
+                'call': 'jlm_decode_texts (host UTF-32 kana -> host n-best paths; lattice build, plan, H2D, frames, D2H '
+                        'pipelined over chunks inside the call)'},
         'gpu_launches': launches,
         'roofline': roof,
         'cpu_baseline': {'value': cpu_chars / cpu_s if world == 1 else None, 'unit': 'chars/s', 'cores': os.cpu_count(),

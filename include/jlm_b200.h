@@ -54,6 +54,9 @@ enum {
 
 typedef struct jlm_handle jlm_handle;
 typedef struct jlm_batch jlm_batch;
+typedef struct jlm_lexicon jlm_lexicon;
+typedef struct jlm_lattice jlm_lattice;
+struct jlm_batch_info_s;
 
 /* config.json keys the hot path reads (model.py:41-56,117) after normalisation by the host. */
 typedef struct {
@@ -155,8 +158,6 @@ typedef struct {
  * already skipped).  Entry e of word_ids is "lexicon entry e"; node_entry reports it per lattice node so
  * the host can recover the word string (-1: '<eos>', -2: the '<unk>' fallback whose word is the kana
  * at node_start, decoder.py:129-130). */
-typedef struct jlm_lexicon jlm_lexicon;
-typedef struct jlm_lattice jlm_lattice;
 int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading_ptr /* [n+1] */,
                            const uint32_t* reading_chars, const int64_t* word_ptr /* [n+1] */,
                            const int32_t* word_ids, int32_t eos_id, int32_t unk_id, jlm_lexicon** out);
@@ -187,6 +188,25 @@ typedef struct {
 int32_t jlm_decode_batch(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
                          int32_t mode, int32_t backend, jlm_nbest* out);
 
+/* Decoder.decode / DynamicDecoder.decode for a batch of kana strings in one call: jlm_lattice_build +
+ * jlm_decode_batch, pipelined over n_chunks sub-batches (0 = automatic) so that the host work of chunk
+ * c+1 (lattice, plan, kernel enqueue) overlaps the device work of chunk c.  Paths come back as lexicon
+ * entries (see jlm_lexicon_create; -1 '<eos>', -2 '<unk>' whose word is the kana at path_start) so no
+ * lattice object outlives the call.  Arguments as jlm_lattice_build / jlm_decode_batch. */
+typedef struct {
+  int32_t top_n;        /* capacity per sentence */
+  int32_t max_len;      /* capacity of one path, >= max(kana per sentence)+1 */
+  double* scores;       /* [n_sent, top_n] */
+  int32_t* n_paths;     /* [n_sent] */
+  int32_t* path_len;    /* [n_sent, top_n] */
+  int32_t* path_entry;  /* [n_sent, top_n, max_len] */
+  int32_t* path_start;  /* [n_sent, top_n, max_len] start frame of each node (-1 for '<eos>') */
+} jlm_text_nbest;
+int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, const int64_t* text_ptr,
+                         const uint32_t* text, int32_t beam_width, int32_t top_n, int32_t mode, int32_t n_extra,
+                         const int32_t* extra_ids, int32_t backend, int32_t n_chunks, jlm_text_nbest* out,
+                         struct jlm_batch_info_s* info /* nullable: totals over the chunks, enables the timers */);
+
 /* The same call split in three so a benchmark can time the device part with the lattices already
  * resident in HBM: upload (plan + H2D), run (enqueue every frame, asynchronous), fetch (D2H). */
 int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
@@ -196,7 +216,7 @@ int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out);
 int32_t jlm_batch_destroy(jlm_batch* b);
 
 /* Introspection used by the parity tests and the benchmark. */
-typedef struct {
+typedef struct jlm_batch_info_s {
   int64_t n_slots;        /* beam entries over all sentences and frames (= LM rows stepped) */
   int64_t n_candidates;   /* expanded candidates scored over all frames */
   int64_t n_nodes;

@@ -42,6 +42,11 @@ class NBest(C.Structure):
                 ('path_len', _i32p), ('path_nodes', _i32p)]
 
 
+class TextNBest(C.Structure):
+    _fields_ = [('top_n', C.c_int32), ('max_len', C.c_int32), ('scores', _f64p), ('n_paths', _i32p),
+                ('path_len', _i32p), ('path_entry', _i32p), ('path_start', _i32p)]
+
+
 class BatchInfo(C.Structure):
     _fields_ = [('n_slots', C.c_int64), ('n_candidates', C.c_int64), ('n_nodes', C.c_int64),
                 ('n_steps', C.c_int32), ('backend', C.c_int32), ('kernel_launches', C.c_int64),
@@ -66,6 +71,8 @@ SYMBOLS = {
                                 _f64p, _f64p, _f32p, _f32p]),
     'jlm_decode_batch': (C.c_int32, [_VP, C.POINTER(LatticeBatch), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.POINTER(NBest)]),
+    'jlm_decode_texts': (C.c_int32, [_VP, _VP, C.c_int32, _i64p, _u32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p,
+                                     C.c_int32, C.c_int32, C.POINTER(TextNBest), C.POINTER(BatchInfo)]),
     'jlm_batch_upload': (C.c_int32, [_VP, C.POINTER(LatticeBatch), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.POINTER(_VP)]),
     'jlm_batch_run': (C.c_int32, [_VP]),

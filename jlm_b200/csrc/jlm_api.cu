@@ -180,6 +180,7 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_free_weights(h);
+  beam_free_plan_scratch(h);
   cudaFree(h->Wg);
   cudaFree(h->bg);
   cudaFree(h->b2);
@@ -189,8 +190,11 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
   for (auto& p : h->Wq_store) cudaFree(p);
   for (auto& p : h->cb_store) cudaFree(p);
   for (auto& b : h->scratch) b.release();
-  h->batch_cache.release();
+  for (auto& b : h->batch_cache) b.release();
   for (auto& b : h->pinned) b.release();
+  for (auto& b : h->stage) b.release();
+  for (auto& ev : h->stage_ev)
+    if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -7,8 +7,11 @@
 // synchronises with the host inside the frame loop.  Beam slots are laid out frame-major (all
 // sentences' frame t are contiguous) so one LM step is one GEMM over a contiguous row range.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
+#include <string>
+#include <thread>
 
 #include "jlm_beam.cuh"
 
@@ -340,6 +343,8 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
 struct HostPlan {
   std::vector<int32_t> node_word, node_pfid, frame_lo, frame_hi, frame_ncand, frame_minpf, bc, sent_T, start_items;
   std::vector<int64_t> cand_pos, frame_cand_lo, slot0, fbase;
+  std::vector<int32_t> nstart;       // host only: nodes starting at each frame
+  std::vector<int64_t> sent_cand;    // host only: prefix sum of candidates per sorted sentence
   std::vector<SubsetJob> vocab_jobs;
   std::vector<DynJobInfo> dyn_info;
   std::vector<int32_t> vocab_cols, vfp;
@@ -347,6 +352,18 @@ struct HostPlan {
 
 template <class T>
 T* place(Arena& a, const std::vector<T>& v) { return a.take<T>(v.size() ? v.size() : 1); }
+
+template <class F>
+void run_threads(int nthreads, F&& work) {
+  if (nthreads == 1) {
+    work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int k = 1; k < nthreads; ++k) th.emplace_back(work, k);
+  work(0);
+  for (auto& t : th) t.join();
+}
 
 int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
   jlm_handle* h = b->h;
@@ -398,41 +415,77 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
   P.sent_T = b->sent_T;
   P.fbase = b->fbase;
 
-  std::vector<int32_t> nstart(F, 0);
-  int64_t n_cand_total = 0;
-  for (int p = 0; p < S; ++p) {
-    const int s = b->order[p];
-    const int T = b->sent_T[p];
-    const int64_t* fp = lat->frame_ptr + lat->frame_ptr_off[s];
-    const int64_t fb = b->fbase[p];
-    JLM_REQUIRE(fp[1] - fp[0] == 1 && lat->node_start[fp[0]] == -1,
-                "decode: frame 0 of sentence %d must hold exactly the <eos> node", s);
-    for (int t = 0; t <= T; ++t) {
-      JLM_REQUIRE(fp[t + 1] >= fp[t], "decode: frame_ptr not monotone (sentence %d)", s);
-      P.frame_lo[fb + t] = (int32_t)fp[t];
-      P.frame_hi[fb + t] = (int32_t)fp[t + 1];
-      int64_t ncand = 0;
-      int minpf = (int)(fb + t);
-      P.frame_cand_lo[fb + t] = n_cand_total;
-      for (int64_t n = fp[t]; n < fp[t + 1]; ++n) {
-        const int w = lat->node_word[n];
-        JLM_REQUIRE(w >= 0 && w < h->V, "decode: word id %d out of range", w);
-        if (t == 0) continue;
-        const int st = lat->node_start[n];
-        JLM_REQUIRE(st >= 0 && st < t, "decode: node %lld of sentence %d has start %d at frame %d", (long long)n, s, st, t);
-        P.node_pfid[n] = (int32_t)(fb + st);
-        nstart[fb + st] += 1;
-        P.cand_pos[n] = n_cand_total + ncand;
-        ncand += P.bc[fb + st];
-        minpf = std::min(minpf, (int)(fb + st));
+  // Sentences are independent: the per-node / per-frame tables are filled on host threads over contiguous
+  // ranges of sorted positions, candidate offsets first relative to the sentence, then shifted by a
+  // prefix sum over the sentences' candidate totals.
+  P.nstart.assign(F, 0);
+  std::vector<int32_t>& nstart = P.nstart;
+  P.sent_cand.assign((size_t)S + 1, 0);
+  int nthreads = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("JLM_HOST_THREADS")) nthreads = atoi(e);
+  nthreads = std::max(1, std::min(std::min(nthreads, 8), S / 128));
+  std::vector<std::string> errs(nthreads);
+  auto plo = [&](int k) { return (int)((int64_t)S * k / nthreads); };
+  const int W = b->W, V = h->V;
+  run_threads(nthreads, [&](int k) {
+    char msg[200];
+    for (int p = plo(k); p < plo(k + 1); ++p) {
+      const int s = b->order[p];
+      const int T = b->sent_T[p];
+      const int64_t* fp = lat->frame_ptr + lat->frame_ptr_off[s];
+      const int64_t fb = b->fbase[p];
+      if (!(fp[1] - fp[0] == 1 && lat->node_start[fp[0]] == -1)) {
+        snprintf(msg, sizeof(msg), "decode: frame 0 of sentence %d must hold exactly the <eos> node", s);
+        errs[k] = msg;
+        return;
       }
-      P.frame_minpf[fb + t] = minpf;
-      JLM_REQUIRE(ncand < (int64_t)1 << 31, "decode: too many candidates in one frame");
-      P.frame_ncand[fb + t] = (int32_t)ncand;
-      P.bc[fb + t] = t == 0 ? 1 : (int32_t)std::min<int64_t>(b->W, ncand);
-      n_cand_total += ncand;
+      int64_t cand = 0;
+      for (int t = 0; t <= T; ++t) {
+        if (fp[t + 1] < fp[t]) {
+          snprintf(msg, sizeof(msg), "decode: frame_ptr not monotone (sentence %d)", s);
+          errs[k] = msg;
+          return;
+        }
+        P.frame_lo[fb + t] = (int32_t)fp[t];
+        P.frame_hi[fb + t] = (int32_t)fp[t + 1];
+        int64_t ncand = 0;
+        int minpf = (int)(fb + t);
+        P.frame_cand_lo[fb + t] = cand;
+        for (int64_t n = fp[t]; n < fp[t + 1]; ++n) {
+          const int w = lat->node_word[n];
+          if (w < 0 || w >= V) {
+            snprintf(msg, sizeof(msg), "decode: word id %d out of range", w);
+            errs[k] = msg;
+            return;
+          }
+          if (t == 0) continue;
+          const int st = lat->node_start[n];
+          if (st < 0 || st >= t) {
+            snprintf(msg, sizeof(msg), "decode: node %lld of sentence %d has start %d at frame %d", (long long)n, s, st, t);
+            errs[k] = msg;
+            return;
+          }
+          P.node_pfid[n] = (int32_t)(fb + st);
+          nstart[fb + st] += 1;
+          P.cand_pos[n] = cand + ncand;
+          ncand += P.bc[fb + st];
+          minpf = std::min(minpf, (int)(fb + st));
+        }
+        P.frame_minpf[fb + t] = minpf;
+        if (ncand >= (int64_t)1 << 31) {
+          errs[k] = "decode: too many candidates in one frame";
+          return;
+        }
+        P.frame_ncand[fb + t] = (int32_t)ncand;
+        P.bc[fb + t] = t == 0 ? 1 : (int32_t)std::min<int64_t>(W, ncand);
+        cand += ncand;
+      }
+      P.sent_cand[p + 1] = cand;
     }
-  }
+  });
+  for (auto& e : errs) JLM_REQUIRE(e.empty(), "%s", e.c_str());
+  for (int p = 0; p < S; ++p) P.sent_cand[p + 1] += P.sent_cand[p];
+  const int64_t n_cand_total = P.sent_cand[S];
   b->bc = P.bc;
   b->n_cand = n_cand_total;
 
@@ -476,10 +529,21 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
       sp.n_items = (int)(item - sp.item0);
     }
     P.start_items.assign(std::max<int64_t>(item, 1), 0);
-    for (int64_t n = 0; n < N; ++n) {
-      const int pf = P.node_pfid[n];
-      if (pf >= 0) P.start_items[item_base[pf]++] = (int32_t)n;
-    }
+    // second pass over the sentences: shift the candidate offsets, fill the work list (a sentence's nodes
+    // only touch its own frames' counters)
+    run_threads(nthreads, [&](int k) {
+      for (int p = plo(k); p < plo(k + 1); ++p) {
+        const int s = b->order[p];
+        const int T = b->sent_T[p];
+        const int64_t* fp = lat->frame_ptr + lat->frame_ptr_off[s];
+        const int64_t fb = b->fbase[p], base = P.sent_cand[p];
+        for (int t = 0; t <= T; ++t) P.frame_cand_lo[fb + t] += base;
+        for (int64_t n = fp[1]; n < fp[T + 1]; ++n) {
+          P.cand_pos[n] += base;
+          P.start_items[item_base[P.node_pfid[n]]++] = (int32_t)n;
+        }
+      }
+    });
   }
 
   // per-step jobs
@@ -709,6 +773,11 @@ int32_t launch_prune(jlm_batch* b, int t) {
 
 }  // namespace
 
+void beam_free_plan_scratch(jlm_handle* h) {
+  delete static_cast<HostPlan*>(h->plan_scratch);
+  h->plan_scratch = nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -728,11 +797,22 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
   b->mode = mode;
   b->dynamic = mode == JLM_DECODE_DYNAMIC;
   b->use_lse = h->cfg.self_norm == 0;
-  HostPlan P;
+  // the plan's host vectors live with the handle so that steady-state uploads touch no fresh memory
+  if (!h->plan_scratch) h->plan_scratch = new HostPlan();
+  HostPlan& P = *static_cast<HostPlan*>(h->plan_scratch);
+  P.vocab_jobs.clear();
+  P.dyn_info.clear();
+  P.vocab_cols.clear();
+  P.vfp.clear();
+  static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+  const auto t_0 = now();
   if (build_plan(b, lat, P)) {
     delete b;
     return 1;
   }
+  const auto t_1 = now();
   if (backend == JLM_BACKEND_AUTO) backend = (b->max_rows_step >= 512) ? JLM_BACKEND_TC : JLM_BACKEND_EXACT;
   JLM_REQUIRE(backend == JLM_BACKEND_EXACT || backend == JLM_BACKEND_TC, "jlm_batch_upload: bad backend %d", backend);
   b->backend = backend;
@@ -742,7 +822,22 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
   layout(b, a, P);
   if (backend == JLM_BACKEND_TC) rc = tc_batch_plan(b, a);
   if (!rc) {
-    std::swap(b->mem, h->batch_cache);   // reuse the previous batch's allocation when it is big enough
+    // reuse a cached arena: the smallest one that is large enough, else grow the largest
+    const size_t need = a.off;
+    int pick = -1;
+    for (int i = 0; i < (int)h->batch_cache.size(); ++i) {
+      const size_t cap = h->batch_cache[i].cap;
+      if (pick < 0) pick = i;
+      else {
+        const size_t pc = h->batch_cache[pick].cap;
+        const bool better = (cap >= need && (pc < need || cap < pc)) || (cap < need && pc < need && cap > pc);
+        if (better) pick = i;
+      }
+    }
+    if (pick >= 0) {
+      std::swap(b->mem, h->batch_cache[pick]);
+      h->batch_cache.erase(h->batch_cache.begin() + pick);
+    }
     std::swap(a.buf, b->mem);
     rc = a.commit();
     std::swap(a.buf, b->mem);
@@ -755,11 +850,24 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
     const size_t plan_bytes = reinterpret_cast<char*>(b->d.slot_score) - reinterpret_cast<char*>(b->mem.p);
     if (backend == JLM_BACKEND_TC) rc = tc_batch_plan(b, a);
     a.buf = DevBuf();  // ownership stays with b->mem
-    if (!rc) rc = h->pinned[0].reserve(plan_bytes);
+    // pinned staging slot: wait only for the copy that last used this slot, never for the stream
+    const int slot = h->stage_next;
+    h->stage_next = (h->stage_next + 1) % jlm_handle::N_STAGE;
+    if (!rc && h->stage_busy[slot]) {
+      if (cudaEventSynchronize(h->stage_ev[slot]) != cudaSuccess) {
+        jlm_set_error("jlm_batch_upload: staging event sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+      }
+      h->stage_busy[slot] = false;
+    }
+    if (!rc && !h->stage_ev[slot] && cudaEventCreateWithFlags(&h->stage_ev[slot], cudaEventDisableTiming) != cudaSuccess) {
+      jlm_set_error("jlm_batch_upload: cudaEventCreate failed");
+      rc = 1;
+    }
+    if (!rc) rc = h->stage[slot].reserve(plan_bytes);
     if (!rc) {
-      char* host = h->pinned[0].as<char>();
+      char* host = h->stage[slot].as<char>();
       char* base = static_cast<char*>(b->mem.p);
-      memset(host, 0, plan_bytes);
       stage(host, base, b->d.node_word, P.node_word);
       stage(host, base, b->d.node_pfid, P.node_pfid);
       stage(host, base, b->d.cand_pos, P.cand_pos);
@@ -777,18 +885,17 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
       stage(host, base, b->d.dyn_info, P.dyn_info);
       stage(host, base, b->d.vocab_cols, P.vocab_cols);
       stage(host, base, b->d.vfp, P.vfp);
-      if (cudaMemcpyAsync(base, host, plan_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+      if (cudaMemcpyAsync(base, host, plan_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+          cudaEventRecord(h->stage_ev[slot], h->stream) != cudaSuccess) {
         jlm_set_error("jlm_batch_upload: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = 1;
+      } else {
+        h->stage_busy[slot] = true;
       }
       b->h2d_bytes = (int64_t)plan_bytes;
-      // the pinned staging buffer is reused by the next upload: wait for the copy
-      if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) {
-        jlm_set_error("jlm_batch_upload: sync failed: %s", cudaGetErrorString(cudaGetLastError()));
-        rc = 1;
-      }
     }
   }
+  if (dbg) fprintf(stderr, "[jlm] upload: build_plan %.3f ms, layout+stage+H2D enqueue %.3f ms\n", ms(t_0, t_1), ms(t_1, now()));
   if (rc) {
     jlm_batch_destroy(b);
     return 1;
@@ -924,7 +1031,10 @@ extern "C" int32_t jlm_batch_destroy(jlm_batch* b) {
   tc_batch_free(b);
   for (auto& e : b->events) cudaEventDestroy(e);
   for (auto& e : b->kev) cudaEventDestroy(e);
-  if (b->mem.cap > b->h->batch_cache.cap) std::swap(b->mem, b->h->batch_cache);
+  if (b->mem.p && b->h->batch_cache.size() < 8) {
+    b->h->batch_cache.push_back(b->mem);      // keep the arena for the next upload
+    b->mem = DevBuf();
+  }
   b->mem.release();
   delete b;
   return 0;

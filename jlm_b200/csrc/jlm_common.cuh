@@ -141,11 +141,20 @@ struct jlm_handle {
   uint8_t* Wq_store[JLM_MAX_SEGMENTS] = {};
   float* cb_store[JLM_MAX_SEGMENTS] = {};
   int q8_policy = -1;   // -1 auto, 0 never, 1 always (JLM_Q8)
+  void* plan_scratch = nullptr;   // host vectors of the last batch plan, reused by the next upload (jlm_beam.cu)
   TcWeights* tc = nullptr;
   // scratch for the model-level API and the batch engine
   DevBuf scratch[8];
-  DevBuf batch_cache;     // device memory of the last destroyed batch, reused by the next upload
+  // device arenas of destroyed batches, reused by later uploads (several batches can be in flight when
+  // a call is pipelined in chunks; the steady state allocates nothing)
+  std::vector<DevBuf> batch_cache;
   HostBuf pinned[4];
+  // pinned staging ring for the plan upload: a slot is reused only after its H2D copy completed
+  static constexpr int N_STAGE = 4;
+  HostBuf stage[N_STAGE];
+  cudaEvent_t stage_ev[N_STAGE] = {};
+  bool stage_busy[N_STAGE] = {};
+  int stage_next = 0;
   cudaEvent_t ev[4] = {};
 };
 
@@ -212,6 +221,8 @@ struct SubsetJob {
 template <typename TT>
 int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t ldt, const SubsetJob* jobs,
                       int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out);
+
+void beam_free_plan_scratch(jlm_handle* h);   // jlm_beam.cu
 
 // ---------------------------------------------------------------- tensor-core back end (jlm_tc.cu)
 int32_t tc_prepare_weights(jlm_handle* h);

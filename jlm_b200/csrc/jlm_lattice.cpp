@@ -9,11 +9,13 @@
 // (jlm_lexicon_create); here it is an open-addressing hash over UTF-32 code points with an
 // incrementally extended FNV-1a hash per start position, so a sentence costs O(T * max_reading) probes.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -37,13 +39,16 @@ struct jlm_lexicon {
   std::vector<uint32_t> chars;
   std::vector<int64_t> word_ptr;      // [n+1] into word_ids; entry index == position in word_ids
   std::vector<int32_t> word_ids;
-  std::vector<int32_t> table;         // open addressing, -1 = empty, else reading index
-  std::vector<uint32_t> tag;          // high hash bits of the slot's reading: rejects most misses without
-                                      // touching the reading itself
-  uint64_t mask = 0;
+  struct Slot { uint32_t tag; int32_t idx; };   // idx -1 = empty; tag = high hash bits of the slot's reading
+  std::vector<Slot> table;            // open addressing; one cache line access per probe
+  std::vector<uint64_t> bloom;        // 1 bit per hash value (cache resident): most substrings are not readings
+  uint64_t mask = 0, bloom_mask = 0;
 };
 
+struct LatPart;   // per-thread scratch of the build, kept with the object so its buffers are reused
+
 struct jlm_lattice {
+  std::vector<LatPart>* parts = nullptr;
   int32_t n_sent = 0;
   std::vector<int32_t> sent_len;
   std::vector<int64_t> frame_ptr_off, frame_ptr;
@@ -84,8 +89,11 @@ extern "C" int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading
   uint64_t cap = 16;
   while (cap < (uint64_t)n_readings * 2 + 2) cap <<= 1;
   L->mask = cap - 1;
-  L->table.assign(cap, -1);
-  L->tag.assign(cap, 0);
+  L->table.assign(cap, jlm_lexicon::Slot{0u, -1});
+  uint64_t bits = (uint64_t)1 << 15;
+  while (bits < (uint64_t)n_readings * 16 && bits < ((uint64_t)1 << 21)) bits <<= 1;
+  L->bloom.assign(bits / 64, 0);
+  L->bloom_mask = bits - 1;
   for (int32_t r = 0; r < n_readings; ++r) {
     const int64_t a = L->reading_ptr[r], b = L->reading_ptr[r + 1];
     if (b < a || L->word_ptr[r + 1] < L->word_ptr[r]) {
@@ -97,8 +105,8 @@ extern "C" int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading
     uint64_t h = FNV_OFF;
     for (int64_t k = a; k < b; ++k) h = fnv_step(h, L->chars[k]);
     uint64_t s = h & L->mask;
-    while (L->table[s] >= 0) {
-      const int32_t q = L->table[s];
+    while (L->table[s].idx >= 0) {
+      const int32_t q = L->table[s].idx;
       const int64_t qa = L->reading_ptr[q], qb = L->reading_ptr[q + 1];
       if (qb - qa == b - a && (b == a || memcmp(&L->chars[qa], &L->chars[a], sizeof(uint32_t) * (b - a)) == 0)) {
         delete L;
@@ -107,8 +115,9 @@ extern "C" int32_t jlm_lexicon_create(int32_t n_readings, const int64_t* reading
       }
       s = (s + 1) & L->mask;
     }
-    L->table[s] = r;
-    L->tag[s] = (uint32_t)(h >> 32);
+    L->table[s] = jlm_lexicon::Slot{(uint32_t)(h >> 32), r};
+    const uint64_t bb = (h >> 20) & L->bloom_mask;
+    L->bloom[bb >> 6] |= (uint64_t)1 << (bb & 63);
   }
   *out = L;
   return 0;
@@ -121,124 +130,193 @@ extern "C" int32_t jlm_lexicon_destroy(jlm_lexicon* lex) {
 
 namespace {
 
-// Builds sentences [s_lo, s_hi) into `lat` with node / vocabulary offsets relative to this chunk.
-int32_t build_range(const jlm_lexicon* L, int32_t s_lo, int32_t s_hi, const int64_t* text_ptr, const uint32_t* text,
-                    int32_t mode, int32_t n_extra, const int32_t* extra_ids, jlm_lattice* lat, char* err, size_t errn) {
-  struct Tmp { int32_t start, word, entry; };
-  std::vector<std::vector<Tmp>> frames;
-  std::vector<int32_t> scratch, seen_sorted, fresh;
-  if (mode != JLM_DECODE_FULL) lat->vocab_ptr.assign(1, 0);
-  if (mode == JLM_DECODE_DYNAMIC) lat->dup_ptr.assign(1, 0);
-  {
-    const size_t chars = (size_t)(text_ptr[s_hi] - text_ptr[s_lo]);
-    lat->node_start.reserve(chars * 12);
-    lat->node_word.reserve(chars * 12);
-    lat->node_entry.reserve(chars * 12);
-    lat->frame_ptr.reserve(chars + 2 * (size_t)(s_hi - s_lo));
+struct Match { int32_t i, end, reading; };
+
+}  // namespace
+
+// per-thread scratch of the two-pass build
+struct LatPart {
+  std::vector<Match> matches;
+  std::vector<int64_t> match_ptr;     // per sentence of the range (+1)
+  std::vector<int32_t> fcount;        // per frame of every sentence of the range: nodes ending there
+  std::vector<int32_t> vocab_ids, vocab_frame_ptr, dup_ids;
+  std::vector<int64_t> vocab_len, dup_len;
+  int32_t rc = 0;
+  char err[200] = "";
+  void reset() {
+    matches.clear(); match_ptr.clear(); fcount.clear(); vocab_ids.clear(); vocab_frame_ptr.clear(); dup_ids.clear();
+    vocab_len.clear(); dup_len.clear();
+    rc = 0;
   }
+};
+typedef LatPart Part;
+
+namespace {
+
+// finished lattice objects are recycled: their (page-touched) buffers make the next build cheaper
+std::mutex g_pool_mu;
+std::vector<jlm_lattice*> g_pool;
+
+// pass 1: probe every substring, remember the matches and how many nodes end at each frame
+void scan_range(const jlm_lexicon* L, int32_t s_lo, int32_t s_hi, const int64_t* text_ptr, const uint32_t* text,
+                Part* P, int64_t* node_total) {
+  P->match_ptr.assign(1, 0);
   for (int32_t s = s_lo; s < s_hi; ++s) {
     const int64_t t0 = text_ptr[s], t1 = text_ptr[s + 1];
     if (t1 < t0 || t1 - t0 > (int64_t)1 << 24) {
-      snprintf(err, errn, "jlm_lattice_build: bad text offsets for sentence %d", s);
-      return 1;
+      snprintf(P->err, sizeof(P->err), "jlm_lattice_build: bad text offsets for sentence %d", s);
+      P->rc = 1;
+      return;
     }
     const int32_t T = (int32_t)(t1 - t0);
     const uint32_t* tx = text + t0;
-    if ((int32_t)frames.size() < T + 1) frames.resize(T + 1);
-    for (int32_t t = 0; t <= T; ++t) frames[t].clear();
-    frames[0].push_back({-1, L->eos_id, -1});                       // decoder.py:89-90
+    const size_t f0 = P->fcount.size();
+    P->fcount.resize(f0 + T + 1, 0);
+    int32_t* fc = P->fcount.data() + f0;
+    fc[0] = 1;                                                       // '<eos>', decoder.py:89-90
     for (int32_t i = 0; i < T; ++i) {
       uint64_t h = FNV_OFF;
       const int32_t jmax = std::min(T - i, L->max_reading);
       for (int32_t j = 0; j < jmax; ++j) {
         h = fnv_step(h, tx[i + j]);
+        const uint64_t bb = (h >> 20) & L->bloom_mask;
+        if (!((L->bloom[bb >> 6] >> (bb & 63)) & 1)) continue;
         uint64_t slot = h & L->mask;
         const uint32_t tg = (uint32_t)(h >> 32);
-        while (L->table[slot] >= 0) {
-          const int32_t q = L->table[slot];
-          const int64_t qa = L->tag[slot] == tg ? L->reading_ptr[q] : 0;
-          if (L->tag[slot] == tg && L->reading_ptr[q + 1] - qa == j + 1 &&
-              memcmp(&L->chars[qa], tx + i, sizeof(uint32_t) * (j + 1)) == 0) {
-            std::vector<Tmp>& end = frames[i + j + 1];
-            for (int64_t e = L->word_ptr[q]; e < L->word_ptr[q + 1]; ++e)   // lexicon-id order, OOV already dropped
-              end.push_back({i, L->word_ids[e], (int32_t)e});
-            break;
+        while (L->table[slot].idx >= 0) {
+          if (L->table[slot].tag == tg) {
+            const int32_t q = L->table[slot].idx;
+            const int64_t qa = L->reading_ptr[q];
+            if (L->reading_ptr[q + 1] - qa == j + 1 && memcmp(&L->chars[qa], tx + i, sizeof(uint32_t) * (j + 1)) == 0) {
+              const int32_t nw = (int32_t)(L->word_ptr[q + 1] - L->word_ptr[q]);
+              if (nw) {
+                P->matches.push_back({i, i + j + 1, q});
+                fc[i + j + 1] += nw;
+              }
+              break;
+            }
           }
           slot = (slot + 1) & L->mask;
         }
-        if (j == 0 && frames[i + 1].empty()) frames[i + 1].push_back({i, L->unk_id, -2});   // decoder.py:129-130
       }
-      if (jmax == 0 && frames[i + 1].empty()) frames[i + 1].push_back({i, L->unk_id, -2});
     }
-    // CSR
-    lat->sent_len.push_back(T);
-    lat->frame_ptr_off.push_back((int64_t)lat->frame_ptr.size());
-    lat->frame_ptr.push_back((int64_t)lat->node_word.size());
+    int64_t total = 0;
     for (int32_t t = 0; t <= T; ++t) {
-      for (const Tmp& n : frames[t]) {
-        lat->node_start.push_back(n.start);
-        lat->node_word.push_back(n.word);
-        lat->node_entry.push_back(n.entry);
-      }
-      lat->frame_ptr.push_back((int64_t)lat->node_word.size());
+      if (fc[t] == 0) fc[t] = -1;          // empty frame -> the '<unk>' fallback node (decoder.py:129-130)
+      total += fc[t] < 0 ? 1 : fc[t];
     }
+    node_total[s] = total;
+    P->match_ptr.push_back((int64_t)P->matches.size());
+  }
+}
+
+// pass 2: place the nodes (frame-major; inside a frame start ascending, then lexicon-id order) and
+// derive the vocabulary lists of the sentence from its finished CSR slice
+void fill_range(const jlm_lexicon* L, int32_t s_lo, int32_t s_hi, const int64_t* text_ptr, int32_t mode, int32_t n_extra,
+                const int32_t* extra_ids, const int64_t* node_off, jlm_lattice* lat, Part* P) {
+  std::vector<int64_t> cursor;
+  std::vector<int32_t> scratch, seen_sorted, fresh;
+  size_t f0 = 0;
+  for (int32_t s = s_lo; s < s_hi; ++s) {
+    const int32_t T = (int32_t)(text_ptr[s + 1] - text_ptr[s]);
+    const int32_t* fc = P->fcount.data() + f0;
+    f0 += T + 1;
+    lat->sent_len[s] = T;
+    int64_t* fp = lat->frame_ptr.data() + lat->frame_ptr_off[s];
+    cursor.resize(T + 1);
+    int64_t pos = node_off[s];
+    for (int32_t t = 0; t <= T; ++t) {
+      fp[t] = pos;
+      cursor[t] = pos;
+      pos += fc[t] < 0 ? 1 : fc[t];
+    }
+    fp[T + 1] = pos;
+    lat->node_start[fp[0]] = -1;
+    lat->node_word[fp[0]] = L->eos_id;
+    lat->node_entry[fp[0]] = -1;
+    for (int32_t t = 1; t <= T; ++t)
+      if (fc[t] < 0) {
+        lat->node_start[fp[t]] = t - 1;
+        lat->node_word[fp[t]] = L->unk_id;
+        lat->node_entry[fp[t]] = -2;
+      }
+    const int32_t ls = s - s_lo;
+    for (int64_t m = P->match_ptr[ls]; m < P->match_ptr[ls + 1]; ++m) {
+      const Match& mt = P->matches[m];
+      int64_t c = cursor[mt.end];
+      for (int64_t e = L->word_ptr[mt.reading]; e < L->word_ptr[mt.reading + 1]; ++e, ++c) {
+        lat->node_start[c] = mt.i;
+        lat->node_word[c] = L->word_ids[e];
+        lat->node_entry[c] = (int32_t)e;
+      }
+      cursor[mt.end] = c;
+    }
+    if (mode == JLM_DECODE_FULL) continue;
     const int32_t* extra = n_extra ? extra_ids + (int64_t)s * n_extra : nullptr;
+    const int32_t* words = lat->node_word.data();
     if (mode == JLM_DECODE_STATIC_VOCAB) {
       // decoder.py:142-151: sorted(set(all node words)) (+ samples, re-sorted, de-duplicated)
-      scratch.clear();
-      for (int32_t t = 0; t <= T; ++t)
-        for (const Tmp& n : frames[t]) scratch.push_back(n.word);
+      scratch.assign(words + fp[0], words + fp[T + 1]);
       for (int32_t k = 0; k < n_extra; ++k) scratch.push_back(extra[k]);
       std::sort(scratch.begin(), scratch.end());
       scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
-      lat->vocab_ids.insert(lat->vocab_ids.end(), scratch.begin(), scratch.end());
-      lat->vocab_ptr.push_back((int64_t)lat->vocab_ids.size());
-    } else if (mode == JLM_DECODE_DYNAMIC) {
+      P->vocab_ids.insert(P->vocab_ids.end(), scratch.begin(), scratch.end());
+      P->vocab_len.push_back((int64_t)scratch.size());
+    } else {
       // decoder_dynamic.py:30-46: lattice_vocab[0] = sorted(frame-0 words) + samples (duplicates kept),
       // lattice_vocab[i] = lattice_vocab[i-1] | words ending at i.  Emitted as columns ordered by first
       // appearance + per-frame boundaries + the duplicate entries of frame 0.
-      scratch.clear();
-      for (const Tmp& n : frames[0]) scratch.push_back(n.word);
+      scratch.assign(words + fp[0], words + fp[1]);
       std::sort(scratch.begin(), scratch.end());
       for (int32_t k = 0; k < n_extra; ++k) scratch.push_back(extra[k]);
       seen_sorted = scratch;
       std::sort(seen_sorted.begin(), seen_sorted.end());
       seen_sorted.erase(std::unique(seen_sorted.begin(), seen_sorted.end()), seen_sorted.end());
+      size_t nd = 0;
       {  // duplicates: every occurrence beyond the first, in list order
         std::vector<char> used(seen_sorted.size(), 0);
         for (int32_t v : scratch) {
           const size_t k = std::lower_bound(seen_sorted.begin(), seen_sorted.end(), v) - seen_sorted.begin();
-          if (used[k]) lat->dup_ids.push_back(v); else used[k] = 1;
+          if (used[k]) {
+            P->dup_ids.push_back(v);
+            ++nd;
+          } else {
+            used[k] = 1;
+          }
         }
       }
-      const int64_t base = (int64_t)lat->vocab_ids.size();
-      lat->vocab_ids.insert(lat->vocab_ids.end(), seen_sorted.begin(), seen_sorted.end());
-      lat->vocab_frame_ptr.push_back(0);
-      lat->vocab_frame_ptr.push_back((int32_t)seen_sorted.size());
+      const size_t base = P->vocab_ids.size();
+      P->vocab_ids.insert(P->vocab_ids.end(), seen_sorted.begin(), seen_sorted.end());
+      P->vocab_frame_ptr.push_back(0);
+      P->vocab_frame_ptr.push_back((int32_t)seen_sorted.size());
       for (int32_t t = 1; t <= T; ++t) {
         fresh.clear();
-        for (const Tmp& n : frames[t])
-          if (!std::binary_search(seen_sorted.begin(), seen_sorted.end(), n.word)) fresh.push_back(n.word);
+        for (int64_t n = fp[t]; n < fp[t + 1]; ++n)
+          if (!std::binary_search(seen_sorted.begin(), seen_sorted.end(), words[n])) fresh.push_back(words[n]);
         std::sort(fresh.begin(), fresh.end());
         fresh.erase(std::unique(fresh.begin(), fresh.end()), fresh.end());
-        lat->vocab_ids.insert(lat->vocab_ids.end(), fresh.begin(), fresh.end());
+        P->vocab_ids.insert(P->vocab_ids.end(), fresh.begin(), fresh.end());
         const size_t mid = seen_sorted.size();
         seen_sorted.insert(seen_sorted.end(), fresh.begin(), fresh.end());
         std::inplace_merge(seen_sorted.begin(), seen_sorted.begin() + mid, seen_sorted.end());
-        lat->vocab_frame_ptr.push_back((int32_t)((int64_t)lat->vocab_ids.size() - base));
+        P->vocab_frame_ptr.push_back((int32_t)(P->vocab_ids.size() - base));
       }
-      lat->vocab_ptr.push_back((int64_t)lat->vocab_ids.size());
-      lat->dup_ptr.push_back((int64_t)lat->dup_ids.size());
+      P->vocab_len.push_back((int64_t)(P->vocab_ids.size() - base));
+      P->dup_len.push_back((int64_t)nd);
     }
   }
-  return 0;
 }
 
-template <class T>
-void append(std::vector<T>& dst, const std::vector<T>& src, T add, size_t skip = 0) {
-  const size_t o = dst.size();
-  dst.resize(o + src.size() - skip);
-  for (size_t i = skip; i < src.size(); ++i) dst[o + i - skip] = src[i] + add;
+template <class F>
+void run_threads(int nthreads, F&& work) {
+  if (nthreads == 1) {
+    work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int k = 1; k < nthreads; ++k) th.emplace_back(work, k);
+  work(0);
+  for (auto& t : th) t.join();
 }
 
 }  // namespace
@@ -250,58 +328,75 @@ extern "C" int32_t jlm_lattice_build(const jlm_lexicon* L, int32_t n_sent, const
   LAT_REQUIRE(mode >= JLM_DECODE_FULL && mode <= JLM_DECODE_DYNAMIC, "jlm_lattice_build: bad mode %d", mode);
   LAT_REQUIRE(n_extra >= 0 && (n_extra == 0 || extra_ids), "jlm_lattice_build: extra ids missing");
   *out = nullptr;
-  // sentences are independent: build contiguous chunks on host threads, then concatenate
+  // sentences are independent: two passes over contiguous ranges on host threads (scan + count, then
+  // fill at the offsets of a prefix sum), so the arrays are written once, in place
   int nthreads = (int)std::thread::hardware_concurrency();
   if (const char* e = getenv("JLM_HOST_THREADS")) nthreads = atoi(e);
-  nthreads = std::max(1, std::min(std::min(nthreads, 8), n_sent / 512));
-  std::vector<jlm_lattice> part(nthreads);
-  std::vector<int32_t> rc(nthreads, 0);
-  std::vector<std::vector<char>> err(nthreads, std::vector<char>(256, 0));
-  auto work = [&](int k) {
-    const int32_t lo = (int32_t)((int64_t)n_sent * k / nthreads), hi = (int32_t)((int64_t)n_sent * (k + 1) / nthreads);
-    rc[k] = build_range(L, lo, hi, text_ptr, text, mode, n_extra, extra_ids, &part[k], err[k].data(), err[k].size());
-  };
-  if (nthreads == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> th;
-    for (int k = 0; k < nthreads; ++k) th.emplace_back(work, k);
-    for (auto& t : th) t.join();
+  nthreads = std::max(1, std::min(std::min(nthreads, 8), n_sent / 128));
+  static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+  const auto t_0 = now();
+  jlm_lattice* lat = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (!g_pool.empty()) {
+      lat = g_pool.back();
+      g_pool.pop_back();
+    }
   }
+  if (!lat) lat = new jlm_lattice();
+  if (!lat->parts) lat->parts = new std::vector<LatPart>();
+  std::vector<Part>& part = *lat->parts;
+  if ((int)part.size() < nthreads) part.resize(nthreads);
+  for (auto& p : part) p.reset();
+  std::vector<int64_t> node_off((size_t)n_sent + 1, 0);
+  auto lo = [&](int k) { return (int32_t)((int64_t)n_sent * k / nthreads); };
+  run_threads(nthreads, [&](int k) { scan_range(L, lo(k), lo(k + 1), text_ptr, text, &part[k], node_off.data() + 1); });
   for (int k = 0; k < nthreads; ++k)
-    if (rc[k]) {
-      jlm_set_error("%s", err[k].data());
+    if (part[k].rc) {
+      jlm_set_error("%s", part[k].err);
+      jlm_lattice_destroy(lat);
       return 1;
     }
-  jlm_lattice* lat = new jlm_lattice();
-  if (nthreads == 1) {
-    *lat = std::move(part[0]);
-  } else {
-    if (mode != JLM_DECODE_FULL) lat->vocab_ptr.assign(1, 0);
-    if (mode == JLM_DECODE_DYNAMIC) lat->dup_ptr.assign(1, 0);
-    for (int k = 0; k < nthreads; ++k) {
-      const jlm_lattice& p = part[k];
-      const int64_t node0 = (int64_t)lat->node_word.size(), fp0 = (int64_t)lat->frame_ptr.size();
-      append(lat->sent_len, p.sent_len, 0);
-      append(lat->frame_ptr_off, p.frame_ptr_off, fp0);
-      append(lat->frame_ptr, p.frame_ptr, node0);
-      append(lat->node_start, p.node_start, 0);
-      append(lat->node_word, p.node_word, 0);
-      append(lat->node_entry, p.node_entry, 0);
-      if (mode != JLM_DECODE_FULL) {
-        append(lat->vocab_ptr, p.vocab_ptr, (int64_t)lat->vocab_ids.size(), 1);
-        append(lat->vocab_ids, p.vocab_ids, 0);
-      }
-      if (mode == JLM_DECODE_DYNAMIC) {
-        append(lat->vocab_frame_ptr, p.vocab_frame_ptr, 0);
-        append(lat->dup_ptr, p.dup_ptr, (int64_t)lat->dup_ids.size(), 1);
-        append(lat->dup_ids, p.dup_ids, 0);
-      }
-    }
-  }
+  const auto t_1 = now();
+  lat->vocab_ptr.clear(); lat->vocab_ids.clear(); lat->vocab_frame_ptr.clear(); lat->dup_ptr.clear(); lat->dup_ids.clear();
   lat->n_sent = n_sent;
   lat->mode = mode;
-  if (mode == JLM_DECODE_DYNAMIC && lat->dup_ids.empty()) lat->dup_ids.push_back(0);   // keep the pointer non-null
+  lat->sent_len.resize(n_sent);
+  lat->frame_ptr_off.resize(n_sent);
+  int64_t fpo = 0;
+  for (int32_t s = 0; s < n_sent; ++s) {
+    node_off[s + 1] += node_off[s];
+    lat->frame_ptr_off[s] = fpo;
+    fpo += (text_ptr[s + 1] - text_ptr[s]) + 2;
+  }
+  lat->frame_ptr.resize(fpo);
+  lat->node_start.resize(node_off[n_sent]);
+  lat->node_word.resize(node_off[n_sent]);
+  lat->node_entry.resize(node_off[n_sent]);
+  const auto t_2 = now();
+  run_threads(nthreads, [&](int k) {
+    fill_range(L, lo(k), lo(k + 1), text_ptr, mode, n_extra, extra_ids, node_off.data(), lat, &part[k]);
+  });
+  if (dbg)
+    fprintf(stderr, "[jlm] lattice_build: %d threads, scan %.3f ms, alloc %.3f ms, fill %.3f ms\n", nthreads, ms(t_0, t_1),
+            ms(t_1, t_2), ms(t_2, now()));
+  if (mode != JLM_DECODE_FULL) {
+    lat->vocab_ptr.assign(1, 0);
+    if (mode == JLM_DECODE_DYNAMIC) lat->dup_ptr.assign(1, 0);
+    for (int k = 0; k < nthreads; ++k) {
+      const Part& p = part[k];
+      lat->vocab_ids.insert(lat->vocab_ids.end(), p.vocab_ids.begin(), p.vocab_ids.end());
+      for (int64_t n : p.vocab_len) lat->vocab_ptr.push_back(lat->vocab_ptr.back() + n);
+      if (mode == JLM_DECODE_DYNAMIC) {
+        lat->vocab_frame_ptr.insert(lat->vocab_frame_ptr.end(), p.vocab_frame_ptr.begin(), p.vocab_frame_ptr.end());
+        lat->dup_ids.insert(lat->dup_ids.end(), p.dup_ids.begin(), p.dup_ids.end());
+        for (int64_t n : p.dup_len) lat->dup_ptr.push_back(lat->dup_ptr.back() + n);
+      }
+    }
+    if (mode == JLM_DECODE_DYNAMIC && lat->dup_ids.empty()) lat->dup_ids.push_back(0);   // keep the pointer non-null
+  }
   *out = lat;
   return 0;
 }
@@ -331,6 +426,15 @@ extern "C" int32_t jlm_lattice_view(const jlm_lattice* lat, jlm_lattice_batch* v
 }
 
 extern "C" int32_t jlm_lattice_destroy(jlm_lattice* lat) {
+  if (!lat) return 0;
+  {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.size() < 4) {
+      g_pool.push_back(lat);
+      return 0;
+    }
+  }
+  delete lat->parts;
   delete lat;
   return 0;
 }

@@ -118,6 +118,53 @@ class Decoder(object):
             out.append(res[:topN])
         return out
 
+    def _run_texts(self, texts, mode, extra, topN, beam_width, backend, n_chunks=0):
+        """One jlm_decode_texts call: kana strings in, n-best word lists out; lattice build, plan and
+        device work are pipelined over chunks inside the library."""
+        lib, h = self._lib, self.model._handle
+        if beam_width is None:
+            beam_width = _lib.MAX_BEAM
+        top = max(1, min(int(topN), int(beam_width)))
+        nlex = self._native()
+        S = len(texts)
+        lens = np.fromiter((len(t) for t in texts), dtype=np.int64, count=S)
+        tptr = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(lens, out=tptr[1:])
+        joined = ''.join(texts)
+        cps = np.frombuffer(joined.encode('utf-32-le'), dtype=np.uint32) if joined else np.zeros(1, dtype=np.uint32)
+        n_extra = 0
+        if extra is not None:
+            extra = np.ascontiguousarray(extra, dtype=np.int32).reshape(S, -1)
+            n_extra = extra.shape[1]
+        max_len = int(lens.max()) + 1
+        scores = np.empty((S, top))
+        n_paths = np.empty(S, dtype=np.int32)
+        path_len = np.empty((S, top), dtype=np.int32)
+        path_entry = np.zeros((S, top, max_len), dtype=np.int32)
+        path_start = np.zeros((S, top, max_len), dtype=np.int32)
+        nb = _lib.TextNBest()
+        nb.top_n, nb.max_len = top, max_len
+        nb.scores, nb.n_paths = _lib.ptr(scores, C.c_double), _lib.ptr(n_paths, C.c_int32)
+        nb.path_len = _lib.ptr(path_len, C.c_int32)
+        nb.path_entry, nb.path_start = _lib.ptr(path_entry, C.c_int32), _lib.ptr(path_start, C.c_int32)
+        info = _lib.BatchInfo()
+        _lib.check(lib.jlm_decode_texts(h, nlex.handle, S, _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
+                                        int(beam_width), top, int(mode), n_extra,
+                                        _lib.ptr(extra, C.c_int32) if n_extra else None, int(backend), int(n_chunks),
+                                        C.byref(nb), C.byref(info)))
+        self.last_info = info
+        ew = nlex.entry_words
+        out = []
+        for s in range(S):
+            res, text = [], texts[s]
+            for k in range(int(n_paths[s])):
+                n = int(path_len[s, k])
+                ents, starts = path_entry[s, k, :n].tolist(), path_start[s, k, :n].tolist()
+                # '<eos>' (-1) is dropped (decoder.py:237); '<unk>' (-2) carries the raw kana (decoder.py:130)
+                res.append((float(scores[s, k]), [ew[e] if e >= 0 else text[st] for e, st in zip(ents, starts) if e != -1]))
+            out.append(res[:topN])
+        return out
+
     def _collect_trace(self, batch, packed, W):
         """Per-frame pruned beams of every sentence (test / debugging aid)."""
         lib = self._lib
@@ -189,6 +236,10 @@ class Decoder(object):
         if native_lattice and inputs and (vocab_select or not self.lattice_vocab):
             mode = _lib.DECODE_STATIC_VOCAB if vocab_select else _lib.DECODE_FULL
             extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling) if vocab_select else None
+            if not getattr(self, '_want_trace', False) and not vocab_select:
+                out = self._run_texts(inputs, mode, extra, topN, beam_width, backend)
+                self._log_batch_perf(len(inputs))
+                return out
             packed = lattice.NativeLattices(self._native(), inputs, mode, extra)
             out = self._run(packed, mode, topN, beam_width, backend, timers=True)
             if vocab_select:

@@ -61,8 +61,11 @@ class DynamicDecoder(Decoder):
         inputs = list(inputs)
         if native_lattice and inputs and vocab_select:
             extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling)
-            packed = lattice.NativeLattices(self._native(), inputs, _lib.DECODE_DYNAMIC, extra)
-            out = self._run(packed, _lib.DECODE_DYNAMIC, topN, beam_width, backend, timers=True)
+            if not getattr(self, '_want_trace', False):
+                out = self._run_texts(inputs, _lib.DECODE_DYNAMIC, extra, topN, beam_width, backend)
+            else:
+                packed = lattice.NativeLattices(self._native(), inputs, _lib.DECODE_DYNAMIC, extra)
+                out = self._run(packed, _lib.DECODE_DYNAMIC, topN, beam_width, backend, timers=True)
         else:
             _, out = self._decode_many(inputs, topN, beam_width, vocab_select, samples, top_sampling,
                                        random_sampling, backend, timers=True)

@@ -316,3 +316,29 @@ def test_quantized_blocks_match_decoded_floats(mode, tmp_path_factory, monkeypat
     bad = np.ascontiguousarray(cbk.reshape(-1) + np.float32(1e-3))
     rc = dq._lib.jlm_set_quantized_block(dq.model._handle, 0, _lib.ptr(code, C.c_uint8), _lib.ptr(bad, C.c_float), len(bad))
     assert rc != 0 and b'differs from the float32 weight' in dq._lib.jlm_last_error()
+
+
+def test_decode_texts_pipeline_equals_unpipelined(tmp_path_factory):
+    """jlm_decode_texts (text in, chunks pipelined inside the library) == the Python-lattice, single-batch path,
+    for the static and the dynamic decoder, whatever the number of chunks."""
+    import jlm_b200
+    from jlm_b200 import _lib, config, synth
+    dec, case, _ = get_decoder('small_tied', tmp_path_factory)
+    _, _, _, lexicon, _, _ = build_case('small_tied')
+    sents = synth.make_sentences(lexicon, 600, min_len=8, seed=31, vocab_size=case['vocab_size']) + ['', 'ヰ']
+    dec._want_trace = False
+    try:
+        want = dec.decode_batch(sents, topN=4, beam_width=5, backend=EXACT, native_lattice=False)
+        got = dec.decode_batch(sents, topN=4, beam_width=5, backend=EXACT)           # automatic chunking (2)
+        assert got == want
+        for chunks in (1, 3, 7):
+            assert dec._run_texts(sents, _lib.DECODE_FULL, None, 4, 5, EXACT, n_chunks=chunks) == want
+        assert dec.last_info.kernel_launches > 0 and dec.last_info.n_slots > 0
+        # dynamic decoder, top sampling (same experiment; other tests may have moved the config root)
+        dd, _, _ = get_decoder('small_tied_dyn_top', tmp_path_factory)
+        dd._want_trace = False
+        kw = dict(topN=4, beam_width=5, vocab_select=True, samples=20, top_sampling=True, backend=EXACT)
+        assert dd.decode_batch(sents[:300], **kw) == dd.decode_batch(sents[:300], native_lattice=False, **kw)
+        dd._want_trace = True
+    finally:
+        dec._want_trace = True

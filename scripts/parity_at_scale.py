@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Tensor-core back end vs the float64 exact back end on a full-size lock-step batch (cfg 2 shape):
+how many n-best lists / top-1 results are identical, and the worst score difference."""
+import os
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import jlm_b200  # noqa: E402
+from jlm_b200 import config, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+root = tempfile.mkdtemp(prefix='jlm_par_')
+cfg, weights, lexicon, reading = synth.make_experiment(root, 1, 50000, 512, 256, 'tied', seed=0)
+sents = synth.make_sentences(lexicon, n, min_len=20, seed=321, vocab_size=50000)
+config.set_root(root)
+dec = jlm_b200.Decoder(1)
+a = dec.decode_batch(sents, topN=10, beam_width=10, backend=1)
+b = dec.decode_batch(sents, topN=10, beam_width=10, backend=2)
+same = sum([w for _, w in x] == [w for _, w in y] for x, y in zip(a, b))
+top1 = sum(x[0][1] == y[0][1] for x, y in zip(a, b))
+worst = max(abs(p[0] - q[0]) for x, y in zip(a, b) for p, q in zip(x, y))
+gaps = sorted(min(abs(x[i + 1][0] - x[i][0]) for i in range(len(x) - 1)) for x in a if len(x) > 1)
+print('sentences %d: identical n-best %d, identical top-1 %d, worst |score diff| %.3e, smallest adjacent n-best gap %.3e (median %.3e)'
+      % (n, same, top1, worst, gaps[0], gaps[len(gaps) // 2]))

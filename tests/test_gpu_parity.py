@@ -205,11 +205,11 @@ def test_decode_tc_full_size(name, tmp_path_factory):
 
 
 def test_tc_matches_exact_on_a_lockstep_batch(tmp_path_factory):
-    """configs[1] shape, 64 sentences decoded in lock-step: tensor-core beams == float64 beams."""
+    """configs[1] shape, 512 sentences decoded in lock-step: tensor-core beams == float64 beams."""
     from jlm_b200 import synth
     dec, case, _ = get_decoder('cfg2_tied', tmp_path_factory)
     _, _, _, lexicon, _, _ = build_case('cfg2_tied')
-    sents = synth.make_sentences(lexicon, 64, min_len=20, seed=77, vocab_size=case['vocab_size'])
+    sents = synth.make_sentences(lexicon, 512, min_len=20, seed=77, vocab_size=case['vocab_size'])
     dec._want_trace = False
     try:
         a = dec.decode_batch(sents, topN=10, beam_width=10, backend=EXACT)
@@ -219,9 +219,9 @@ def test_tc_matches_exact_on_a_lockstep_batch(tmp_path_factory):
     same = sum([w for _, w in x] == [w for _, w in y] for x, y in zip(a, b))
     top1 = sum(x[0][1] == y[0][1] for x, y in zip(a, b))
     worst = max(abs(p[0] - q[0]) for x, y in zip(a, b) for p, q in zip(x, y))
-    print('lock-step 64: identical n-best %d/64, identical top-1 %d/64, worst score diff %.3e' % (same, top1, worst))
-    assert top1 == 64
-    assert same == 64
+    print('lock-step 512: identical n-best %d/512, identical top-1 %d/512, worst score diff %.3e' % (same, top1, worst))
+    assert top1 == 512
+    assert same == 512
     assert worst < 1e-3
 
 

@@ -191,6 +191,7 @@ def main():
     ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--chunks', type=int, default=0, help='e2e arm: pipeline chunks of jlm_decode_texts (0 = automatic)')
+    ap.add_argument('--e2e-depth', type=int, default=2, help='e2e arm: batches in flight through submit/collect')
     ap.add_argument('--profile', action='store_true', help='1 warm-up + K plain steps only (for ncu); prints no JSON')
     args = ap.parse_args()
 
@@ -335,27 +336,49 @@ def main():
     tnb.path_len = _lib.ptr(t_len, C.c_int32)
     tnb.path_entry, tnb.path_start = _lib.ptr(t_entry, C.c_int32), _lib.ptr(t_start, C.c_int32)
 
-    def e2e_step():
-        # ONE public call: lattice build, plan, H2D, every frame, D2H, pipelined over chunks in the library
-        _lib.check(lib.jlm_decode_texts(hdl, nlex.handle, len(sents), _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
-                                        BEAM, TOPN, MODE, n_extra, _lib.ptr(extra, C.c_int32) if n_extra else None,
-                                        args.backend, args.chunks, C.byref(tnb), None))
+    def e2e_submit():
+        # public streaming call, first half: lattice build, plan, H2D, every frame + the n-best D2H enqueued
+        job = C.c_void_p()
+        _lib.check(lib.jlm_decode_texts_submit(hdl, nlex.handle, len(sents), _lib.ptr(tptr, C.c_int64),
+                                               _lib.ptr(cps, C.c_uint32), BEAM, TOPN, MODE, n_extra,
+                                               _lib.ptr(extra, C.c_int32) if n_extra else None, args.backend,
+                                               args.chunks, 0, C.byref(job)))
+        return job
+
+    def e2e_collect(job):
+        # second half: wait for that job, n-best (lexicon entries) into host arrays
+        _lib.check(lib.jlm_decode_texts_collect(job, C.byref(tnb), None))
+
+    def e2e_run(n_steps, depth):
+        """n_steps batches through submit/collect with at most `depth` in flight (depth 1 = the blocking
+        jlm_decode_texts call); every batch is built from the host text again, copied H2D, decoded, copied
+        D2H and unpacked inside the timed region."""
+        barrier()
+        t0 = time.perf_counter()
+        inflight = []
+        for _ in range(n_steps):
+            inflight.append(e2e_submit())
+            if len(inflight) >= depth:
+                e2e_collect(inflight.pop(0))
+        while inflight:
+            e2e_collect(inflight.pop(0))
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
 
     for _ in range(2):
-        e2e_step()
+        e2e_collect(e2e_submit())
     # the e2e arm must reproduce the device-resident arm: same scores, same paths (as lexicon entries)
     assert np.array_equal(t_scores, scores) and np.array_equal(t_len, path_len), 'e2e arm and device-resident arm disagree'
     for s_i in (0, S // 2, S - 1):
         ids = path_nodes[s_i, 0, :path_len[s_i, 0]]
         assert np.array_equal(packed.node_entry[ids], t_entry[s_i, 0, :t_len[s_i, 0]]), 'e2e paths differ'
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_run(args.e2e_depth + 2, args.e2e_depth)      # untimed warm-up: the second in-flight arena is allocated here
+    e2e_s = e2e_run(args.steps, args.e2e_depth)
+    assert np.array_equal(t_scores, scores) and np.array_equal(t_len, path_len), 'streamed e2e arm disagrees'
+    e2e_blocking_s = e2e_run(args.steps, 1)
     t_load1 = time.perf_counter()
     e2e = total_chars * args.steps / e2e_s
+    e2e_blocking = total_chars * args.steps / e2e_blocking_s
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
     # one more upload to read the byte counters of a single call
     b2 = C.c_void_p()
@@ -448,8 +471,11 @@ def main():
                    'wall_s_timed_region': wall},
         'e2e': {'value': e2e, 'unit': 'chars/s', 'h2d_bytes_per_step': int(i2.h2d_bytes),
                 'd2h_bytes_per_step': int(i2.d2h_bytes),
-                'call': 'jlm_decode_texts (host UTF-32 kana -> host n-best paths; lattice build, plan, H2D, frames, D2H '
-                        'pipelined over chunks inside the call)'},
+                'call': 'jlm_decode_texts_submit + jlm_decode_texts_collect, %d batches in flight (host UTF-32 kana -> '
+                        'host n-best paths; per batch: lattice build, plan, H2D, frames, D2H, unpack - all inside the '
+                        'timed region; the host work of batch k+1 overlaps the device work of batch k)' % args.e2e_depth,
+                'blocking_value': e2e_blocking,
+                'blocking_call': 'jlm_decode_texts (one blocking call per batch, nothing overlapped)'},
         'gpu_launches': launches,
         'roofline': roof,
         'cpu_baseline': {'value': cpu_chars / cpu_s if world == 1 else None, 'unit': 'chars/s', 'cores': os.cpu_count(),

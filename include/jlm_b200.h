@@ -207,12 +207,30 @@ int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, 
                          const int32_t* extra_ids, int32_t backend, int32_t n_chunks, jlm_text_nbest* out,
                          struct jlm_batch_info_s* info /* nullable: totals over the chunks, enables the timers */);
 
+/* jlm_decode_texts split in two for streaming callers (a server decoding batch after batch): submit
+ * builds the lattices and the plan, copies the plan to the device and enqueues every frame plus the
+ * n-best device->host copy, then returns without waiting; collect waits for THAT job only, fills `out`
+ * and frees the job.  Submitting job k+1 before collecting job k hides all host work behind the device
+ * work of job k (one handle, one stream, jobs complete in submission order).  The text buffers may be
+ * reused as soon as submit returns; `timers` != 0 enables the CUDA-event buckets reported by collect.
+ * collect consumes the job even when it fails; cancel waits for and discards a job. */
+typedef struct jlm_text_job jlm_text_job;
+int32_t jlm_decode_texts_submit(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, const int64_t* text_ptr,
+                                const uint32_t* text, int32_t beam_width, int32_t top_n, int32_t mode,
+                                int32_t n_extra, const int32_t* extra_ids, int32_t backend, int32_t n_chunks,
+                                int32_t timers, jlm_text_job** job);
+int32_t jlm_decode_texts_collect(jlm_text_job* job, jlm_text_nbest* out, struct jlm_batch_info_s* info /* nullable */);
+int32_t jlm_decode_texts_cancel(jlm_text_job* job);
+
 /* The same call split in three so a benchmark can time the device part with the lattices already
  * resident in HBM: upload (plan + H2D), run (enqueue every frame, asynchronous), fetch (D2H). */
 int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
                          int32_t mode, int32_t backend, jlm_batch** out);
 int32_t jlm_batch_run(jlm_batch* b);
 int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out);
+/* enqueue the n-best device->host copy behind the batch's kernels without waiting; jlm_batch_fetch and
+ * jlm_batch_destroy then wait for this batch's completion event only, not for the whole stream */
+int32_t jlm_batch_fetch_async(jlm_batch* b);
 int32_t jlm_batch_destroy(jlm_batch* b);
 
 /* Introspection used by the parity tests and the benchmark. */

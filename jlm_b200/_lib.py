@@ -73,6 +73,11 @@ SYMBOLS = {
                                      C.POINTER(NBest)]),
     'jlm_decode_texts': (C.c_int32, [_VP, _VP, C.c_int32, _i64p, _u32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p,
                                      C.c_int32, C.c_int32, C.POINTER(TextNBest), C.POINTER(BatchInfo)]),
+    'jlm_decode_texts_submit': (C.c_int32, [_VP, _VP, C.c_int32, _i64p, _u32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            _i32p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    'jlm_decode_texts_collect': (C.c_int32, [_VP, C.POINTER(TextNBest), C.POINTER(BatchInfo)]),
+    'jlm_decode_texts_cancel': (C.c_int32, [_VP]),
+    'jlm_batch_fetch_async': (C.c_int32, [_VP]),
     'jlm_batch_upload': (C.c_int32, [_VP, C.POINTER(LatticeBatch), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.POINTER(_VP)]),
     'jlm_batch_run': (C.c_int32, [_VP]),

@@ -191,6 +191,7 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
   for (auto& p : h->cb_store) cudaFree(p);
   for (auto& b : h->scratch) b.release();
   for (auto& b : h->batch_cache) b.release();
+  for (auto& b : h->out_pool) b.release();
   for (auto& b : h->pinned) b.release();
   for (auto& b : h->stage) b.release();
   for (auto& ev : h->stage_ev)

@@ -941,6 +941,39 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   b->ran = true;
+  b->d2h_queued = false;
+  if (!b->done) JLM_CUDA(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+  JLM_CUDA(cudaEventRecord(b->done, st));
+  return 0;
+}
+
+// Enqueues the device->host copy of the n-best block behind the batch's kernels and re-records the
+// completion event.  Asynchronous: jlm_batch_fetch then only waits for this batch, so a caller can
+// upload + run the NEXT batch before fetching this one and the device never idles between batches.
+extern "C" int32_t jlm_batch_fetch_async(jlm_batch* b) {
+  JLM_REQUIRE(b, "jlm_batch_fetch_async: null batch");
+  JLM_REQUIRE(b->ran, "jlm_batch_fetch_async: jlm_batch_run has not been called");
+  if (b->d2h_queued) return 0;
+  jlm_handle* h = b->h;
+  JLM_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)b->S * b->topN;
+  const char* src = reinterpret_cast<const char*>(b->d.out_score);
+  // out_score .. out_nodes are consecutive 256-aligned arena blocks: copy them in one transfer
+  const size_t total = (reinterpret_cast<const char*>(b->d.out_nodes) - src) + n * b->max_len * sizeof(int32_t);
+  if (!b->out_host.p && !h->out_pool.empty()) {
+    int pick = 0;   // smallest pooled buffer that fits, else the largest
+    for (int i = 1; i < (int)h->out_pool.size(); ++i) {
+      const size_t c = h->out_pool[i].cap, pc = h->out_pool[pick].cap;
+      if ((c >= total && (pc < total || c < pc)) || (c < total && pc < total && c > pc)) pick = i;
+    }
+    b->out_host = h->out_pool[pick];
+    h->out_pool.erase(h->out_pool.begin() + pick);
+  }
+  JLM_TRY(b->out_host.reserve(total));
+  JLM_CUDA(cudaMemcpyAsync(b->out_host.p, src, total, cudaMemcpyDeviceToHost, h->stream));
+  JLM_CUDA(cudaEventRecord(b->done, h->stream));
+  b->d2h_bytes = (int64_t)total;
+  b->d2h_queued = true;
   return 0;
 }
 
@@ -952,20 +985,10 @@ extern "C" int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out) {
               out->max_len, b->max_len);
   jlm_handle* h = b->h;
   JLM_CUDA(cudaSetDevice(h->device));
-  const size_t n = (size_t)b->S * b->topN;
-  const size_t bytes_score = n * sizeof(double), bytes_np = (size_t)b->S * sizeof(int32_t),
-               bytes_len = n * sizeof(int32_t), bytes_nodes = n * b->max_len * sizeof(int32_t);
-  // out_score .. out_nodes are consecutive 256-aligned arena blocks: copy them in one transfer
+  JLM_TRY(jlm_batch_fetch_async(b));
+  JLM_CUDA(cudaEventSynchronize(b->done));   // this batch only: later batches keep running
   const char* src = reinterpret_cast<const char*>(b->d.out_score);
-  const size_t total = (reinterpret_cast<const char*>(b->d.out_nodes) - src) + bytes_nodes;
-  JLM_TRY(h->pinned[1].reserve(total));
-  char* host = h->pinned[1].as<char>();
-  JLM_CUDA(cudaMemcpyAsync(host, src, total, cudaMemcpyDeviceToHost, h->stream));
-  JLM_CUDA(cudaStreamSynchronize(h->stream));
-  b->d2h_bytes = (int64_t)total;
-  (void)bytes_score;
-  (void)bytes_np;
-  (void)bytes_len;
+  const char* host = b->out_host.as<char>();
   const double* sc = reinterpret_cast<const double*>(host);
   const int32_t* np_ = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_npaths) - src));
   const int32_t* ln = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_len) - src));
@@ -1027,7 +1050,18 @@ extern "C" int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out) {
 extern "C" int32_t jlm_batch_destroy(jlm_batch* b) {
   if (!b) return 0;
   cudaSetDevice(b->h->device);
-  cudaStreamSynchronize(b->h->stream);
+  // wait for this batch's own work only (its arena and pinned buffer go back to the pools)
+  if (b->done) {
+    cudaEventSynchronize(b->done);
+    cudaEventDestroy(b->done);
+  } else {
+    cudaStreamSynchronize(b->h->stream);
+  }
+  if (b->out_host.p) {
+    if (b->h->out_pool.size() < 8) b->h->out_pool.push_back(b->out_host);
+    else b->out_host.release();
+    b->out_host = HostBuf();
+  }
   tc_batch_free(b);
   for (auto& e : b->events) cudaEventDestroy(e);
   for (auto& e : b->kev) cudaEventDestroy(e);

@@ -92,6 +92,11 @@ struct jlm_batch {
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   bool timers = false;
   bool ran = false;
+  // completion: `done` is recorded after the batch's last enqueued operation (run, then the n-best D2H),
+  // so fetch / destroy wait for THIS batch only and later batches on the stream keep the device busy
+  cudaEvent_t done = nullptr;
+  HostBuf out_host;              // pinned n-best landing buffer, taken from / returned to h->out_pool
+  bool d2h_queued = false;
   std::vector<cudaEvent_t> events;
   float ms_lstm = 0.f, ms_softmax = 0.f, ms_beam = 0.f;
   std::vector<cudaEvent_t> kev;  // tensor-core back end: 4 per step around the gate / projection GEMMs

@@ -149,6 +149,7 @@ struct jlm_handle {
   // a call is pipelined in chunks; the steady state allocates nothing)
   std::vector<DevBuf> batch_cache;
   HostBuf pinned[4];
+  std::vector<HostBuf> out_pool;   // pinned n-best landing buffers of finished batches
   // pinned staging ring for the plan upload: a slot is reused only after its H2D copy completed
   static constexpr int N_STAGE = 4;
   HostBuf stage[N_STAGE];

@@ -22,23 +22,34 @@ struct Chunk {
 };
 }  // namespace
 
-extern "C" int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, const int64_t* text_ptr,
-                                    const uint32_t* text, int32_t beam_width, int32_t top_n, int32_t mode,
-                                    int32_t n_extra, const int32_t* extra_ids, int32_t backend, int32_t n_chunks,
-                                    jlm_text_nbest* out, jlm_batch_info* info) {
-  if (!h || !lex || !text_ptr || !out || n_sent <= 0) {
-    jlm_set_error("jlm_decode_texts: bad argument");
+struct jlm_text_job {
+  jlm_handle* h = nullptr;
+  int32_t n_sent = 0, top = 0;
+  bool timers = false;
+  std::vector<Chunk> chunks;
+};
+
+static void job_free(jlm_text_job* job) {
+  if (!job) return;
+  for (auto& ck : job->chunks) {
+    if (ck.batch) jlm_batch_destroy(ck.batch);
+    if (ck.lat) jlm_lattice_destroy(ck.lat);
+  }
+  delete job;
+}
+
+// First half of jlm_decode_texts: everything up to and including the enqueue of the n-best D2H copy.
+// Returns as soon as the work is queued; the text buffers are not referenced after the call.
+extern "C" int32_t jlm_decode_texts_submit(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, const int64_t* text_ptr,
+                                           const uint32_t* text, int32_t beam_width, int32_t top_n, int32_t mode,
+                                           int32_t n_extra, const int32_t* extra_ids, int32_t backend, int32_t n_chunks,
+                                           int32_t timers, jlm_text_job** out_job) {
+  if (!h || !lex || !text_ptr || !out_job || n_sent <= 0) {
+    jlm_set_error("jlm_decode_texts_submit: bad argument");
     return 1;
   }
-  if (!out->scores || !out->n_paths || !out->path_len || !out->path_entry || !out->path_start) {
-    jlm_set_error("jlm_decode_texts: null output arrays");
-    return 1;
-  }
+  *out_job = nullptr;
   const int32_t top = std::max(1, std::min(top_n, beam_width));
-  if (out->top_n < top) {
-    jlm_set_error("jlm_decode_texts: output top_n %d < %d", out->top_n, top);
-    return 1;
-  }
   // Chunk boundaries.  Measured on B200 (1024 sentences, cfg 2): equal splits cost more device time
   // (smaller GEMMs, per-frame launch overheads) than the host work they hide (1.15 M chars/s with 1 chunk,
   // 1.11 M with 2, 0.74 M with 8), and a small head chunk that gets the device busy while the host prepares
@@ -56,7 +67,13 @@ extern "C" int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32
     for (int c = 1; c <= n_chunks; ++c) bounds.push_back((int32_t)((int64_t)n_sent * c / n_chunks));
   }
   n_chunks = (int32_t)bounds.size() - 1;
-  std::vector<Chunk> chunks(n_chunks);
+  jlm_text_job* job = new jlm_text_job();
+  job->h = h;
+  job->n_sent = n_sent;
+  job->top = top;
+  job->timers = timers != 0;
+  job->chunks.resize(n_chunks);
+  std::vector<Chunk>& chunks = job->chunks;
   int32_t rc = 0;
   // stage 1..3 for every chunk: build, upload, enqueue (all asynchronous with respect to the device)
   for (int c = 0; c < n_chunks && !rc; ++c) {
@@ -68,9 +85,40 @@ extern "C" int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32
     jlm_lattice_batch view;
     if (!rc) rc = jlm_lattice_view(ck.lat, &view, nullptr, nullptr);
     if (!rc) rc = jlm_batch_upload(h, &view, beam_width, top, mode, backend, &ck.batch);
-    if (!rc && info) rc = jlm_batch_enable_timers(ck.batch, 1);
+    if (!rc && timers) rc = jlm_batch_enable_timers(ck.batch, 1);
     if (!rc) rc = jlm_batch_run(ck.batch);
+    if (!rc) rc = jlm_batch_fetch_async(ck.batch);
   }
+  if (rc) {
+    job_free(job);
+    return rc;
+  }
+  *out_job = job;
+  return 0;
+}
+
+// Second half: waits for the job's own batches (not for work submitted after it), translates node
+// indices into (lexicon entry, start frame), releases the job.  The job is consumed even on error.
+extern "C" int32_t jlm_decode_texts_collect(jlm_text_job* job, jlm_text_nbest* out, jlm_batch_info* info) {
+  if (!job || !out) {
+    jlm_set_error("jlm_decode_texts_collect: bad argument");
+    job_free(job);
+    return 1;
+  }
+  if (!out->scores || !out->n_paths || !out->path_len || !out->path_entry || !out->path_start) {
+    jlm_set_error("jlm_decode_texts_collect: null output arrays");
+    job_free(job);
+    return 1;
+  }
+  const int32_t top = job->top;
+  if (out->top_n < top) {
+    jlm_set_error("jlm_decode_texts_collect: output top_n %d < %d", out->top_n, top);
+    job_free(job);
+    return 1;
+  }
+  std::vector<Chunk>& chunks = job->chunks;
+  const int32_t n_chunks = (int32_t)chunks.size();
+  int32_t rc = 0;
   // stage 4: fetch in order; translate node indices into (lexicon entry, start frame)
   std::vector<double> sc;
   std::vector<int32_t> np_, ln, nd;
@@ -137,9 +185,26 @@ extern "C" int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32
       }
     }
   }
-  for (auto& ck : chunks) {
-    if (ck.batch) jlm_batch_destroy(ck.batch);
-    if (ck.lat) jlm_lattice_destroy(ck.lat);
-  }
+  job_free(job);
   return rc;
+}
+
+extern "C" int32_t jlm_decode_texts_cancel(jlm_text_job* job) {
+  job_free(job);
+  return 0;
+}
+
+extern "C" int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, const int64_t* text_ptr,
+                                    const uint32_t* text, int32_t beam_width, int32_t top_n, int32_t mode,
+                                    int32_t n_extra, const int32_t* extra_ids, int32_t backend, int32_t n_chunks,
+                                    jlm_text_nbest* out, jlm_batch_info* info) {
+  if (!out) {
+    jlm_set_error("jlm_decode_texts: bad argument");
+    return 1;
+  }
+  jlm_text_job* job = nullptr;
+  int32_t rc = jlm_decode_texts_submit(h, lex, n_sent, text_ptr, text, beam_width, top_n, mode, n_extra, extra_ids,
+                                       backend, n_chunks, info != nullptr, &job);
+  if (rc) return rc;
+  return jlm_decode_texts_collect(job, out, info);
 }

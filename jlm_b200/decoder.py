@@ -118,9 +118,9 @@ class Decoder(object):
             out.append(res[:topN])
         return out
 
-    def _run_texts(self, texts, mode, extra, topN, beam_width, backend, n_chunks=0):
-        """One jlm_decode_texts call: kana strings in, n-best word lists out; lattice build, plan and
-        device work are pipelined over chunks inside the library."""
+    def _submit_texts(self, texts, mode, extra, topN, beam_width, backend, n_chunks=0):
+        """jlm_decode_texts_submit: lattice build, plan, H2D and every frame enqueued; returns a pending job
+        (dict) without waiting for the device."""
         lib, h = self._lib, self.model._handle
         if beam_width is None:
             beam_width = _lib.MAX_BEAM
@@ -136,7 +136,18 @@ class Decoder(object):
         if extra is not None:
             extra = np.ascontiguousarray(extra, dtype=np.int32).reshape(S, -1)
             n_extra = extra.shape[1]
-        max_len = int(lens.max()) + 1
+        job = C.c_void_p()
+        _lib.check(lib.jlm_decode_texts_submit(h, nlex.handle, S, _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
+                                               int(beam_width), top, int(mode), n_extra,
+                                               _lib.ptr(extra, C.c_int32) if n_extra else None, int(backend),
+                                               int(n_chunks), 1, C.byref(job)))
+        return {'job': job, 'texts': texts, 'top': top, 'topN': topN, 'max_len': int(lens.max()) + 1}
+
+    def _collect_texts(self, pending):
+        """jlm_decode_texts_collect: waits for that job only and turns its n-best block into word lists."""
+        lib = self._lib
+        texts, top, max_len = pending['texts'], pending['top'], pending['max_len']
+        S = len(texts)
         scores = np.empty((S, top))
         n_paths = np.empty(S, dtype=np.int32)
         path_len = np.empty((S, top), dtype=np.int32)
@@ -148,12 +159,10 @@ class Decoder(object):
         nb.path_len = _lib.ptr(path_len, C.c_int32)
         nb.path_entry, nb.path_start = _lib.ptr(path_entry, C.c_int32), _lib.ptr(path_start, C.c_int32)
         info = _lib.BatchInfo()
-        _lib.check(lib.jlm_decode_texts(h, nlex.handle, S, _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
-                                        int(beam_width), top, int(mode), n_extra,
-                                        _lib.ptr(extra, C.c_int32) if n_extra else None, int(backend), int(n_chunks),
-                                        C.byref(nb), C.byref(info)))
+        job, pending['job'] = pending['job'], None       # collect consumes the job, also on error
+        _lib.check(lib.jlm_decode_texts_collect(job, C.byref(nb), C.byref(info)))
         self.last_info = info
-        ew = nlex.entry_words
+        ew = self._native().entry_words
         out = []
         for s in range(S):
             res, text = [], texts[s]
@@ -162,8 +171,41 @@ class Decoder(object):
                 ents, starts = path_entry[s, k, :n].tolist(), path_start[s, k, :n].tolist()
                 # '<eos>' (-1) is dropped (decoder.py:237); '<unk>' (-2) carries the raw kana (decoder.py:130)
                 res.append((float(scores[s, k]), [ew[e] if e >= 0 else text[st] for e, st in zip(ents, starts) if e != -1]))
-            out.append(res[:topN])
+            out.append(res[:pending['topN']])
         return out
+
+    def _run_texts(self, texts, mode, extra, topN, beam_width, backend, n_chunks=0):
+        """One jlm_decode_texts call: kana strings in, n-best word lists out."""
+        return self._collect_texts(self._submit_texts(texts, mode, extra, topN, beam_width, backend, n_chunks))
+
+    def decode_stream(self, batches, topN=10, beam_width=10, backend=_lib.BACKEND_AUTO, depth=2):
+        """decode_batch() over an iterable of sentence batches, as a generator of their results in order.
+        Batch k+1 is submitted (lattices, plan, H2D, kernels enqueued) before batch k is collected, so the
+        host work of one batch is hidden behind the device work of the previous one; `depth` batches are in
+        flight at most.  Full-softmax decoding only (the mode decode_batch sends through jlm_decode_texts)."""
+        if self.dynamic:
+            raise ValueError('decode_stream: DynamicDecoder batches go through decode_batch')
+        pending = []
+        try:
+            for texts in batches:
+                texts = list(texts)
+                if not texts:
+                    raise ValueError('decode_stream: empty batch')
+                pending.append(self._submit_texts(texts, _lib.DECODE_FULL, None, topN, beam_width, backend))
+                while len(pending) >= max(1, int(depth)):
+                    p = pending.pop(0)
+                    out = self._collect_texts(p)
+                    self._log_batch_perf(len(p['texts']))
+                    yield out
+            while pending:
+                p = pending.pop(0)
+                out = self._collect_texts(p)
+                self._log_batch_perf(len(p['texts']))
+                yield out
+        finally:
+            for p in pending:       # generator closed early or an error: wait for and drop what is in flight
+                if p['job'] is not None:
+                    self._lib.jlm_decode_texts_cancel(p['job'])
 
     def _collect_trace(self, batch, packed, W):
         """Per-frame pruned beams of every sentence (test / debugging aid)."""

@@ -342,3 +342,30 @@ def test_decode_texts_pipeline_equals_unpipelined(tmp_path_factory):
         dd._want_trace = True
     finally:
         dec._want_trace = True
+
+
+def test_decode_stream_equals_decode_batch(tmp_path_factory):
+    """jlm_decode_texts_submit / _collect with several batches in flight return, batch by batch, what the
+    blocking call returns - different batch sizes, both back ends alternating arenas, early close."""
+    from jlm_b200 import synth
+    dec, case, _ = get_decoder('small_tied', tmp_path_factory)
+    _, _, _, lexicon, _, _ = build_case('small_tied')
+    sents = synth.make_sentences(lexicon, 900, min_len=6, seed=77, vocab_size=case['vocab_size'])
+    cuts = [0, 300, 301, 640, 900]
+    batches = [sents[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    dec._want_trace = False
+    try:
+        for backend in (EXACT, TC):
+            want = [dec.decode_batch(b, topN=4, beam_width=5, backend=backend) for b in batches]
+            for depth in (1, 2, 3):
+                n0 = dec.perf_sen
+                got = list(dec.decode_stream(batches, topN=4, beam_width=5, backend=backend, depth=depth))
+                assert got == want
+                assert dec.perf_sen - n0 == len(sents)
+            # closing the generator early cancels what is in flight and leaves the handle usable
+            g = dec.decode_stream(batches, topN=4, beam_width=5, backend=backend, depth=3)
+            assert next(g) == want[0]
+            g.close()
+            assert dec.decode_batch(batches[1], topN=4, beam_width=5, backend=backend) == want[1]
+    finally:
+        dec._want_trace = True

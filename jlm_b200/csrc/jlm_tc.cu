@@ -27,7 +27,8 @@ struct TcOperand {
   __half* lo = nullptr;
   int64_t rows = 0, K = 0;
   float scale = 1.f;
-  CUtensorMap map_hi, map_lo;
+  CUtensorMap map_hi, map_lo;         // box = box_rows x 64 (one CTA loads the whole N tile)
+  CUtensorMap pair_hi, pair_lo;       // box = box_rows/2 x 64 (each CTA of a pair loads half of the N tile)
 };
 
 namespace {
@@ -63,11 +64,15 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return fmaf(-2.f, rcp_approx(ex2_approx((2.f * LOG2E) * x) + 1.f), 1.f);   // 1 - 2/(e^{2x}+1)
 }
 
-template <int BN>
+// CG = 1: one CTA per tile (128 x BN).  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per
+// 256 x BN tile - each CTA stages its own 128 rows of A and HALF of the B tile, so a stage is 64 KB
+// instead of 96 KB and the per-MMA shared-memory traffic (operand reads + TMA writes), which is what
+// caps the single-CTA kernel at ~88 % tensor-pipe, drops from 20 KB to 13.3 KB per 128 cycles.
+template <int BN, int CG = 1>
 struct TileCfg {
-  static constexpr int B_TILE = BN * BK * 2;
+  static constexpr int B_TILE = (BN / CG) * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int STAGES = (CG == 2) ? 3 : ((BN == 256) ? 2 : 3);
   static constexpr int BIAS_BYTES = 2 * BN * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM = STAGES * STAGE + BIAS_BYTES + BAR_BYTES + 1024;
@@ -117,11 +122,15 @@ __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const floa
   dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
           const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const GemmArgs g) {
-  using C = TileCfg<BN>;
+  using C = TileCfg<BN, CG>;
+  // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tmem-empty barriers that count)
+  const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-loop index of this CTA (pair)
+  const int n_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -152,20 +161,28 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);
-        ptx::mbar_init(tempty_bar(a), EpiCfg<EPI>::WARPS);
+        ptx::mbar_init(tempty_bar(a), CG * EpiCfg<EPI>::WARPS);   // pair: both CTAs' epilogue warps arrive on the leader's
       }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();   // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
+  // tiles: CG == 1 -> 128-row blocks; CG == 2 -> 256-row blocks, rows [rank*128, +128) of each belong to this CTA
+  const int num_m_units = (CG == 2) ? (g.num_m_blocks + 1) / 2 : g.num_m_blocks;
+  const int num_tiles = num_m_units * g.num_n_blocks;
   const int num_kb = g.K / BK;
 
   if (warp == 0) {
@@ -173,16 +190,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
+        const int m_blk = (tile % num_m_units) * CG + (int)rank, n_blk = tile / num_m_units;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_expect_tx(full_bar(stage), C::STAGE);
           const uint32_t sa = base + stage * C::STAGE;
-          ptx::tma_load_2d(sa, &mAh, full_bar(stage), kb * BK, m_blk * BM);
-          ptx::tma_load_2d(sa + A_TILE, &mAl, full_bar(stage), kb * BK, m_blk * BM);
-          ptx::tma_load_2d(sa + 2 * A_TILE, &mBh, full_bar(stage), kb * BK, n_blk * BN);
-          ptx::tma_load_2d(sa + 2 * A_TILE + C::B_TILE, &mBl, full_bar(stage), kb * BK, n_blk * BN);
+          if (CG == 2) {
+            // both CTAs' loads are counted on the LEADER's full barrier: it expects two stages' worth of bytes
+            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::STAGE);
+            const int b_row = n_blk * BN + (int)rank * (BN / 2);
+            ptx::tma_load_2d_pair(sa, &mAh, full_bar(stage), kb * BK, m_blk * BM);
+            ptx::tma_load_2d_pair(sa + A_TILE, &mAl, full_bar(stage), kb * BK, m_blk * BM);
+            ptx::tma_load_2d_pair(sa + 2 * A_TILE, &mBh, full_bar(stage), kb * BK, b_row);
+            ptx::tma_load_2d_pair(sa + 2 * A_TILE + C::B_TILE, &mBl, full_bar(stage), kb * BK, b_row);
+          } else {
+            ptx::mbar_expect_tx(full_bar(stage), C::STAGE);
+            ptx::tma_load_2d(sa, &mAh, full_bar(stage), kb * BK, m_blk * BM);
+            ptx::tma_load_2d(sa + A_TILE, &mAl, full_bar(stage), kb * BK, m_blk * BM);
+            ptx::tma_load_2d(sa + 2 * A_TILE, &mBh, full_bar(stage), kb * BK, n_blk * BN);
+            ptx::tma_load_2d(sa + 2 * A_TILE + C::B_TILE, &mBl, full_bar(stage), kb * BK, n_blk * BN);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -192,13 +219,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(BM, BN);
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -212,17 +239,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
             const uint64_t al = ptx::umma_desc_sw128(sa + A_TILE + k * 32);
             const uint64_t bh = ptx::umma_desc_sw128(sa + 2 * A_TILE + k * 32);
             const uint64_t bl = ptx::umma_desc_sw128(sa + 2 * A_TILE + C::B_TILE + k * 32);
-            ptx::mma_f16_ss(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
-            ptx::mma_f16_ss(d_tmem, al, bh, idesc, 1u);
-            ptx::mma_f16_ss(d_tmem, ah, bh, idesc, 1u);
+            if (CG == 2) {
+              ptx::mma_f16_ss_pair(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss_pair(d_tmem, al, bh, idesc, 1u);
+              ptx::mma_f16_ss_pair(d_tmem, ah, bh, idesc, 1u);
+            } else {
+              ptx::mma_f16_ss(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss(d_tmem, al, bh, idesc, 1u);
+              ptx::mma_f16_ss(d_tmem, ah, bh, idesc, 1u);
+            }
           }
-          ptx::tc_commit(empty_bar(stage));
+          if (CG == 2) ptx::tc_commit_pair(empty_bar(stage), 3);   // frees the stage in both CTAs
+          else ptx::tc_commit(empty_bar(stage));
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        ptx::tc_commit(tfull_bar(acc));
+        if (CG == 2) ptx::tc_commit_pair(tfull_bar(acc), 3);
+        else ptx::tc_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -234,8 +269,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
     const int te = threadIdx.x - 64;      // 0..ET-1
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % g.num_m_blocks, n_blk = tile / g.num_m_blocks;
+    for (int tile = unit; tile < num_tiles; tile += n_units) {
+      const int m_blk = (tile % num_m_units) * CG + (int)rank, n_blk = tile / num_m_units;
       float* bs = bias_s + acc * BN;
       for (int c = te; c < BN; c += ET) {
         const int n = n_blk * BN + c;
@@ -363,14 +398,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's barrier gates the next MMAs
+        else ptx::mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (CG == 2) {
+    ptx::cluster_sync();   // no CTA of the pair may exit while the other can still signal it or read its smem
+    if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
 // A = [ h[parent] | LM_in[word] ] * scale -> fp16 hi/lo, 8 elements per thread
@@ -497,6 +540,8 @@ int32_t upload_split(TcOperand* op, const std::vector<double>& w, int64_t rows, 
   JLM_CUDA(cudaMemcpy(op->lo, lo.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
   JLM_TRY(make_map(&op->map_hi, op->hi, K, rows, K, box_rows));
   JLM_TRY(make_map(&op->map_lo, op->lo, K, rows, K, box_rows));
+  JLM_TRY(make_map(&op->pair_hi, op->hi, K, rows, K, box_rows / 2));
+  JLM_TRY(make_map(&op->pair_lo, op->lo, K, rows, K, box_rows / 2));
   return 0;
 }
 
@@ -506,22 +551,55 @@ void free_operand(TcOperand* op) {
   op->hi = op->lo = nullptr;
 }
 
+// CTA pairs (cta_group::2) are used whenever the problem has at least two 128-row blocks; JLM_TC_PAIR=0
+// forces the single-CTA kernel (A/B comparison, debugging).
+static bool tc_pair_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_TC_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 template <int BN, int EPI>
-int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al, const CUtensorMap& Bh,
-                    const CUtensorMap& Bl, GemmArgs g) {
-  using C = TileCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    configured = true;
-  }
+int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al, const TcOperand& B, GemmArgs g) {
   JLM_REQUIRE(g.K % BK == 0 && g.K > 0, "tc gemm: K=%d must be a positive multiple of %d", g.K, BK);
   g.num_m_blocks = ceil_div(g.M, BM);
   g.num_n_blocks = ceil_div(g.N, BN);
+  if (g.num_m_blocks * g.num_n_blocks <= 0) return 0;
+  if (g.num_m_blocks >= 2 && h->sm_count >= 2 && tc_pair_enabled()) {
+    using C = TileCfg<BN, 2>;
+    static bool configured = false;
+    if (!configured) {
+      JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      configured = true;
+    }
+    const int tiles = ceil_div(g.num_m_blocks, 2) * g.num_n_blocks;
+    const int pairs = std::min(tiles, h->sm_count / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    JLM_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, EPI, 2>, Ah, Al, B.pair_hi, B.pair_lo, g));
+    return 0;
+  }
+  using C = TileCfg<BN, 1>;
+  static bool configured = false;
+  if (!configured) {
+    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
-  if (tiles <= 0) return 0;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  k_tc_gemm<BN, EPI><<<grid, EpiCfg<EPI>::THREADS, C::SMEM, h->stream>>>(Ah, Al, Bh, Bl, g);
+  k_tc_gemm<BN, EPI, 1><<<grid, EpiCfg<EPI>::THREADS, C::SMEM, h->stream>>>(Ah, Al, B.map_hi, B.map_lo, g);
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -709,7 +787,7 @@ int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out)
     g.lds = h->Hp;
     g.split_scale = w->sH;
     if (b->timers) cudaEventRecord(b->kev[4 * t], st);
-    JLM_TRY((launch_gemm<GATE_BN, EPI_LSTM>(h, s->mAg_hi, s->mAg_lo, w->Wg.map_hi, w->Wg.map_lo, g)));
+    JLM_TRY((launch_gemm<GATE_BN, EPI_LSTM>(h, s->mAg_hi, s->mAg_lo, w->Wg, g)));
     if (b->timers) cudaEventRecord(b->kev[4 * t + 1], st);
   }
   b->launches += 2;
@@ -728,7 +806,7 @@ int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out)
     g.s_lo = s->Ts_lo;
     g.lds = h->Kt;
     g.split_scale = w->sT;
-    JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1.map_hi, w->P1.map_lo, g)));
+    JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
     b->launches += 1;
     T32 = s->T32;
     ldt = h->Kt;
@@ -747,7 +825,7 @@ int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out)
       g.part = s->part;
       g.part_ld = w->lse_tiles;
       g.part_tile0 = tile0;
-      JLM_TRY((launch_gemm<256, EPI_LSE>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i].map_hi, w->seg[i].map_lo, g)));
+      JLM_TRY((launch_gemm<256, EPI_LSE>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], g)));
       tile0 += ceil_div(g.N, 256);
       b->launches += 1;
     }
@@ -801,7 +879,7 @@ extern "C" int32_t jlm_tc_gemm_selftest(jlm_handle* h, const float* A, const flo
     g.C32 = dC;
     g.ldc = N;
     cudaEventRecord(h->ev[0], h->stream);
-    rc = launch_gemm<256, EPI_STORE>(h, a.map_hi, a.map_lo, bop.map_hi, bop.map_lo, g);
+    rc = launch_gemm<256, EPI_STORE>(h, a.map_hi, a.map_lo, bop, g);
     cudaEventRecord(h->ev[1], h->stream);
     if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) {
       jlm_set_error("selftest: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));

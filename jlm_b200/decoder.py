@@ -28,8 +28,10 @@ class Decoder(object):
             self.full_lexicon = pickle.load(f)
         with open(os.path.join(config.root_path, 'data', 'reading_dict.pkl'), 'rb') as f:
             self.full_reading_dict = pickle.load(f)
-        if self.config.get('char_rnn'):
-            raise NotImplementedError('char_rnn experiments use CharRNNDecoder in the reference; out of scope here')
+        if bool(self.config.get('char_rnn')) != bool(getattr(self, 'char_rnn', False)):
+            # the reference picks the class from config['char_rnn'] (decoder.py:345-348, eval.py:43-44)
+            raise ValueError('config char_rnn={} needs {}'.format(self.config.get('char_rnn'),
+                                                                  'CharRNNDecoder' if self.config.get('char_rnn') else 'Decoder'))
         self.model = LSTM_Model(experiment_id, comp, device=device)
         self.lattice_vocab = None
         self.backward_lookup = None

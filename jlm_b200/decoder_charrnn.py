@@ -1,0 +1,165 @@
+"""CharRNNDecoder: word lattice scored by a CHARACTER language model (reference decoder/decoder.py:244-341).
+
+A node's first character is scored from its parent path's distribution; the remaining characters of a
+multi-character word take one LM step each, for EVERY candidate path, before the frame is pruned
+(_eval_frame, decoder.py:301-320); candidates that spell the same string as an earlier candidate of the
+frame are dropped (decoder.py:293-297).  Every LM step runs on the device through the C ABI
+(jlm_predict via LSTM_Model.predict_with_context); the candidate bookkeeping, which is per-sentence and
+string-keyed, stays on the host as flat arrays.
+
+The reference class does not run as shipped - it reads `self.vocab.words` and indexes `self.w2i` with
+characters, while Decoder._load_vocab builds the word-keyed train.data.Vocab (AttributeError at
+decoder.py:264; recorded in tests/golden/charrnn_*.json "as_shipped").  This mirror loads what those
+lines need, the reference's own CharVocab (train/data.py:28-46): `vocab.words`, w2i = c2i, i2w = i2c.
+"""
+import math
+
+import numpy as np
+
+from . import lattice
+from .decoder import Decoder
+from .vocab import CharVocab
+
+
+class CharRNNDecoder(Decoder):
+    char_rnn = True
+
+    def _load_vocab(self):
+        self.vocab = CharVocab(self.config['vocab_size'])
+        self.i2w = self.vocab.i2c
+        self.w2i = self.vocab.c2i
+
+    def _check_oov(self, word):
+        # decoder/decoder.py:263-264
+        return word not in self.vocab.words
+
+    def _char_check_oov(self, word):
+        # decoder/decoder.py:266-267: number of characters of the display string the model does not know
+        return sum([c not in self.w2i for c in word.split('/')[0]])
+
+    def _word_length(self, word):
+        # decoder/decoder.py:269-273
+        return 1 if word in ('<eos>', '<unk>') else len(word)
+
+    # ------------------------------------------------------------------------------------------
+    def _reading_nodes(self, reading):
+        """[(first character id, display string)] of one reading: lexicon ids ascending, OOV words and words
+        with unknown characters skipped, one node per display string, at most 201 strings (decoder.py:95-125)."""
+        hit = self._reading_cache.get(reading)
+        if hit is None:
+            hit, seen = [], set()
+            for lex_id in sorted(self.full_reading_dict[reading]):
+                word = self.full_lexicon[lex_id][0]
+                if self._check_oov(word) or self._char_check_oov(word):
+                    continue
+                disp = word.split('/')[0]
+                if disp in seen or len(seen) > 200:
+                    continue
+                seen.add(disp)
+                hit.append((self.w2i[disp[0]], disp))
+            self._reading_cache[reading] = hit
+        return hit
+
+    def _build_lattice(self, input, vocab_select=False, samples=0, top_sampling=False, random_sampling=False):
+        """decoder/decoder.py:79-135 (char_rnn branch) -> frames[t] = [(start, first char id, display string)]."""
+        if not hasattr(self, '_reading_cache'):
+            self._reading_cache = {}
+            self._max_reading = max((len(k) for k in self.full_reading_dict), default=0)
+        T = len(input)
+        frames = [[] for _ in range(T + 1)]
+        frames[0].append((-1, self.w2i['<eos>'], '<eos>'))
+        for i in range(T):
+            for j in range(min(T - i, self._max_reading)):
+                sub = input[i:i + j + 1]
+                if sub in self.full_reading_dict:
+                    end = frames[i + j + 1]
+                    for cid, disp in self._reading_nodes(sub):
+                        end.append((i, cid, disp))
+                if j == 0 and not frames[i + 1]:
+                    frames[i + 1].append((i, self.w2i['<unk>'], input[i]))
+            if self._max_reading == 0 and not frames[i + 1]:
+                frames[i + 1].append((i, self.w2i['<unk>'], input[i]))
+        if vocab_select:
+            # kept for interface parity: CharRNNDecoder.decode never passes it to the model
+            self._build_lattice_vocab(frames, samples, top_sampling, random_sampling)
+        return frames
+
+    # ------------------------------------------------------------------------------------------
+    def _step(self, char_ids, h, c):
+        """One batched LM step (decoder.py:202-218): rows in, (probabilities, h, c) out; logs the timers."""
+        (pred, _y, t_lstm, t_soft), h2, c2 = self.model.predict_with_context(list(char_ids), h, c, None)
+        self.perf_log_lstm.append(t_lstm)
+        self.perf_log_softmax.append(t_soft)
+        return pred, h2, c2
+
+    def decode(self, input, topN=10, beam_width=10, vocab_select=False, samples=0, top_sampling=False,
+               random_sampling=False):
+        """decoder/decoder.py:322-341 -> [(neg_log_prob, [display string, ...])][:topN]."""
+        frames = self._build_lattice(input, vocab_select=vocab_select, samples=samples, top_sampling=top_sampling,
+                                     random_sampling=random_sampling)
+        self.backward_lookup = lattice.to_backward_lookup(frames)
+        H = self.model.hidden_size
+        w2i = self.w2i
+        beams = []       # per frame: dict(score [n], h [n,H], c [n,H], probs [n,V], words [n][...], text [n])
+        for t, nodes in enumerate(frames):
+            if t == 0:
+                score = np.zeros(1)
+                h = np.zeros((1, H))
+                c = np.zeros((1, H))
+                words, text, cur = [['<eos>']], ['<eos>'], [w2i['<eos>']]
+                wlen = [1]
+            else:
+                # expand in the reference's order (node, then parent rank); the first spelling of a string wins
+                s_l, h_l, c_l, words, text, cur, wlen, seen = [], [], [], [], [], [], [], set()
+                for (start, cid, disp) in nodes:
+                    par = beams[start]
+                    for r in range(len(par['score'])):
+                        spelled = par['text'][r] + disp
+                        if spelled in seen:
+                            continue
+                        seen.add(spelled)
+                        s_l.append(par['score'][r] + -math.log(par['probs'][r, cid]))     # Path.append_node :43-49
+                        h_l.append(par['h'][r])
+                        c_l.append(par['c'][r])
+                        words.append(par['words'][r] + [disp])
+                        text.append(spelled)
+                        cur.append(cid)
+                        wlen.append(self._word_length(disp))
+                score = np.array(s_l)
+                h = np.stack(h_l)
+                c = np.stack(c_l)
+                # the remaining characters of multi-character words, one LM step per character, all
+                # candidates of the frame that still have characters left batched together (:301-320)
+                k = 1
+                active = [a for a in range(len(cur)) if wlen[a] > 1]
+                while active:
+                    pred, h2, c2 = self._step([cur[a] for a in active], h[active], c[active])
+                    h[active], c[active] = h2, c2
+                    for row, a in enumerate(active):
+                        cur[a] = w2i[words[a][-1][k]]
+                        score[a] += -np.log(pred[row, cur[a]])
+                    k += 1
+                    active = [a for a in active if wlen[a] > k]
+            if beam_width is not None:
+                keep = np.argsort(score, kind='stable')[:beam_width]      # list.sort is stable (:331-333)
+            else:
+                keep = np.arange(len(score))
+            score, h, c = score[keep], h[keep], c[keep]
+            words = [words[a] for a in keep]
+            text = [text[a] for a in keep]
+            pred, h, c = self._step([cur[a] for a in keep], h, c)        # feeds each survivor's LAST character
+            beams.append({'score': score, 'h': h, 'c': c, 'probs': pred, 'words': words, 'text': text})
+        self._last_beams = beams
+        last = beams[len(input)]
+        out = [(float(last['score'][r]), [w for w in last['words'][r] if w != '<eos>']) for r in range(len(last['score']))]
+        self.perf_sen += 1
+        return out[:topN]
+
+    def decode_batch(self, inputs, topN=10, beam_width=10, **kw):
+        """decode() per sentence (the multi-step word evaluation is sentence-local host control flow)."""
+        kw.pop('backend', None)
+        kw.pop('native_lattice', None)
+        return [self.decode(x, topN=topN, beam_width=beam_width, **kw) for x in inputs]
+
+    def decode_stream(self, *a, **kw):
+        raise NotImplementedError('decode_stream is the full-softmax word decoder\'s lock-step path')

@@ -17,6 +17,7 @@ import numpy as np
 
 from . import config
 from .decoder import Decoder
+from .decoder_charrnn import CharRNNDecoder
 from .decoder_dynamic import DynamicDecoder
 from .vocab import Vocab
 
@@ -62,8 +63,9 @@ class Evaluator(object):
         else:
             self.config = config.load_config(args.experiment_id)
             if self.config.get('char_rnn'):
-                raise NotImplementedError('char-RNN experiments are out of scope (SURVEY.md section 2, row 4)')
-            cls = DynamicDecoder if args.dynamic_decoding else Decoder
+                cls = CharRNNDecoder                      # eval.py:43-44
+            else:
+                cls = DynamicDecoder if args.dynamic_decoding else Decoder
             self.decoder = cls(experiment_id=args.experiment_id, comp=args.comp, device=args.device)
         self.vocab = getattr(self.decoder, 'vocab', None) or Vocab(self.config['vocab_size'])
         self.w2i = self.vocab.w2i

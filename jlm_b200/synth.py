@@ -287,3 +287,98 @@ def write_test_corpus(root, lines):
     os.makedirs(os.path.join(root, 'data'), exist_ok=True)
     with open(os.path.join(root, 'data', 'test.txt'), 'w', encoding='utf-8') as f:
         f.write('\n'.join(lines) + '\n')
+
+
+# --------------------------------------------------------------------------------------
+# char-RNN experiments (reference decoder/decoder.py:244-341, train/data.py:28-46)
+# --------------------------------------------------------------------------------------
+def make_char_lexicon(vocab_size, seed=0, n_chars=48, extra_oov=200):
+    """Lexicon whose display strings are 1-3 characters over a small alphabet, so that (a) most words
+    take several character steps, (b) different segmentations of a reading spell the same string (the
+    decoder de-duplicates paths by string, decoder.py:293-297) and (c) one reading carries the same
+    display string under several parts of speech (per-substring de-duplication, decoder.py:113-122)."""
+    rng = np.random.default_rng(seed)
+    chars = [chr(0x4E00 + k) for k in range(n_chars)]
+    n_pool = max(vocab_size // 3, 8)
+    lens = rng.choice(np.arange(1, 7), size=n_pool, p=_LEN_P)
+    pool, seen = [], set()
+    for L in lens:
+        r = ''.join(KANA[k] for k in rng.integers(0, len(KANA), size=int(L)))
+        if r not in seen:
+            seen.add(r)
+            pool.append(r)
+    n_words = vocab_size - 2 + extra_oov
+    w = 1.0 / np.power(np.arange(1, len(pool) + 1), 0.6)
+    w /= w.sum()
+    ridx = rng.choice(len(pool), size=n_words, p=w)
+    dlen = rng.choice([1, 2, 3], size=n_words, p=[.3, .45, .25])
+    # characters are drawn from a vocabulary-dependent prefix of the alphabet for in-vocabulary words and from
+    # the whole alphabet for the tail, so a few tail characters are unknown to the model (_char_check_oov)
+    lexicon = [('<eos>', 10 ** 8)]
+    reading_dict = {}
+    used = set()
+    kind = rng.random(size=n_words)
+    pick = rng.integers(0, 1 << 30, size=(n_words, 2))
+    base = []                                   # (display, reading) of the plain words generated so far
+    for n in range(n_words):
+        reading = pool[int(ridx[n])]
+        hi = n_chars - 4 if n < vocab_size - 2 else n_chars
+        disp = ''.join(chars[k] for k in rng.integers(0, hi, size=int(dlen[n])))
+        if len(base) >= 8 and kind[n] < 0.2:
+            # compound: spelled and read as two earlier words back to back -> the segmentations [a, b]
+            # and [ab] give the same string
+            (da, ra), (db, rb) = base[int(pick[n, 0]) % len(base)], base[int(pick[n, 1]) % len(base)]
+            if len(da + db) <= 4 and len(ra + rb) <= 8:
+                disp, reading = da + db, ra + rb
+        elif len(base) >= 8 and kind[n] < 0.3:
+            # homograph: an earlier word's spelling and reading under another part of speech
+            disp, reading = base[int(pick[n, 0]) % len(base)]
+        else:
+            base.append((disp, reading))
+        pos = 'P%d' % int(rng.integers(0, 3))
+        word = '{}/{}/{}'.format(disp, reading, pos)
+        if word in used:
+            word = '{}/{}/Q{}'.format(disp, reading, n)
+        used.add(word)
+        lexicon.append((word, 10 ** 8 // (n + 1)))
+        reading_dict.setdefault(reading, []).append(n + 1)
+    return lexicon, reading_dict
+
+
+def make_char_sentences(lexicon, n_sent, min_len=10, seed=1, vocab_size=None):
+    """Kana strings from in-vocabulary words drawn UNIFORMLY (compounds and homographs are then common,
+    so string de-duplication and the per-reading display filter are exercised in most frames)."""
+    rng = np.random.default_rng(seed)
+    words = lexicon[1:(vocab_size - 1 if vocab_size else len(lexicon))]
+    out = []
+    for _ in range(n_sent):
+        s = ''
+        while len(s) < min_len:
+            s += words[int(rng.integers(0, len(words)))][0].split('/')[1]
+        out.append(s)
+    return out
+
+
+def char_vocab(lexicon, vocab_size):
+    """CharVocab (train/data.py:28-46): c2i over the display strings of lexicon[2:] of the size-limited
+    vocabulary ('<unk>' 0, '<eos>' 1, then characters in order of first appearance)."""
+    lex = [('<unk>', 0)] + list(lexicon[:vocab_size - 1])
+    c2i = {'<unk>': 0, '<eos>': 1}
+    for item in lex[2:]:
+        for c in item[0].split('/')[0]:
+            if c not in c2i:
+                c2i[c] = len(c2i)
+    return c2i
+
+
+def make_char_experiment(root, experiment_id, vocab_size, hidden_size, embed_size, seed=0):
+    """Tied standard-softmax character LM over CharVocab; config['vocab_size'] stays the WORD vocabulary
+    size (it is what Vocab/CharVocab are built with), the model's output width is len(c2i)."""
+    lexicon, reading_dict = make_char_lexicon(vocab_size, seed=seed)
+    c2i = char_vocab(lexicon, vocab_size)
+    cfg = make_config(len(c2i), hidden_size, embed_size, MODE_TIED)
+    weights = make_weights(cfg, seed=seed)
+    cfg['vocab_size'] = vocab_size
+    cfg['char_rnn'] = True
+    write_experiment(root, experiment_id, cfg, weights, lexicon, reading_dict)
+    return cfg, weights, lexicon, reading_dict

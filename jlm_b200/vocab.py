@@ -16,3 +16,22 @@ class Vocab(object):
 
     def __len__(self):
         return len(self.w2i)
+
+
+class CharVocab(Vocab):
+    """Character index over the display strings of the size-limited vocabulary (reference
+    train/data.py:28-46): '<unk>' 0, '<eos>' 1, then characters in order of first appearance in lexicon[2:].
+    `words` is the set CharRNNDecoder._check_oov tests membership in (decoder/decoder.py:263-264)."""
+
+    def __init__(self, size, lexicon=None):
+        super(CharVocab, self).__init__(size, lexicon)
+        self.c2i = {'<unk>': 0, '<eos>': 1}
+        for item in self.lexicon[2:]:
+            for c in item[0].split('/')[0]:
+                if c not in self.c2i:
+                    self.c2i[c] = len(self.c2i)
+        self.i2c = {v: k for k, v in self.c2i.items()}
+        self.words = set(x[0] for x in self.lexicon)
+
+    def __len__(self):
+        return len(self.c2i)

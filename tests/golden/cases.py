@@ -57,3 +57,10 @@ CASES = {
                                              top_sampling=True),
                           model_probe={'index': [[1, 7], [40000, 12]], 'vocab': None}),
 }
+
+# --- char-RNN decoder (decoder/decoder.py:244-341): character LM over CharVocab, word lattice ---
+_CHAR = dict(vocab_size=1000, hidden_size=64, embed_size=32, n_sent=4, min_len=10, seed=3)
+CHAR_CASES = {
+    'charrnn_small': _c(_CHAR, decode_kwargs=dict(topN=10, beam_width=5)),
+    'charrnn_beam20': _c(_CHAR, n_sent=3, decode_kwargs=dict(topN=4, beam_width=20, vocab_select=True)),
+}

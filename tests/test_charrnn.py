@@ -1,0 +1,132 @@
+"""Char-RNN decoder (reference decoder/decoder.py:244-341).
+
+CPU: the oracle restatement against fixtures written by the reference class (tests/golden/charrnn_*.json,
+generator tests/golden/make_golden_charrnn.py - the class needs the CharVocab attributes supplied to run at
+all; the fixture records the as-shipped AttributeError).  GPU: jlm_b200.CharRNNDecoder, whose LM steps go
+through the C ABI, against the same fixtures and against the oracle on fresh sentences."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from jlm_b200 import synth
+from oracle import jlm_oracle as O
+from tests.golden.cases import CHAR_CASES
+from tests.helpers import GOLDEN
+
+TOL = 1e-9
+
+
+def _case(name):
+    case = CHAR_CASES[name]
+    meta = json.load(open(os.path.join(GOLDEN, name + '.json')))
+    return case, meta
+
+
+def _experiment(case, root):
+    cfg, weights, lexicon, reading_dict = synth.make_char_experiment(
+        str(root), 1, case['vocab_size'], case['hidden_size'], case['embed_size'], seed=case['seed'])
+    return cfg, weights, lexicon, reading_dict
+
+
+def _check_weights(meta, weights):
+    chk = float(sum(float(np.sum(np.asarray(v, dtype=np.float64))) for k, v in sorted(weights.items())
+                    if not isinstance(v, list)))
+    assert chk == meta['weights_checksum'], 'synthetic generator drifted from the golden fixture'
+
+
+@pytest.mark.parametrize('name', sorted(CHAR_CASES))
+def test_oracle_charrnn_matches_reference(name, tmp_path):
+    case, meta = _case(name)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    _check_weights(meta, weights)
+    # the unmodified class cannot run (decoder.py:264); the fixture pins that too
+    assert meta['as_shipped'].startswith("AttributeError: 'Vocab' object has no attribute 'words'")
+    words, c2i = O.make_char_vocab(lexicon, cfg['vocab_size'])
+    assert len(c2i) == meta['n_chars'] == weights['LM'].shape[0]
+    model = O.OracleModel(cfg, weights)
+    kw = case['decode_kwargs']
+    sentences = synth.make_char_sentences(lexicon, case['n_sent'], min_len=case['min_len'], seed=case['seed'] + 1,
+                                          vocab_size=case['vocab_size'])
+    assert sentences == meta['sentences']
+    dropped = 0
+    for sent, g in zip(sentences, meta['decode']):
+        frames = O.build_lattice_char(sent, words, c2i, lexicon, reading_dict)
+        assert {str(t): [[n[0], n[1], n[2]] for n in fr] for t, fr in enumerate(frames) if fr} == g['lattice']
+        trace = []
+        res = O.decode_charrnn(model, frames, c2i, kw['topN'], kw['beam_width'], trace=trace)
+        assert [ws for _, ws in res] == [ws for _, ws in g['nbest']]
+        np.testing.assert_allclose([s for s, _ in res], [s for s, _ in g['nbest']], rtol=0, atol=TOL)
+        # candidates kept after string de-duplication, and the rows of every LM call, frame by frame
+        assert [t['n_candidates'] for t in trace] == g['n_candidates']
+        rows = []
+        for t in trace:
+            rows += t['eval_rows'] + [len(t['paths'])]
+        assert rows == g['predict_rows']
+        for t, gp in zip(trace, g['pruned']):
+            assert [p[1] for p in t['paths']] == [p[1] for p in gp]
+            np.testing.assert_allclose([p[0] for p in t['paths']], [p[0] for p in gp], rtol=0, atol=TOL)
+        raw = [1] + [sum(len(trace[n[0]]['paths']) for n in frames[t]) for t in range(1, len(frames))]
+        dropped += sum(raw) - sum(g['n_candidates'])
+    if name == 'charrnn_beam20':
+        assert dropped > 0, 'fixture no longer exercises string de-duplication'
+
+
+def test_char_vocab_mirror_matches_oracle():
+    from jlm_b200.vocab import CharVocab
+    lexicon, _ = synth.make_char_lexicon(500, seed=5)
+    v = CharVocab(500, lexicon=lexicon)
+    words, c2i = O.make_char_vocab(lexicon, 500)
+    assert v.c2i == c2i == synth.char_vocab(lexicon, 500) and v.words == words
+    assert v.i2c[0] == '<unk>' and v.i2c[1] == '<eos>' and len(v) == len(c2i)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(CHAR_CASES))
+def test_gpu_charrnn_matches_reference(name, tmp_path):
+    import jlm_b200
+    from jlm_b200 import config
+    case, meta = _case(name)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    _check_weights(meta, weights)
+    config.set_root(str(tmp_path))
+    with pytest.raises(ValueError):
+        jlm_b200.Decoder(1)                       # a char_rnn experiment needs the char decoder
+    dec = jlm_b200.CharRNNDecoder(1)
+    assert dec._check_oov('no such word') and not dec._check_oov(lexicon[1][0])
+    for sent, g in zip(meta['sentences'], meta['decode']):
+        n0 = len(dec.perf_log_lstm)
+        res = dec.decode(sent, **case['decode_kwargs'])
+        assert {str(t): [[n.start_idx, n.word_idx, n.word] for n in fr]
+                for t, fr in dec.backward_lookup.items() if fr} == g['lattice']
+        assert [ws for _, ws in res] == [ws for _, ws in g['nbest']]            # same strings, same order
+        np.testing.assert_allclose([s for s, _ in res], [s for s, _ in g['nbest']], rtol=0, atol=2e-5)
+        assert len(dec.perf_log_lstm) - n0 == len(g['predict_rows'])           # one timer entry per LM call
+        for t, gp in enumerate(g['pruned']):
+            b = dec._last_beams[t]
+            assert [[w for w in ws] for ws in b['words']] == [[n[1] for n in p[1]] for p in gp]
+            np.testing.assert_allclose(b['score'], [p[0] for p in gp], rtol=0, atol=2e-5)
+    assert dec.perf_sen == len(meta['sentences'])
+
+
+@pytest.mark.gpu
+def test_gpu_charrnn_matches_oracle_on_fresh_sentences(tmp_path):
+    import jlm_b200
+    from jlm_b200 import config
+    case = dict(CHAR_CASES['charrnn_small'], seed=11, hidden_size=96, embed_size=48)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    config.set_root(str(tmp_path))
+    dec = jlm_b200.CharRNNDecoder(1)
+    words, c2i = O.make_char_vocab(lexicon, cfg['vocab_size'])
+    model = O.OracleModel(cfg, weights)
+    sents = synth.make_char_sentences(lexicon, 12, min_len=14, seed=99, vocab_size=case['vocab_size']) + ['ヰ', 'ヰヱ']
+    short = [x[:6] for x in sents[:4]] + sents[-2:]
+    for beam, batch in ((1, sents), (8, sents), (None, short)):       # beam_width=None: no pruning (decoder.py:331)
+        got = dec.decode_batch(batch, topN=5, beam_width=beam)
+        for sent, res in zip(batch, got):
+            frames = O.build_lattice_char(sent, words, c2i, lexicon, reading_dict)
+            want = O.decode_charrnn(model, frames, c2i, 5, beam)
+            assert [ws for _, ws in res] == [ws for _, ws in want]
+            np.testing.assert_allclose([s for s, _ in res], [s for s, _ in want], rtol=0, atol=2e-5)

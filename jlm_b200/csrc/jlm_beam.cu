@@ -34,6 +34,21 @@ __global__ void k_init_frame0(BeamDev d, int S) {
   if (d.slot_cumy) d.slot_cumy[s0] = 0.0;
 }
 
+__global__ void k_build_items(BeamDev d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n_items) return;
+  const int n = d.start_items[i];
+  const int pf = d.node_pfid[n];
+  ScoreItem it;
+  it.word = d.node_word[n];
+  it.rows = d.bc[pf];
+  it.node = n;
+  it.pad = 0;
+  it.ps0 = d.slot0[pf];
+  it.cpos = d.cand_pos[n];
+  d.items[i] = it;
+}
+
 // Score: Path.append_node (decoder.py:43-49) for every lattice node that STARTS at the frame that
 // was just stepped.  One warp per node: the node's word row of the output block is read once and
 // dotted (float64 accumulation) with the stage-1 projection row of each kept path of the start frame;
@@ -43,6 +58,7 @@ __global__ void k_init_frame0(BeamDev d, int S) {
 //   dynamic: cand_val = y[word]; scores depend on the end frame's vocabulary and are formed at prune time
 constexpr int SC_RC = 8;       // rows accumulated per pass
 constexpr int SC_WARPS = 8;    // warps (= nodes) per CTA
+constexpr int SC_MAXPASS = 2;  // row passes whose parent scores are prefetched (beam <= 16); wider beams load late
 
 __device__ __forceinline__ void load4(const float* p, double (&t)[4]) {
   const float4 v = *reinterpret_cast<const float4*>(p);
@@ -60,12 +76,21 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
   if (item >= n_items) return;
-  const int n = d.start_items[item0 + item];
-  const int w = d.node_word[n];
-  const int pf = d.node_pfid[n];
-  const int rows = d.bc[pf];
-  const int64_t ps0 = d.slot0[pf];
-  const int64_t cpos = d.cand_pos[n];
+  const int4* ip = reinterpret_cast<const int4*>(d.items + item0 + item);
+  const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+  const int w = i0.x;
+  const int rows = i0.y;
+  const int64_t ps0 = ((int64_t)(uint32_t)i1.x) | ((int64_t)i1.y << 32);
+  const int64_t cpos = ((int64_t)(uint32_t)i1.z) | ((int64_t)i1.w << 32);
+  // the parent rows' (score, LSE) this lane will combine with its dot products: fetched now, used last
+  const int my_r = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  double pre[SC_MAXPASS];
+#pragma unroll
+  for (int q = 0; q < SC_MAXPASS; ++q) {
+    pre[q] = 0.0;
+    const int r = q * SC_RC + my_r;
+    if (!DYN && (lane & 3) == 0 && r < rows) pre[q] = d.slot_score[ps0 + r] + (use_lse ? d.slot_lse[ps0 + r] : 0.0);
+  }
   int s = 0;
 #pragma unroll
   for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
@@ -125,7 +150,12 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
     if ((lane & 3) == 0 && r0 + r < rows) {
       const double y = v1 + bias;
       const int64_t ps = ps0 + r0 + r;
-      d.cand_val[cpos + r0 + r] = DYN ? y : d.slot_score[ps] + ((use_lse ? d.slot_lse[ps] : 0.0) - y);
+      const int q = r0 / SC_RC;
+      double base_score;
+      static_assert(SC_MAXPASS == 2, "select below is written for two prefetched passes");
+      if (q < SC_MAXPASS) base_score = q == 0 ? pre[0] : pre[1];
+      else base_score = d.slot_score[ps] + (use_lse ? d.slot_lse[ps] : 0.0);
+      d.cand_val[cpos + r0 + r] = DYN ? y : base_score - y;
       if (DYN) d.cand_parent[cpos + r0 + r] = (int32_t)ps;
     }
   }
@@ -138,6 +168,8 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
 // displaces kept entries that are strictly worse, so equal scores keep the earlier ordinal.  The kept
 // list lives in registers, sorted, entry e at (lane e%32, register e/32), as (score, ordinal); the
 // (node, parent) of the survivors is recovered at the end by a binary search over the frame's nodes.
+constexpr int PRUNE_CAP = 96;   // survivors of the threshold filter a warp can rank in shared memory
+
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
 k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
@@ -164,6 +196,99 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
     es[l] = INFINITY;
     ec[l] = -1;
   }
+  auto value = [&](int c) -> double {
+    if (DYN) {
+      const int par = cpar[c];
+      return (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + val[c]);
+    }
+    return val[c];
+  };
+
+  // ---- parallel selection (W <= 32) ----------------------------------------------------------------
+  // (1) every lane takes the minimum of its strided share of the candidates; the W-th smallest of those
+  //     32 minima is an upper bound tau of the frame's W-th best score (they are 32 of the candidates).
+  // (2) the candidates <= tau - about 2W of them - are compacted, in ordinal order, into shared memory.
+  // (3) each survivor counts the survivors that sort before it under (score, ordinal): that count is its
+  //     rank in the reference's stable sort (decoder.py:227-229), and ranks < W are the kept paths.
+  // No step has a serial dependence on the candidate count; the insertion list below remains for wider
+  // beams and for the rare frame whose survivors overflow the buffer (many exact ties).
+  bool selected = false;
+  if (L == 1) {
+    __shared__ double sv_all[4][PRUNE_CAP];
+    __shared__ int sc_all[4][PRUNE_CAP];
+    __shared__ double ov_all[4][32];
+    __shared__ int oc_all[4][32];
+    double* sv = sv_all[threadIdx.x >> 5];
+    int* sc = sc_all[threadIdx.x >> 5];
+    double* ov = ov_all[threadIdx.x >> 5];
+    int* oc = oc_all[threadIdx.x >> 5];
+    // loads are issued eight groups at a time: a frame with thousands of candidates (one long-tailed
+    // sentence per batch sets the kernel's duration) must not pay one L2 round trip per 32 of them
+    constexpr int UN = 8;
+    double lmin = INFINITY;
+    for (int base = 0; base < nc; base += 32 * UN) {
+      double v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = base + u * 32 + lane;
+        v[u] = c < nc ? value(c) : INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) lmin = fmin(lmin, v[u]);
+    }
+    int rk = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const double o = __shfl_sync(FULL, lmin, j);
+      rk += (o < lmin || (o == lmin && j < lane)) ? 1 : 0;
+    }
+    const unsigned holder = __ballot_sync(FULL, rk == W - 1);
+    const double tau = __shfl_sync(FULL, lmin, __ffs(holder) - 1);
+    int ns = 0;
+    for (int base = 0; base < nc; base += 32 * UN) {
+      double v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = base + u * 32 + lane;
+        v[u] = c < nc ? value(c) : INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int c = base + u * 32 + lane;
+        const bool keep = c < nc && v[u] <= tau;
+        const unsigned m = __ballot_sync(FULL, keep);
+        const int pos = ns + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < PRUNE_CAP) {
+          sv[pos] = v[u];
+          sc[pos] = c;
+        }
+        ns += __popc(m);
+      }
+    }
+    if (ns <= PRUNE_CAP) {
+      __syncwarp();
+      for (int i = lane; i < ns; i += 32) {
+        const double x = sv[i];
+        int r = 0;
+        for (int j = 0; j < ns; ++j) {
+          const double y = sv[j];
+          r += (y < x || (y == x && j < i)) ? 1 : 0;
+        }
+        if (r < W) {          // ranks are a permutation of 0..ns-1: each kept slot is written exactly once
+          ov[r] = x;
+          oc[r] = sc[i];
+        }
+      }
+      __syncwarp();
+      if (lane < W && lane < ns) {
+        es[0] = ov[lane];
+        ec[0] = oc[lane];
+      }
+      selected = true;
+    }
+  }
+
+  if (!selected) {
   const int kl = (W - 1) >> 5, klane = (W - 1) & 31;
   double kth = INFINITY;
 
@@ -174,14 +299,7 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
     for (int u = 0; u < U; ++u) {
       const int c = base + u * 32 + lane;
       v[u] = INFINITY;
-      if (c < nc) {
-        if (DYN) {
-          const int par = cpar[c];
-          v[u] = (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + val[c]);
-        } else {
-          v[u] = val[c];
-        }
-      }
+      if (c < nc) v[u] = value(c);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -223,6 +341,8 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
         kth = __shfl_sync(FULL, kv, klane);
       }
     }
+  }
+
   }
 
   const int cnt = d.bc[fid];
@@ -628,6 +748,7 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   d.fbase = place(a, P.fbase);
   d.sent_T = place(a, P.sent_T);
   d.start_items = place(a, P.start_items);
+  d.n_items = (int64_t)P.start_items.size();
   d.vocab_jobs = place(a, P.vocab_jobs);
   d.dyn_info = place(a, P.dyn_info);
   d.vocab_cols = place(a, P.vocab_cols);
@@ -648,6 +769,7 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
     d.dyn_lse = a.take<double>(ns * (size_t)(b->Tmax + 1));
   }
   d.cand_val = a.take<double>(ncd);
+  d.items = a.take<ScoreItem>((size_t)std::max<int64_t>(d.n_items, 1));
   d.out_score = a.take<double>((size_t)b->S * b->topN);
   d.out_npaths = a.take<int32_t>((size_t)b->S);
   d.out_len = a.take<int32_t>((size_t)b->S * b->topN);
@@ -921,7 +1043,9 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
     if (t == 0) {
       k_init_frame0<<<ceil_div(b->S, 128), 128, 0, st>>>(b->d, b->S);
       JLM_CUDA(cudaGetLastError());
-      b->launches += 1;
+      k_build_items<<<ceil_div(b->d.n_items, 256), 256, 0, st>>>(b->d);
+      JLM_CUDA(cudaGetLastError());
+      b->launches += 2;
     } else if (b->dynamic) {
       JLM_TRY(launch_prune<true>(b, t));
     } else {

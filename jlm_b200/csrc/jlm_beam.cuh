@@ -20,6 +20,18 @@ struct DynJobInfo {
   int32_t nv, nd, T, pad;
 };
 
+// Work item of the scoring kernel: everything a warp needs about one lattice node, gathered once per run
+// by k_build_items so the scoring warps start their weight / T-row loads after ONE dependent load
+// instead of three (start_items -> node_word, node_pfid, cand_pos -> bc, slot0).
+struct __align__(16) ScoreItem {
+  int32_t word;     // node_word
+  int32_t rows;     // kept paths of the node's start frame (bc)
+  int32_t node;
+  int32_t pad;
+  int64_t ps0;      // first slot of the start frame
+  int64_t cpos;     // first candidate slot of the node
+};
+
 struct BeamDev {
   // ---- plan (read-only on the device) ----
   int32_t* node_word = nullptr;
@@ -35,6 +47,8 @@ struct BeamDev {
   int64_t* fbase = nullptr;         // first frame id per sorted sentence
   int32_t* sent_T = nullptr;
   int32_t* start_items = nullptr;   // node ids grouped by the lock-step frame they start at
+  ScoreItem* items = nullptr;       // start_items expanded on the device (k_build_items)
+  int64_t n_items = 0;
   SubsetJob* vocab_jobs = nullptr;
   DynJobInfo* dyn_info = nullptr;
   int32_t* vocab_cols = nullptr;

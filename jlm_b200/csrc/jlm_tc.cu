@@ -463,14 +463,27 @@ __global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, int
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
   const float2* p = part + (int64_t)warp * part_ld;
+  // one pass: the partials of a row (<= 8 per lane for V <= 65536) stay in registers between the max and the sum
+  constexpr int PL = 8;
+  float2 v[PL];
   float mx = -INFINITY;
-  for (int t = lane; t < n_tiles; t += 32) mx = fmaxf(mx, p[t].x);
+#pragma unroll
+  for (int i = 0; i < PL; ++i) {
+    const int t = lane + 32 * i;
+    v[i] = t < n_tiles ? p[t] : make_float2(-INFINITY, 0.f);
+    mx = fmaxf(mx, v[i].x);
+  }
+  for (int t = lane + 32 * PL; t < n_tiles; t += 32) mx = fmaxf(mx, p[t].x);
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  // 2^(c_tile - c_max) in fp32 (the tile sums themselves are fp32); products and the sum in float64
   double s = 0.0;
-  for (int t = lane; t < n_tiles; t += 32) {
-    const float2 v = p[t];
-    if (v.x > -INFINITY) s += (double)v.y * exp2((double)v.x - (double)mx);
+#pragma unroll
+  for (int i = 0; i < PL; ++i)
+    if (v[i].x > -INFINITY) s += (double)v[i].y * (double)exp2f(v[i].x - mx);
+  for (int t = lane + 32 * PL; t < n_tiles; t += 32) {
+    const float2 w = p[t];
+    if (w.x > -INFINITY) s += (double)w.y * (double)exp2f(w.x - mx);
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

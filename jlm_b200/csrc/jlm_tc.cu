@@ -29,6 +29,7 @@ struct TcOperand {
   float scale = 1.f;
   CUtensorMap map_hi, map_lo;         // box = box_rows x 64 (one CTA loads the whole N tile)
   CUtensorMap pair_hi, pair_lo;       // box = box_rows/2 x 64 (each CTA of a pair loads half of the N tile)
+  CUtensorMap q_hi, q_lo;             // box = box_rows/4 x 64 (narrow 64-column tiles)
 };
 
 namespace {
@@ -555,6 +556,8 @@ int32_t upload_split(TcOperand* op, const std::vector<double>& w, int64_t rows, 
   JLM_TRY(make_map(&op->map_lo, op->lo, K, rows, K, box_rows));
   JLM_TRY(make_map(&op->pair_hi, op->hi, K, rows, K, box_rows / 2));
   JLM_TRY(make_map(&op->pair_lo, op->lo, K, rows, K, box_rows / 2));
+  JLM_TRY(make_map(&op->q_hi, op->hi, K, rows, K, box_rows / 4));
+  JLM_TRY(make_map(&op->q_lo, op->lo, K, rows, K, box_rows / 4));
   return 0;
 }
 
@@ -574,13 +577,21 @@ static bool tc_pair_enabled() {
   return v != 0;
 }
 
+static bool tc_narrow_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_TC_NARROW");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 template <int BN, int EPI>
 int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al, const TcOperand& B, GemmArgs g) {
   JLM_REQUIRE(g.K % BK == 0 && g.K > 0, "tc gemm: K=%d must be a positive multiple of %d", g.K, BK);
   g.num_m_blocks = ceil_div(g.M, BM);
   g.num_n_blocks = ceil_div(g.N, BN);
   if (g.num_m_blocks * g.num_n_blocks <= 0) return 0;
-  if (g.num_m_blocks >= 2 && h->sm_count >= 2 && tc_pair_enabled()) {
+  if constexpr (BN == 256) if (g.num_m_blocks >= 2 && h->sm_count >= 2 && tc_pair_enabled()) {
     using C = TileCfg<BN, 2>;
     static bool configured = false;
     if (!configured) {
@@ -612,7 +623,9 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
   }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  k_tc_gemm<BN, EPI, 1><<<grid, EpiCfg<EPI>::THREADS, C::SMEM, h->stream>>>(Ah, Al, B.map_hi, B.map_lo, g);
+  // 64-column tiles read B through the quarter-box maps (operands are uploaded with 256-row boxes)
+  k_tc_gemm<BN, EPI, 1><<<grid, EpiCfg<EPI>::THREADS, C::SMEM, h->stream>>>(Ah, Al, BN == 64 ? B.q_hi : B.map_hi,
+                                                                           BN == 64 ? B.q_lo : B.map_lo, g);
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -819,7 +832,14 @@ int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out)
     g.s_lo = s->Ts_lo;
     g.lds = h->Kt;
     g.split_scale = w->sT;
-    JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
+    // h.PM has few output columns (Kt = E): 256-column tiles give ceil(M/128) CTAs, each with an epilogue
+    // nothing overlaps.  64-column tiles quadruple the tile count so every SM works and the store
+    // epilogue of one tile runs under the MMAs of the next.
+    const int tiles256 = ceil_div(M, BM) * ceil_div(h->Kt, 256);
+    if (tiles256 < 2 * h->sm_count && tc_narrow_enabled())
+      JLM_TRY((launch_gemm<64, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
+    else
+      JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
     b->launches += 1;
     T32 = s->T32;
     ldt = h->Kt;

@@ -369,3 +369,40 @@ def test_decode_stream_equals_decode_batch(tmp_path_factory):
             assert dec.decode_batch(batches[1], topN=4, beam_width=5, backend=backend) == want[1]
     finally:
         dec._want_trace = True
+
+
+def test_all_candidates_tied_keep_enumeration_order(tmp_path_factory):
+    """A model whose projection and output bias are zero scores every candidate of a frame identically, so the
+    kept paths are decided by the stable sort alone (decoder.py:227-229: first `beam` candidates in node order, then
+    parent rank).  Dense readings give frames with hundreds of tied candidates - more than k_prune's shared-memory
+    survivor buffer, so its insertion-list path runs too.  Both back ends, beams 3 / 10 / 40."""
+    import jlm_b200
+    from jlm_b200 import config, synth
+    from oracle import jlm_oracle as O
+    root = tmp_path_factory.mktemp('exp_ties')
+    cfg = synth.make_config(400, 64, 32, 'tied')
+    weights = synth.make_weights(cfg, seed=4)
+    weights['PM'][:] = 0
+    weights['b2'][:] = 0
+    # few distinct readings -> many words per reading -> frames with hundreds of candidates
+    kana = synth.KANA[:3]
+    lexicon = [('<eos>', 10 ** 8)]
+    reading_dict = {}
+    rng = np.random.default_rng(0)
+    for n in range(398):
+        reading = ''.join(kana[k] for k in rng.integers(0, 3, size=int(rng.integers(1, 3))))
+        lexicon.append(('w{}/{}/P'.format(n, reading), 10 ** 8 // (n + 1)))
+        reading_dict.setdefault(reading, []).append(n + 1)
+    synth.write_experiment(str(root), 1, cfg, weights, lexicon, reading_dict)
+    config.set_root(str(root))
+    dec = jlm_b200.Decoder(1)
+    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict)
+    sents = [''.join(kana[k] for k in rng.integers(0, 3, size=6)) for _ in range(5)]
+    for beam in (3, 10, 40):
+        want = [ora.decode(s, topN=beam, beam_width=beam) for s in sents]
+        assert max(len(fr) for fr in ora.frames) * min(beam, 10) > 96
+        for backend in (EXACT, TC):
+            got = dec.decode_batch(sents, topN=beam, beam_width=beam, backend=backend)
+            for g, w in zip(got, want):
+                assert [ws for _, ws in g] == [ws for _, ws in w], (beam, backend)
+                np.testing.assert_allclose([s for s, _ in g], [s for s, _ in w], rtol=0, atol=1e-3)

@@ -198,6 +198,7 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;

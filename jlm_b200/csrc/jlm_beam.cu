@@ -72,7 +72,7 @@ __device__ __forceinline__ void load4(const double* p, double (&t)[4]) {
 template <typename TT, bool DYN>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
-              int64_t item0, int n_items, int64_t row0, int use_lse) {
+              int64_t item0, int n_items, int64_t row0, int use_lse, int defer) {
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
   if (item >= n_items) return;
@@ -89,7 +89,8 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
   for (int q = 0; q < SC_MAXPASS; ++q) {
     pre[q] = 0.0;
     const int r = q * SC_RC + my_r;
-    if (!DYN && (lane & 3) == 0 && r < rows) pre[q] = d.slot_score[ps0 + r] + (use_lse ? d.slot_lse[ps0 + r] : 0.0);
+    if (!DYN && !defer && (lane & 3) == 0 && r < rows)
+      pre[q] = d.slot_score[ps0 + r] + (use_lse ? d.slot_lse[ps0 + r] : 0.0);
   }
   int s = 0;
 #pragma unroll
@@ -151,14 +152,34 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
       const double y = v1 + bias;
       const int64_t ps = ps0 + r0 + r;
       const int q = r0 / SC_RC;
-      double base_score;
       static_assert(SC_MAXPASS == 2, "select below is written for two prefetched passes");
-      if (q < SC_MAXPASS) base_score = q == 0 ? pre[0] : pre[1];
-      else base_score = d.slot_score[ps] + (use_lse ? d.slot_lse[ps] : 0.0);
-      d.cand_val[cpos + r0 + r] = DYN ? y : base_score - y;
-      if (DYN) d.cand_parent[cpos + r0 + r] = (int32_t)ps;
+      if (DYN) {
+        d.cand_val[cpos + r0 + r] = y;
+        d.cand_parent[cpos + r0 + r] = (int32_t)ps;
+      } else if (defer) {
+        // the parent rows' LSE is still being computed (output GEMM on the main stream): leave -y, k_add_base
+        // finishes the score with the same association, score + (LSE - y)
+        d.cand_val[cpos + r0 + r] = -y;
+      } else {
+        double base_score;
+        if (q < SC_MAXPASS) base_score = q == 0 ? pre[0] : pre[1];
+        else base_score = d.slot_score[ps] + (use_lse ? d.slot_lse[ps] : 0.0);
+        d.cand_val[cpos + r0 + r] = base_score - y;
+      }
     }
   }
+}
+
+// Second half of a deferred k_score_nodes: cand_val holds -y; add the parent path's score and LSE.
+__global__ void k_add_base(BeamDev d, int64_t item0, int n_items, int W) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = (int)(i / W), r = (int)(i % W);
+  if (item >= n_items) return;
+  const ScoreItem* it = d.items + item0 + item;
+  if (r >= it->rows) return;
+  const int64_t ps = it->ps0 + r;
+  double* v = d.cand_val + it->cpos + r;
+  *v = d.slot_score[ps] + (d.slot_lse[ps] + *v);
 }
 
 // Prune: one warp per sentence keeps the beam_width best candidates of the frame under the
@@ -797,6 +818,24 @@ void stage(char* host, char* dev_base, T* dev_ptr, const std::vector<T>& v) {
 // Shared tail of an LM step: vocabulary-subset softmax statistics (static / dynamic selection) and
 // the logits of the words that can follow each kept path (nodes starting at this frame).
 template <typename TT>
+int32_t launch_score(jlm_batch* b, int t, const TT* T, int ldt, cudaStream_t st, int defer) {
+  const StepPlan& sp = b->steps[t];
+  if (sp.n_items <= 0) return 0;
+  jlm_handle* h = b->h;
+  const int grid = ceil_div(sp.n_items, SC_WARPS);
+  const int ul = b->use_lse ? 1 : 0;
+  if (b->dynamic)
+    k_score_nodes<TT, true><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items,
+                                                           sp.row0, ul, 0);
+  else
+    k_score_nodes<TT, false><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items,
+                                                            sp.row0, ul, defer);
+  JLM_CUDA(cudaGetLastError());
+  b->launches += 1;
+  return 0;
+}
+
+template <typename TT>
 int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
   jlm_handle* h = b->h;
   cudaStream_t st = h->stream;
@@ -814,19 +853,7 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
     JLM_CUDA(cudaGetLastError());
     b->launches += 2;
   }
-  if (sp.n_items > 0) {
-    const int grid = ceil_div(sp.n_items, SC_WARPS);
-    const int ul = b->use_lse ? 1 : 0;
-    if (b->dynamic)
-      k_score_nodes<TT, true><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, d, h->b2, sp.item0, sp.n_items,
-                                                             sp.row0, ul);
-    else
-      k_score_nodes<TT, false><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, d, h->b2, sp.item0, sp.n_items,
-                                                              sp.row0, ul);
-    JLM_CUDA(cudaGetLastError());
-    b->launches += 1;
-  }
-  return 0;
+  return launch_score<TT>(b, t, T, ldt, st, 0);
 }
 
 int32_t exact_lm_step(jlm_batch* b, int t) {
@@ -872,6 +899,16 @@ int32_t exact_lm_step(jlm_batch* b, int t) {
     b->launches += 1;
   }
   return lm_step_tail<double>(b, t, T, ldt);
+}
+
+bool score_overlap_enabled() {
+  static const int v = [] {
+    // Measured on B200 (cfg 2, 1024 sentences): with the scoring kernel co-resident the output GEMM slows from
+    // 0.394 to 0.418 ms per launch - more than the 0.024 ms the overlap hides - so it is off unless asked for.
+    const char* e = getenv("JLM_OVERLAP_SCORE");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0;
 }
 
 template <bool DYN>
@@ -1032,6 +1069,11 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   JLM_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   b->launches = 0;
+  if (b->backend == JLM_BACKEND_TC && score_overlap_enabled()) {
+    if (!h->side_stream) JLM_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    if (!b->ev_fork) JLM_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    if (!b->ev_join) JLM_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  }
   if (b->timers && b->events.empty()) {
     b->events.resize(3 * (size_t)b->n_steps + 1);
     for (auto& e : b->events) JLM_CUDA(cudaEventCreate(&e));
@@ -1056,8 +1098,28 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
     } else {
       const float* T32 = nullptr;
       int ldt = 0;
-      JLM_TRY(tc_batch_lm_step(b, t, &T32, &ldt));
-      if (T32) JLM_TRY(lm_step_tail<float>(b, t, T32, ldt));
+      JLM_TRY(tc_batch_lm_state(b, t, &T32, &ldt));
+      // Full softmax: the needed-word dot products depend on the stage-1 rows only, not on the LSE, so they
+      // CAN run on a side stream under the output GEMM, a one-pass kernel adding parent score + LSE after the
+      // merge (JLM_OVERLAP_SCORE=1; measured slower, see score_overlap_enabled).
+      const bool overlap = T32 && b->use_lse && b->mode == JLM_DECODE_FULL && b->steps[t].n_items > 0 &&
+                           score_overlap_enabled() && h->side_stream;
+      if (overlap) {
+        JLM_CUDA(cudaEventRecord(b->ev_fork, st));
+        JLM_CUDA(cudaStreamWaitEvent(h->side_stream, b->ev_fork, 0));
+        JLM_TRY(launch_score<float>(b, t, T32, ldt, h->side_stream, 1));
+        JLM_CUDA(cudaEventRecord(b->ev_join, h->side_stream));
+      }
+      JLM_TRY(tc_batch_lm_lse(b, t));
+      if (overlap) {
+        const StepPlan& sp = b->steps[t];
+        JLM_CUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
+        k_add_base<<<ceil_div((int64_t)sp.n_items * b->W, 256), 256, 0, st>>>(b->d, sp.item0, sp.n_items, b->W);
+        JLM_CUDA(cudaGetLastError());
+        b->launches += 1;
+      } else if (T32) {
+        JLM_TRY(lm_step_tail<float>(b, t, T32, ldt));
+      }
     }
   }
   if (b->timers) cudaEventRecord(b->events[3 * (size_t)b->n_steps], st);
@@ -1181,6 +1243,8 @@ extern "C" int32_t jlm_batch_destroy(jlm_batch* b) {
   } else {
     cudaStreamSynchronize(b->h->stream);
   }
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->out_host.p) {
     if (b->h->out_pool.size() < 8) b->h->out_pool.push_back(b->out_host);
     else b->out_host.release();

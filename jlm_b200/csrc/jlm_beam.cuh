@@ -109,6 +109,7 @@ struct jlm_batch {
   // completion: `done` is recorded after the batch's last enqueued operation (run, then the n-best D2H),
   // so fetch / destroy wait for THIS batch only and later batches on the stream keep the device busy
   cudaEvent_t done = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // side-stream scoring under the output GEMM
   HostBuf out_host;              // pinned n-best landing buffer, taken from / returned to h->out_pool
   bool d2h_queued = false;
   std::vector<cudaEvent_t> events;
@@ -121,6 +122,7 @@ struct jlm_batch {
 // tensor-core back end hooks (jlm_tc.cu)
 int32_t tc_batch_plan(jlm_batch* b, Arena& a);                 // called twice: dry run + real
 // gate GEMM .. full-vocabulary LSE for step t; returns the fp32 stage-1 rows for the needed-word dots
-int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out);
+int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out);   // gather, gate GEMM, stage-1
+int32_t tc_batch_lm_lse(jlm_batch* b, int t);                                         // output GEMMs + LSE merge
 int32_t tc_batch_get_state(jlm_batch* b, int64_t slot, int count, double* h_out, double* c_out);
 void tc_batch_free(jlm_batch* b);

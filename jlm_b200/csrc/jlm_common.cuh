@@ -122,6 +122,7 @@ struct jlm_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side_stream = nullptr;   // needed-word dot products run here while the output GEMM holds `stream`
   int sm_count = 148;
   jlm_config cfg{};
   int V = 0, H = 0, E = 0;

@@ -775,7 +775,8 @@ void tc_batch_free(jlm_batch* b) {
   b->tc = nullptr;
 }
 
-int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out) {
+// LM step, first half: gather -> gate GEMM (+LSTM epilogue) -> stage-1 projection.  Returns the fp32 stage-1 rows.
+int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out) {
   jlm_handle* h = b->h;
   TcWeights* w = h->tc;
   TcBatchState* s = b->tc;
@@ -844,6 +845,20 @@ int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out)
     T32 = s->T32;
     ldt = h->Kt;
   }
+  *T_out = T32;
+  *ldt_out = ldt;
+  return 0;
+}
+
+// LM step, second half: full-vocabulary logits + online LSE (one GEMM per segment) -> per-row LSE.
+int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
+  jlm_handle* h = b->h;
+  TcWeights* w = h->tc;
+  TcBatchState* s = b->tc;
+  cudaStream_t st = h->stream;
+  const StepPlan& sp = b->steps[t];
+  const int M = sp.rows_step;
+  if (M == 0) return 0;
   if (b->use_lse && b->mode == JLM_DECODE_FULL) {
     int tile0 = 0;
     if (b->timers) cudaEventRecord(b->kev[4 * t + 2], st);
@@ -868,8 +883,6 @@ int32_t tc_batch_lm_step(jlm_batch* b, int t, const float** T_out, int* ldt_out)
     JLM_CUDA(cudaGetLastError());
     b->launches += 1;
   }
-  *T_out = T32;
-  *ldt_out = ldt;
   return 0;
 }
 

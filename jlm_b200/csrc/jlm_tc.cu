@@ -45,6 +45,10 @@ template <int EPI>
 struct EpiCfg {
   static constexpr int WARPS = (EPI == EPI_LSTM) ? 8 : 4;   // epilogue warps
   static constexpr int THREADS = 64 + 32 * WARPS;
+  // LSTM epilogue: per-warp transpose buffer, 32 rows x (64 B payload + 16 B pad); see stage_rows / unstage_rows
+  static constexpr int STG_ROW = 80;
+  static constexpr int STG_WARP = 32 * STG_ROW;
+  static constexpr int STG = (EPI == EPI_LSTM) ? WARPS * STG_WARP : 0;
 };
 
 // sigmoid / tanh straight on the MUFU pipe (ex2.approx + rcp.approx, ~2e-7 absolute): the gate
@@ -139,6 +143,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
   float* bias_s = reinterpret_cast<float*>(gen + C::STAGES * C::STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(gen + C::STAGES * C::STAGE + C::BIAS_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint8_t* epi_stage = gen + C::STAGES * C::STAGE + C::BIAS_BYTES + C::BAR_BYTES;   // EpiCfg<EPI>::STG bytes
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
@@ -287,22 +292,38 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       constexpr int UPT = BN / 4;                       // hidden units per tile
       constexpr int UPW = UPT / (EpiCfg<EPI>::WARPS / 4);   // units per epilogue warp
       const int ubase = ((warp - 2) >> 2) * UPW;        // this warp's first unit inside the tile
+      // The epilogue's global traffic goes through a per-warp shared-memory transpose: in the TMEM layout a lane
+      // owns a ROW, so direct 16-byte accesses touch 32 different 128-byte lines per instruction, and ncu shows
+      // those L1 tag cycles coming straight out of the MMA's shared-memory operand bandwidth.  Staged, one
+      // instruction covers 8 rows x 64 contiguous bytes (lane -> row (lane & 7), 16-byte piece (lane >> 3)).
       float cprev[EPI == EPI_LSTM ? UPW : 1];
+      uint8_t* stg = epi_stage + (EPI == EPI_LSTM ? (warp - 2) * EpiCfg<EPI>::STG_WARP : 0);
+      constexpr int SR = EpiCfg<EPI>::STG_ROW;
+      const int t_row = lane & 7, t_piece = lane >> 3;
       if (EPI == EPI_LSTM) {
         const int par = row_ok ? g.parent[row] : -1;
-        if (par >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(g.c_src + (int64_t)par * g.ld_state + n_blk * UPT + ubase);
 #pragma unroll
-          for (int j = 0; j < UPW / 4; ++j) {
-            const float4 t = src[j];
-            cprev[4 * j] = t.x;
-            cprev[4 * j + 1] = t.y;
-            cprev[4 * j + 2] = t.z;
-            cprev[4 * j + 3] = t.w;
+        for (int uc = 0; uc < UPW / 16; ++uc) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + t_row;
+            const int p = __shfl_sync(0xffffffffu, par, rr);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p >= 0)
+              v = *reinterpret_cast<const float4*>(g.c_src + (int64_t)p * g.ld_state + n_blk * UPT + ubase + uc * 16 +
+                                                   4 * t_piece);
+            *reinterpret_cast<float4*>(stg + rr * SR + 16 * t_piece) = v;
           }
-        } else {
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < UPW; ++j) cprev[j] = 0.f;
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(stg + lane * SR + 16 * j);
+            cprev[uc * 16 + 4 * j] = t.x;
+            cprev[uc * 16 + 4 * j + 1] = t.y;
+            cprev[uc * 16 + 4 * j + 2] = t.z;
+            cprev[uc * 16 + 4 * j + 3] = t.w;
+          }
+          __syncwarp();
         }
       }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
@@ -373,9 +394,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
           ptx::tmem_ld_x16(taddr + 2 * UPT + ul, ro);
           ptx::tmem_ld_x16(taddr + 3 * UPT + ul, rg);
           ptx::tmem_ld_wait();
-          if (row_ok) {
-            const int u0 = n_blk * UPT + ul;
-            float hv[16], cv[16];
+          float hv[16], cv[16];      // rows past M hold the zero-filled tile: computed, never stored
+          {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float pi = fmaf(__uint_as_float(ri[j]), g.inv_scale, bs[ul + j]);
@@ -386,14 +406,55 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
               cv[j] = c;
               hv[j] = fast_tanh(c) * fast_sigmoid(po);
             }
-            float4* dc = reinterpret_cast<float4*>(g.c_out + (int64_t)row * g.ld_state + u0);
-            float4* dh = reinterpret_cast<float4*>(g.h_out + (int64_t)row * g.ld_state + u0);
+          }
+          // ---- staged stores: c, h (fp32, 64 B per row) then the fp16 split of h (hi 32 B | lo 32 B per row) ----
+          const int u0 = n_blk * UPT + ul;
+          const int row_base = m_blk * BM + q * 32;
+          {
+            float* const outs[2] = {g.c_out, g.h_out};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dc[j] = make_float4(cv[4 * j], cv[4 * j + 1], cv[4 * j + 2], cv[4 * j + 3]);
-              dh[j] = make_float4(hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
+            for (int which = 0; which < 2; ++which) {
+              const float* src = which ? hv : cv;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * SR + 16 * j) =
+                    make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + t_row;
+                const float4 v = *reinterpret_cast<const float4*>(stg + rr * SR + 16 * t_piece);
+                if (row_base + rr < g.M)
+                  *reinterpret_cast<float4*>(outs[which] + (int64_t)(row_base + rr) * g.ld_state + u0 + 4 * t_piece) = v;
+              }
+              __syncwarp();
             }
-            split_store16(g.s_hi + (int64_t)row * g.lds + u0, g.s_lo + (int64_t)row * g.lds + u0, hv, g.split_scale);
+          }
+          {
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = hv[2 * j] * g.split_scale, b2_ = hv[2 * j + 1] * g.split_scale;
+              const __half2 h2 = __floats2half2_rn(a, b2_);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(a - hf.x, b2_ - hf.y);
+              ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            uint4* w4 = reinterpret_cast<uint4*>(stg + lane * SR);
+            w4[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            w4[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            w4[2] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            w4[3] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + t_row;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * SR + 16 * t_piece);
+              __half* dst = (t_piece < 2 ? g.s_hi : g.s_lo) + (int64_t)(row_base + rr) * g.lds + u0 + 8 * (t_piece & 1);
+              if (row_base + rr < g.M) *reinterpret_cast<uint4*>(dst) = v;
+            }
+            __syncwarp();
           }
         }
       }
@@ -595,7 +656,7 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
     using C = TileCfg<BN, 2>;
     static bool configured = false;
     if (!configured) {
-      JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
       configured = true;
     }
     const int tiles = ceil_div(g.num_m_blocks, 2) * g.num_n_blocks;
@@ -603,7 +664,7 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.dynamicSmemBytes = C::SMEM + EpiCfg<EPI>::STG;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -618,13 +679,13 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
   using C = TileCfg<BN, 1>;
   static bool configured = false;
   if (!configured) {
-    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
     configured = true;
   }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
   // 64-column tiles read B through the quarter-box maps (operands are uploaded with 256-row boxes)
-  k_tc_gemm<BN, EPI, 1><<<grid, EpiCfg<EPI>::THREADS, C::SMEM, h->stream>>>(Ah, Al, BN == 64 ? B.q_hi : B.map_hi,
+  k_tc_gemm<BN, EPI, 1><<<grid, EpiCfg<EPI>::THREADS, C::SMEM + EpiCfg<EPI>::STG, h->stream>>>(Ah, Al, BN == 64 ? B.q_hi : B.map_hi,
                                                                            BN == 64 ? B.q_lo : B.map_lo, g);
   JLM_CUDA(cudaGetLastError());
   return 0;

@@ -225,28 +225,33 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
     return val[c];
   };
 
-  // ---- parallel selection (W <= 32) ----------------------------------------------------------------
-  // (1) every lane takes the minimum of its strided share of the candidates; the W-th smallest of those
-  //     32 minima is an upper bound tau of the frame's W-th best score (they are 32 of the candidates).
+  // ---- parallel selection ---------------------------------------------------------------------------
+  // (1) every lane takes L minima over its strided share of the candidates; the W-th smallest of those
+  //     32 L >= W values is an upper bound tau of the frame's W-th best score (they are candidates).
   // (2) the candidates <= tau - about 2W of them - are compacted, in ordinal order, into shared memory.
   // (3) each survivor counts the survivors that sort before it under (score, ordinal): that count is its
   //     rank in the reference's stable sort (decoder.py:227-229), and ranks < W are the kept paths.
   // No step has a serial dependence on the candidate count; the insertion list below remains for wider
   // beams and for the rare frame whose survivors overflow the buffer (many exact ties).
   bool selected = false;
-  if (L == 1) {
-    __shared__ double sv_all[4][PRUNE_CAP];
-    __shared__ int sc_all[4][PRUNE_CAP];
-    __shared__ double ov_all[4][32];
-    __shared__ int oc_all[4][32];
+  {
+    constexpr int CAP = PRUNE_CAP * L;
+    __shared__ double sv_all[4][CAP];
+    __shared__ int sc_all[4][CAP];
+    __shared__ double ov_all[4][32 * L];
+    __shared__ int oc_all[4][32 * L];
     double* sv = sv_all[threadIdx.x >> 5];
     int* sc = sc_all[threadIdx.x >> 5];
     double* ov = ov_all[threadIdx.x >> 5];
     int* oc = oc_all[threadIdx.x >> 5];
     // loads are issued eight groups at a time: a frame with thousands of candidates (one long-tailed
-    // sentence per batch sets the kernel's duration) must not pay one L2 round trip per 32 of them
+    // sentence per batch sets the kernel's duration) must not pay one L2 round trip per 32 of them.
+    // A lane keeps L minima (32-candidate group g goes to slot g % L) so that 32 L >= W values are ranked.
     constexpr int UN = 8;
-    double lmin = INFINITY;
+    static_assert(UN % L == 0, "slot of a group must be a compile-time function of the unroll index");
+    double lmin[L];
+#pragma unroll
+    for (int k = 0; k < L; ++k) lmin[k] = INFINITY;
     for (int base = 0; base < nc; base += 32 * UN) {
       double v[UN];
 #pragma unroll
@@ -255,16 +260,27 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
         v[u] = c < nc ? value(c) : INFINITY;
       }
 #pragma unroll
-      for (int u = 0; u < UN; ++u) lmin = fmin(lmin, v[u]);
+      for (int u = 0; u < UN; ++u) lmin[u % L] = fmin(lmin[u % L], v[u]);
     }
-    int rk = 0;
-#pragma unroll 8
+    int rk[L];
+#pragma unroll
+    for (int k = 0; k < L; ++k) rk[k] = 0;
+#pragma unroll 4
     for (int j = 0; j < 32; ++j) {
-      const double o = __shfl_sync(FULL, lmin, j);
-      rk += (o < lmin || (o == lmin && j < lane)) ? 1 : 0;
+#pragma unroll
+      for (int k2 = 0; k2 < L; ++k2) {
+        const double o = __shfl_sync(FULL, lmin[k2], j);
+        const int oid = j * L + k2;
+#pragma unroll
+        for (int k = 0; k < L; ++k) rk[k] += (o < lmin[k] || (o == lmin[k] && oid < lane * L + k)) ? 1 : 0;
+      }
     }
-    const unsigned holder = __ballot_sync(FULL, rk == W - 1);
-    const double tau = __shfl_sync(FULL, lmin, __ffs(holder) - 1);
+    double tau = INFINITY;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const unsigned holder = __ballot_sync(FULL, rk[k] == W - 1);
+      if (holder) tau = __shfl_sync(FULL, lmin[k], __ffs(holder) - 1);
+    }
     int ns = 0;
     for (int base = 0; base < nc; base += 32 * UN) {
       double v[UN];
@@ -279,14 +295,14 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
         const bool keep = c < nc && v[u] <= tau;
         const unsigned m = __ballot_sync(FULL, keep);
         const int pos = ns + __popc(m & ((1u << lane) - 1u));
-        if (keep && pos < PRUNE_CAP) {
+        if (keep && pos < CAP) {
           sv[pos] = v[u];
           sc[pos] = c;
         }
         ns += __popc(m);
       }
     }
-    if (ns <= PRUNE_CAP) {
+    if (ns <= CAP) {
       __syncwarp();
       for (int i = lane; i < ns; i += 32) {
         const double x = sv[i];
@@ -301,9 +317,13 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
         }
       }
       __syncwarp();
-      if (lane < W && lane < ns) {
-        es[0] = ov[lane];
-        ec[0] = oc[lane];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        const int idx = l * 32 + lane;
+        if (idx < W && idx < ns) {
+          es[l] = ov[idx];
+          ec[l] = oc[idx];
+        }
       }
       selected = true;
     }

@@ -862,8 +862,15 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
   const StepPlan& sp = b->steps[t];
   BeamDev& d = b->d;
   if (b->use_lse && b->mode != JLM_DECODE_FULL) {
-    JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.vocab_jobs + sp.job0, sp.nstep, sp.max_vocab_cols, d.vocab_cols, nullptr,
-                              b->yv));
+    // tensor-core back end: gathered split-fp16 GEMM per sentence; else (or for shapes it does not take) float64
+    int32_t on_tc = 2;
+    if (b->backend == JLM_BACKEND_TC && sizeof(TT) == sizeof(float)) {
+      on_tc = tc_vocab_logits(b, t, b->yv);
+      if (on_tc == 1) return 1;
+    }
+    if (on_tc != 0)
+      JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.vocab_jobs + sp.job0, sp.nstep, sp.max_vocab_cols, d.vocab_cols, nullptr,
+                                b->yv));
     dim3 grid(ceil_div(b->W, 4), sp.nstep);
     if (b->dynamic)
       k_dyn_prefix_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse,

@@ -125,4 +125,5 @@ int32_t tc_batch_plan(jlm_batch* b, Arena& a);                 // called twice: 
 int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out);   // gather, gate GEMM, stage-1
 int32_t tc_batch_lm_lse(jlm_batch* b, int t);                                         // output GEMMs + LSE merge
 int32_t tc_batch_get_state(jlm_batch* b, int64_t slot, int count, double* h_out, double* c_out);
+int32_t tc_vocab_logits(jlm_batch* b, int t, double* out);   // 0 = done, 1 = error, 2 = shape not supported: use the float64 kernel
 void tc_batch_free(jlm_batch* b);

@@ -518,6 +518,134 @@ __global__ void k_tc_gather_split(const float* __restrict__ h_src, const int32_t
   }
 }
 
+// Vocabulary-selection logits on the tensor cores (static vocab_select / DynamicDecoder, decoder.py:137-151,
+// decoder_dynamic.py:93-148): per sentence, y[r][j] = T[r] . LM[cols[j]] + b2[cols[j]] for its own word list.
+// The word rows are a GATHER, so there is no TMA tile: the CTA's threads copy 128 gathered rows of the
+// fp16 hi/lo weight copies (A operand, M = 128 vocabulary entries) and the sentence's <= 32 stage-1 rows
+// (B operand, N = 32) into shared memory in the SWIZZLE_128B layout the UMMA descriptors expect
+// (row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c at position c ^ (r%8)), make the writes visible to the
+// async proxy, and one thread issues the 3-MMA split products (128 x 32 x 16, fp32 accumulators in TMEM).
+// K is consumed in halves of 128 so a CTA needs 80 KB and two CTAs share an SM: one gathers while the other
+// multiplies.  TMEM lane = vocabulary entry, column = sentence row, so the epilogue's stores are coalesced
+// along the word list.  Replaces the float64 CUDA-core k_vocab_logits (414 us per frame at cfg 4) on this
+// back end; the needed-word logits are still recomputed in float64 by k_score_nodes.
+constexpr int VT_M = 128;                 // vocabulary entries per CTA
+constexpr int VT_N = 32;                  // sentence rows (beam) per CTA, zero padded
+constexpr int VT_KH = 128;                // K consumed per pass
+constexpr int VT_A_TILE = VT_M * 128;     // bytes of one 64-wide k-block of A (hi or lo)
+constexpr int VT_B_TILE = VT_N * 128;
+constexpr int VT_SMEM = (VT_KH / BK) * (2 * VT_A_TILE + 2 * VT_B_TILE) + 1024 + 64;
+
+__global__ void __launch_bounds__(128, 2)
+k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_lo, int64_t ldw,
+                  const __half* __restrict__ T_hi, const __half* __restrict__ T_lo, int64_t ldt, int K,
+                  const SubsetJob* __restrict__ jobs, const int32_t* __restrict__ cols, const float* __restrict__ b2,
+                  float inv_scale, double* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int32_t wid[VT_M];
+  __shared__ uint64_t bar_s;
+  __shared__ uint32_t tmem_slot;
+  const SubsetJob job = jobs[blockIdx.y];
+  const int c0 = blockIdx.x * VT_M;
+  if (c0 >= job.ncols) return;
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar = ptx::smem_u32(&bar_s);
+  wid[tid] = (c0 + tid < job.ncols) ? cols[job.col0 + c0 + tid] : -1;
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), VT_N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  constexpr int KBH = VT_KH / BK;                 // k-blocks per pass
+  constexpr int PASS = 2 * VT_A_TILE + 2 * VT_B_TILE;
+  uint32_t phase = 0;
+  for (int kh = 0; kh < K; kh += VT_KH) {
+    // ---- gather this K half: A rows by word id, B rows from the sentence's stage-1 block ----
+#pragma unroll
+    for (int kb = 0; kb < KBH; ++kb) {
+      uint8_t* a_hi = gen + kb * PASS;
+      uint8_t* a_lo = a_hi + VT_A_TILE;
+      uint8_t* b_hi = a_lo + VT_A_TILE;
+      uint8_t* b_lo = b_hi + VT_B_TILE;
+      const int kcol = kh + kb * BK;
+      for (int i = tid; i < VT_M * 8; i += 128) {
+        const int r = i >> 3, c = i & 7;
+        const int w = wid[r];
+        uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+        if (w >= 0 && kcol + c * 8 < K) {
+          vh = *reinterpret_cast<const uint4*>(W_hi + (int64_t)w * ldw + kcol + c * 8);
+          vl = *reinterpret_cast<const uint4*>(W_lo + (int64_t)w * ldw + kcol + c * 8);
+        }
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = vh;
+        *reinterpret_cast<uint4*>(a_lo + off) = vl;
+      }
+      for (int i = tid; i < VT_N * 8; i += 128) {
+        const int r = i >> 3, c = i & 7;
+        uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+        if (r < job.rows && kcol + c * 8 < K) {
+          vh = *reinterpret_cast<const uint4*>(T_hi + (job.row0 + r) * ldt + kcol + c * 8);
+          vl = *reinterpret_cast<const uint4*>(T_lo + (job.row0 + r) * ldt + kcol + c * 8);
+        }
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(b_hi + off) = vh;
+        *reinterpret_cast<uint4*>(b_lo + off) = vl;
+      }
+    }
+    ptx::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
+    __syncthreads();
+    if (warp == 0 && ptx::elect_one()) {
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(VT_M, VT_N);
+#pragma unroll
+      for (int kb = 0; kb < KBH; ++kb) {
+        const uint32_t sa = base + kb * PASS;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ah = ptx::umma_desc_sw128(sa + k * 32);
+          const uint64_t al = ptx::umma_desc_sw128(sa + VT_A_TILE + k * 32);
+          const uint64_t bh = ptx::umma_desc_sw128(sa + 2 * VT_A_TILE + k * 32);
+          const uint64_t bl = ptx::umma_desc_sw128(sa + 2 * VT_A_TILE + VT_B_TILE + k * 32);
+          ptx::mma_f16_ss(tmem_base, ah, bl, idesc, (kh | kb | k) != 0 ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_base, al, bh, idesc, 1u);
+          ptx::mma_f16_ss(tmem_base, ah, bh, idesc, 1u);
+        }
+      }
+      ptx::tc_commit(bar);             // arrives when every MMA above has read its operands and written TMEM
+    }
+    __syncwarp();
+    ptx::mbar_wait(bar, phase);        // shared memory may be overwritten / accumulators may be read
+    phase ^= 1u;
+    ptx::tc_fence_after();
+  }
+  // ---- epilogue: lane = vocabulary entry, columns = sentence rows ----
+  {
+    uint32_t r[32];
+    ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), r);
+    ptx::tmem_ld_wait();
+    const int j = c0 + tid;
+    if (j < job.ncols) {
+      const double bias = (double)b2[wid[tid]];
+      for (int q = 0; q < job.rows; ++q)
+        out[job.out0 + (int64_t)q * job.ncols + j] = (double)(__uint_as_float(r[q]) * inv_scale) + bias;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, VT_N);
+}
+
 // partial (c = max*log2e, s = sum 2^(v*log2e - c)) per 256-column tile -> natural-log LSE in float64
 __global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, int n_tiles, int M,
                                double* __restrict__ lse) {
@@ -958,6 +1086,36 @@ int32_t tc_batch_get_state(jlm_batch* b, int64_t slot, int count, double* h_out,
     for (int k = 0; k < count; ++k)
       for (int j = 0; j < h->H; ++j) dst[(size_t)k * h->H + j] = (double)tmp[(size_t)k * h->Hp + j];
   }
+  return 0;
+}
+
+// Vocabulary-selection logits for step t on the tensor cores; returns 2 when this back end cannot take the
+// job shape (segmented projection, beam > 32) and the float64 kernel must run instead, 1 on a CUDA error.
+int32_t tc_vocab_logits(jlm_batch* b, int t, double* out) {
+  jlm_handle* h = b->h;
+  TcWeights* w = h->tc;
+  TcBatchState* s = b->tc;
+  const StepPlan& sp = b->steps[t];
+  static const int enabled = [] {
+    const char* e = getenv("JLM_TC_VOCAB");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || !w || !s || h->untied || h->n_seg != 1 || b->W > VT_N || h->seg[0].kpad % BK != 0) return 2;
+  if (sp.nstep <= 0 || sp.max_vocab_cols <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    JLM_CUDA(cudaFuncSetAttribute(k_tc_vocab_logits, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
+    configured = true;
+  }
+  const int gx = ceil_div(sp.max_vocab_cols, VT_M);
+  const float inv_scale = 1.f / (w->sT * w->seg[0].scale);
+  for (int j0 = 0; j0 < sp.nstep; j0 += 65535) {
+    const int nj = std::min(sp.nstep - j0, 65535);
+    k_tc_vocab_logits<<<dim3(gx, nj), 128, VT_SMEM, h->stream>>>(
+        w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, s->Ts_hi + h->seg[0].koff, s->Ts_lo + h->seg[0].koff, h->Kt,
+        h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, b->d.vocab_cols, h->b2, inv_scale, out);
+  }
+  JLM_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -455,6 +455,8 @@ k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv
 // i > k (decoder_dynamic.py:112-148).  Columns are ordered by first appearance, so LSE_i is a
 // running log-sum-exp cut at the per-frame boundaries; frame 0 also counts the duplicate entries the
 // reference keeps in lattice_vocab[0].
+constexpr int DYN_CAP = 1024;   // columns of a sentence's cumulative word list the scan path buffers per warp
+
 __global__ void __launch_bounds__(128)
 k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restrict__ info,
                  const int32_t* __restrict__ vfp, const double* __restrict__ yv, double* __restrict__ dyn_lse,
@@ -467,6 +469,50 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
   const double* p = yv + job.out0 + (int64_t)r * job.ncols;
   const int64_t slot = slot_base + job.row0 + r;
   const int par = slot_parent[slot];
+  // Fast path: one maximum over every column the row will ever be scored under, then ONE pass of
+  // exp(y - max) with a warp scan; the running sums at the per-frame boundaries are the softmax denominators
+  // of lattice_vocab[i] (all terms positive, so a prefix of the sum is as accurate as a sum of its own),
+  // and lane i takes the log for frame i.  The per-frame two-pass loop below costs two warp reductions and
+  // four float64 transcendentals per future frame and remains for word lists longer than the buffer.
+  __shared__ double csum_all[4][DYN_CAP];
+  const int n_all = vfp[inf.vfp_off + inf.T + 1];
+  if (n_all <= DYN_CAP && n_all > 0) {
+    double* csum = csum_all[threadIdx.x >> 5];
+    const bool dup = (k == 0);
+    double gmax = -INFINITY;
+    for (int j = lane; j < n_all; j += 32) gmax = fmax(gmax, p[j]);
+    if (dup)
+      for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) gmax = fmax(gmax, p[j]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    double sdup = 0.0;
+    if (dup) {
+      for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) sdup += exp(p[j] - gmax);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sdup += __shfl_xor_sync(0xffffffffu, sdup, o);
+    }
+    double carry = 0.0;
+    for (int base = 0; base < n_all; base += 32) {
+      const int j = base + lane;
+      double e = j < n_all ? exp(p[j] - gmax) : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, e, o);
+        if (lane >= o) e += up;
+      }
+      e += carry;
+      if (j < n_all) csum[j] = e;
+      carry = __shfl_sync(0xffffffffu, e, 31);
+    }
+    __syncwarp();
+    for (int i = k + 1 + lane; i <= inf.T; i += 32) {
+      const int end = vfp[inf.vfp_off + i + 1];
+      const double lse = gmax + log((end > 0 ? csum[end - 1] : 0.0) + sdup);
+      dyn_lse[slot * tstride + i] = lse;
+      dyn_chain[slot * tstride + i] = (par >= 0 ? dyn_chain[(int64_t)par * tstride + i] : 0.0) + lse;
+    }
+    return;
+  }
   double M = -INFINITY, Ssum = 0.0;
   int pos = 0;
   for (int i = k + 1; i <= inf.T; ++i) {

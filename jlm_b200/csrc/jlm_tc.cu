@@ -579,6 +579,7 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
       uint8_t* b_hi = a_lo + VT_A_TILE;
       uint8_t* b_lo = b_hi + VT_B_TILE;
       const int kcol = kh + kb * BK;
+#pragma unroll
       for (int i = tid; i < VT_M * 8; i += 128) {
         const int r = i >> 3, c = i & 7;
         const int w = wid[r];
@@ -591,6 +592,7 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
         *reinterpret_cast<uint4*>(a_hi + off) = vh;
         *reinterpret_cast<uint4*>(a_lo + off) = vl;
       }
+#pragma unroll
       for (int i = tid; i < VT_N * 8; i += 128) {
         const int r = i >> 3, c = i & 7;
         uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;

@@ -224,3 +224,19 @@ def test_native_lexicon_rejects_bad_input():
     rc = lib.jlm_lexicon_create(2, _lib.ptr(rptr, ctypes.c_int64), _lib.ptr(chars, ctypes.c_uint32),
                                 _lib.ptr(wptr, ctypes.c_int64), _lib.ptr(wids, ctypes.c_int32), 1, 0, ctypes.byref(h))
     assert rc != 0 and b'duplicate reading' in lib.jlm_last_error()
+
+
+def test_streaming_entry_points_reject_bad_arguments_without_a_device():
+    """jlm_decode_texts_submit / _collect / _cancel validate before touching CUDA: null handles and jobs come back
+    as status 1 with a message (never a crash), and cancel(NULL) is a no-op."""
+    lib = _lib.load()
+    job = ctypes.c_void_p()
+    rc = lib.jlm_decode_texts_submit(None, None, 1, None, None, 5, 5, 0, 0, None, 0, 0, 0, ctypes.byref(job))
+    assert rc != 0 and b'jlm_decode_texts_submit' in lib.jlm_last_error() and not job.value
+    nb = _lib.TextNBest()
+    rc = lib.jlm_decode_texts_collect(None, ctypes.byref(nb), None)
+    assert rc != 0 and b'jlm_decode_texts_collect' in lib.jlm_last_error()
+    assert lib.jlm_decode_texts_cancel(None) == 0
+    assert lib.jlm_batch_fetch_async(None) != 0 and b'jlm_batch_fetch_async' in lib.jlm_last_error()
+    rc = lib.jlm_decode_texts(None, None, 1, None, None, 5, 5, 0, 0, None, 0, 0, ctypes.byref(nb), None)
+    assert rc != 0

@@ -87,6 +87,7 @@ struct TileCfg {
 struct GemmArgs {
   int M, N, K;
   int num_m_blocks, num_n_blocks;
+  int a_row0;           // first row of the A operand inside its tensor map (per-slot arrays: the step's first slot)
   float inv_scale;      // 1 / (scale_A * scale_B)
   const float* bias;    // [N] (tile order) or nullptr
   // EPI_LSE
@@ -205,14 +206,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
             // both CTAs' loads are counted on the LEADER's full barrier: it expects two stages' worth of bytes
             if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::STAGE);
             const int b_row = n_blk * BN + (int)rank * (BN / 2);
-            ptx::tma_load_2d_pair(sa, &mAh, full_bar(stage), kb * BK, m_blk * BM);
-            ptx::tma_load_2d_pair(sa + A_TILE, &mAl, full_bar(stage), kb * BK, m_blk * BM);
+            ptx::tma_load_2d_pair(sa, &mAh, full_bar(stage), kb * BK, g.a_row0 + m_blk * BM);
+            ptx::tma_load_2d_pair(sa + A_TILE, &mAl, full_bar(stage), kb * BK, g.a_row0 + m_blk * BM);
             ptx::tma_load_2d_pair(sa + 2 * A_TILE, &mBh, full_bar(stage), kb * BK, b_row);
             ptx::tma_load_2d_pair(sa + 2 * A_TILE + C::B_TILE, &mBl, full_bar(stage), kb * BK, b_row);
           } else {
             ptx::mbar_expect_tx(full_bar(stage), C::STAGE);
-            ptx::tma_load_2d(sa, &mAh, full_bar(stage), kb * BK, m_blk * BM);
-            ptx::tma_load_2d(sa + A_TILE, &mAl, full_bar(stage), kb * BK, m_blk * BM);
+            ptx::tma_load_2d(sa, &mAh, full_bar(stage), kb * BK, g.a_row0 + m_blk * BM);
+            ptx::tma_load_2d(sa + A_TILE, &mAl, full_bar(stage), kb * BK, g.a_row0 + m_blk * BM);
             ptx::tma_load_2d(sa + 2 * A_TILE, &mBh, full_bar(stage), kb * BK, n_blk * BN);
             ptx::tma_load_2d(sa + 2 * A_TILE + C::B_TILE, &mBl, full_bar(stage), kb * BK, n_blk * BN);
           }
@@ -414,6 +415,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
             float* const outs[2] = {g.c_out, g.h_out};
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
+              if (which == 1 && !g.h_out) continue;      // tied models keep h only as its fp16 split
               const float* src = which ? hv : cv;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -478,43 +480,32 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
   }
 }
 
-// A = [ h[parent] | LM_in[word] ] * scale -> fp16 hi/lo, 8 elements per thread
-__global__ void k_tc_gather_split(const float* __restrict__ h_src, const int32_t* __restrict__ parent,
-                                  const int32_t* __restrict__ word, const float* __restrict__ LM_in, int Hp, int Ep,
-                                  int M, float scale, __half* __restrict__ A_hi, __half* __restrict__ A_lo) {
+// A = [ h[parent] | LM_in[word] ] as fp16 hi/lo at the gate-input scale: pure 16-byte row copies - the LSTM
+// epilogue leaves h as its split per slot and the embedding table is split once at load time (same formula, same
+// bits as splitting on the fly).
+__global__ void k_tc_gather_rows(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo,
+                                 const int32_t* __restrict__ parent, const int32_t* __restrict__ word,
+                                 const __half* __restrict__ E_hi, const __half* __restrict__ E_lo, int Hp, int Ep, int M,
+                                 __half* __restrict__ A_hi, __half* __restrict__ A_lo) {
   const int Kg = Hp + Ep;
   const int64_t total = (int64_t)M * (Kg / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / (Kg / 8));
     const int k = (int)(i % (Kg / 8)) * 8;
-    float v[8];
-    const float* src = nullptr;
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
     if (k < Hp) {
       const int p = parent[m];
-      if (p >= 0) src = h_src + (int64_t)p * Hp + k;
+      if (p >= 0) {
+        vh = *reinterpret_cast<const uint4*>(H_hi + (int64_t)p * Hp + k);
+        vl = *reinterpret_cast<const uint4*>(H_lo + (int64_t)p * Hp + k);
+      }
     } else {
-      src = LM_in + (int64_t)word[m] * Ep + (k - Hp);
+      const int64_t o = (int64_t)word[m] * Ep + (k - Hp);
+      vh = *reinterpret_cast<const uint4*>(E_hi + o);
+      vl = *reinterpret_cast<const uint4*>(E_lo + o);
     }
-    if (src) {
-      const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    }
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = v[2 * j] * scale, y = v[2 * j + 1] * scale;
-      const __half2 h2 = __floats2half2_rn(x, y);
-      const float2 hf = __half22float2(h2);
-      const __half2 l2 = __floats2half2_rn(x - hf.x, y - hf.y);
-      ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
-      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
-    }
-    *reinterpret_cast<uint4*>(A_hi + (int64_t)m * Kg + k) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    *reinterpret_cast<uint4*>(A_lo + (int64_t)m * Kg + k) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    *reinterpret_cast<uint4*>(A_hi + (int64_t)m * Kg + k) = vh;
+    *reinterpret_cast<uint4*>(A_lo + (int64_t)m * Kg + k) = vl;
   }
 }
 
@@ -726,10 +717,11 @@ float pow2_scale_for(double max_abs) {
 }
 
 // split a host matrix (float64 values) [rows, K] into device fp16 hi/lo
-int32_t upload_split(TcOperand* op, const std::vector<double>& w, int64_t rows, int64_t K, int box_rows) {
+int32_t upload_split(TcOperand* op, const std::vector<double>& w, int64_t rows, int64_t K, int box_rows,
+                     float fixed_scale = 0.f) {
   double mx = 0;
   for (double v : w) mx = std::max(mx, std::fabs(v));
-  op->scale = pow2_scale_for(mx);
+  op->scale = fixed_scale > 0.f ? fixed_scale : pow2_scale_for(mx);
   op->rows = rows;
   op->K = K;
   std::vector<__half> hi(w.size()), lo(w.size());
@@ -831,8 +823,8 @@ struct TcWeights {
   float* bg_perm = nullptr;           // [4*Hp]
   TcOperand P1;                       // [Kt, Hp]
   TcOperand seg[JLM_MAX_SEGMENTS];    // [V_i, kpad_i]
-  float sA = 1.f;                     // gate-input scale (h and embedding share it)
-  float sH = 16384.f;                 // |h| < 1
+  TcOperand Emb;                      // [V, Ep] input embedding, split at the gate-input scale sA
+  float sA = 1.f;                     // gate-input scale: h (kept per slot as its fp16 split) and embedding share it
   float sT = 1.f;                     // stage-1 output scale
   int lse_tiles = 0;
 };
@@ -869,6 +861,8 @@ int32_t tc_prepare_weights(jlm_handle* h) {
     double mx = 1.0;
     for (float v : LM) mx = std::max(mx, (double)std::fabs(v));
     w->sA = pow2_scale_for(mx);
+    std::vector<double> Ed(LM.begin(), LM.end());
+    JLM_TRY(upload_split(&w->Emb, Ed, V, h->Ep, 256, w->sA));
   }
   if (!h->untied) {
     std::vector<double> P1((size_t)h->Kt * Hp);
@@ -882,7 +876,7 @@ int32_t tc_prepare_weights(jlm_handle* h) {
     }
     w->sT = pow2_scale_for(bound);
   } else {
-    w->sT = w->sH;
+    w->sT = w->sA;      // untied: the output GEMM reads the h split directly
   }
   w->lse_tiles = 0;
   for (int i = 0; i < h->n_seg; ++i) {
@@ -902,6 +896,7 @@ void tc_free_weights(jlm_handle* h) {
   TcWeights* w = h->tc;
   free_operand(&w->Wg);
   free_operand(&w->P1);
+  free_operand(&w->Emb);
   for (auto& s : w->seg) free_operand(&s);
   cudaFree(w->bg_perm);
   delete w;
@@ -912,10 +907,10 @@ void tc_free_weights(jlm_handle* h) {
 // batch-level state
 // ------------------------------------------------------------------------------------------------
 struct TcBatchState {
-  float* h32 = nullptr;   // [n_slots, Hp]
-  float* c32 = nullptr;
+  float* h32 = nullptr;   // [n_slots, Hp], untied projections only (their needed-word dots read fp32 h rows)
+  float* c32 = nullptr;   // [n_slots, Hp]
   __half *Ag_hi = nullptr, *Ag_lo = nullptr;   // [Mpad, Kg]
-  __half *Hs_hi = nullptr, *Hs_lo = nullptr;   // [Mpad, Hp]
+  __half *Hs_hi = nullptr, *Hs_lo = nullptr;   // [n_slots, Hp]: h * sA as hi + lo, written by the LSTM epilogue
   float* T32 = nullptr;                        // [Mpad, Kt]
   __half *Ts_hi = nullptr, *Ts_lo = nullptr;   // [Mpad, Kt]
   float2* part = nullptr;
@@ -932,12 +927,12 @@ int32_t tc_batch_plan(jlm_batch* b, Arena& a) {
   const size_t ns = (size_t)b->n_slots;
   s->Mpad = round_up64(std::max(b->max_rows_step, 1), BM);
   const size_t mp = (size_t)s->Mpad;
-  s->h32 = a.take<float>(ns * h->Hp);
+  s->h32 = h->untied ? a.take<float>(ns * h->Hp) : nullptr;
   s->c32 = a.take<float>(ns * h->Hp);
   s->Ag_hi = a.take<__half>(mp * h->Kg);
   s->Ag_lo = a.take<__half>(mp * h->Kg);
-  s->Hs_hi = a.take<__half>(mp * h->Hp);
-  s->Hs_lo = a.take<__half>(mp * h->Hp);
+  s->Hs_hi = a.take<__half>((ns + BM) * h->Hp);      // + one tile: the last step's last TMA box stays inside
+  s->Hs_lo = a.take<__half>((ns + BM) * h->Hp);
   if (!h->untied) {
     s->T32 = a.take<float>(mp * h->Kt);
     s->Ts_hi = a.take<__half>(mp * h->Kt);
@@ -951,12 +946,14 @@ int32_t tc_batch_plan(jlm_batch* b, Arena& a) {
   if (a.dry) return 0;
   JLM_TRY(make_map(&s->mAg_hi, s->Ag_hi, h->Kg, s->Mpad, h->Kg, BM));
   JLM_TRY(make_map(&s->mAg_lo, s->Ag_lo, h->Kg, s->Mpad, h->Kg, BM));
-  JLM_TRY(make_map(&s->mHs_hi, s->Hs_hi, h->Hp, s->Mpad, h->Hp, BM));
-  JLM_TRY(make_map(&s->mHs_lo, s->Hs_lo, h->Hp, s->Mpad, h->Hp, BM));
+  const int64_t hs_rows = (int64_t)ns + BM;
+  JLM_TRY(make_map(&s->mHs_hi, s->Hs_hi, h->Hp, hs_rows, h->Hp, BM));
+  JLM_TRY(make_map(&s->mHs_lo, s->Hs_lo, h->Hp, hs_rows, h->Hp, BM));
   const int64_t ldT = h->untied ? h->Hp : h->Kt;
+  const int64_t t_rows = h->untied ? hs_rows : s->Mpad;      // untied: T aliases the per-slot h split
   for (int i = 0; i < h->n_seg; ++i) {
-    JLM_TRY(make_map(&s->mTs_hi[i], s->Ts_hi + h->seg[i].koff, h->seg[i].kpad, s->Mpad, ldT, BM));
-    JLM_TRY(make_map(&s->mTs_lo[i], s->Ts_lo + h->seg[i].koff, h->seg[i].kpad, s->Mpad, ldT, BM));
+    JLM_TRY(make_map(&s->mTs_hi[i], s->Ts_hi + h->seg[i].koff, h->seg[i].kpad, t_rows, ldT, BM));
+    JLM_TRY(make_map(&s->mTs_lo[i], s->Ts_lo + h->seg[i].koff, h->seg[i].kpad, t_rows, ldT, BM));
   }
   return 0;
 }
@@ -979,13 +976,14 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
   if (M == 0) return 0;
   const int32_t* parent = b->d.slot_parent + sp.row0;
   const int32_t* word = b->d.slot_word + sp.row0;
-  float* hrow = s->h32 + sp.row0 * h->Hp;
+  float* hrow = s->h32 ? s->h32 + sp.row0 * h->Hp : nullptr;
   float* crow = s->c32 + sp.row0 * h->Hp;
   if (b->timers) cudaEventRecord(b->events[3 * t + 1], st);
   {
     const int64_t total = (int64_t)M * (h->Kg / 8);
     int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
-    k_tc_gather_split<<<grid, 256, 0, st>>>(s->h32, parent, word, h->LM_in, h->Hp, h->Ep, M, w->sA, s->Ag_hi, s->Ag_lo);
+    k_tc_gather_rows<<<grid, 256, 0, st>>>(s->Hs_hi, s->Hs_lo, parent, word, w->Emb.hi, w->Emb.lo, h->Hp, h->Ep, M,
+                                           s->Ag_hi, s->Ag_lo);
     JLM_CUDA(cudaGetLastError());
   }
   {
@@ -1000,10 +998,10 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
     g.h_out = hrow;
     g.c_out = crow;
     g.ld_state = h->Hp;
-    g.s_hi = s->Hs_hi;
-    g.s_lo = s->Hs_lo;
+    g.s_hi = s->Hs_hi + sp.row0 * h->Hp;
+    g.s_lo = s->Hs_lo + sp.row0 * h->Hp;
     g.lds = h->Hp;
-    g.split_scale = w->sH;
+    g.split_scale = w->sA;
     if (b->timers) cudaEventRecord(b->kev[4 * t], st);
     JLM_TRY((launch_gemm<GATE_BN, EPI_LSTM>(h, s->mAg_hi, s->mAg_lo, w->Wg, g)));
     if (b->timers) cudaEventRecord(b->kev[4 * t + 1], st);
@@ -1017,7 +1015,8 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
     g.M = M;
     g.N = h->Kt;
     g.K = h->Hp;
-    g.inv_scale = 1.f / (w->sH * w->P1.scale);
+    g.inv_scale = 1.f / (w->sA * w->P1.scale);
+    g.a_row0 = (int)sp.row0;
     g.C32 = s->T32;
     g.ldc = h->Kt;
     g.s_hi = s->Ts_hi;
@@ -1064,6 +1063,7 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
       g.part = s->part;
       g.part_ld = w->lse_tiles;
       g.part_tile0 = tile0;
+      g.a_row0 = h->untied ? (int)sp.row0 : 0;      // untied: A is the per-slot h split itself
       JLM_TRY((launch_gemm<256, EPI_LSE>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], g)));
       tile0 += ceil_div(g.N, 256);
       b->launches += 1;
@@ -1079,14 +1079,24 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
 
 int32_t tc_batch_get_state(jlm_batch* b, int64_t slot, int count, double* h_out, double* c_out) {
   jlm_handle* h = b->h;
-  std::vector<float> tmp((size_t)count * h->Hp);
-  for (int which = 0; which < 2; ++which) {
-    double* dst = which ? c_out : h_out;
-    if (!dst) continue;
-    const float* src = (which ? b->tc->c32 : b->tc->h32) + slot * h->Hp;
-    JLM_CUDA(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  const size_t n = (size_t)count * h->Hp;
+  if (c_out) {
+    std::vector<float> tmp(n);
+    JLM_CUDA(cudaMemcpy(tmp.data(), b->tc->c32 + slot * h->Hp, n * sizeof(float), cudaMemcpyDeviceToHost));
     for (int k = 0; k < count; ++k)
-      for (int j = 0; j < h->H; ++j) dst[(size_t)k * h->H + j] = (double)tmp[(size_t)k * h->Hp + j];
+      for (int j = 0; j < h->H; ++j) c_out[(size_t)k * h->H + j] = (double)tmp[(size_t)k * h->Hp + j];
+  }
+  if (h_out) {
+    // h lives as its fp16 split at the gate-input scale: h = (hi + lo) / sA
+    std::vector<__half> hi(n), lo(n);
+    JLM_CUDA(cudaMemcpy(hi.data(), b->tc->Hs_hi + slot * h->Hp, n * sizeof(__half), cudaMemcpyDeviceToHost));
+    JLM_CUDA(cudaMemcpy(lo.data(), b->tc->Hs_lo + slot * h->Hp, n * sizeof(__half), cudaMemcpyDeviceToHost));
+    const double inv = 1.0 / (double)h->tc->sA;
+    for (int k = 0; k < count; ++k)
+      for (int j = 0; j < h->H; ++j) {
+        const size_t i = (size_t)k * h->Hp + j;
+        h_out[(size_t)k * h->H + j] = ((double)__half2float(hi[i]) + (double)__half2float(lo[i])) * inv;
+      }
   }
   return 0;
 }

@@ -207,6 +207,22 @@ int32_t jlm_decode_texts(jlm_handle* h, const jlm_lexicon* lex, int32_t n_sent, 
                          const int32_t* extra_ids, int32_t backend, int32_t n_chunks, jlm_text_nbest* out,
                          struct jlm_batch_info_s* info /* nullable: totals over the chunks, enables the timers */);
 
+/* LM state pool: LSTM_Model.predict_with_context (decoder/model.py:195-198) for host-driven searches such as
+ * CharRNNDecoder (decoder/decoder.py:244-341), with the (hidden, cell) pairs resident on the device and named by slot.
+ * jlm_pool_step: row k reads the state in slot src[k] (-1 = the zero state of Path.__init__, decoder.py:35-36),
+ * feeds word index[k] (_lstm_cell, model.py:125-139) and leaves the new state, its projection and the log-normaliser
+ * of its softmax (project + softmax, model.py:141-193,15-20) in slot *first_slot + k.  jlm_pool_nll: -log p(col[k] |
+ * state slot[k]), i.e. Path.append_node's -math.log(transition_probs[0][idx]) (decoder.py:43-49); -y for self-normalised
+ * models.  Only indices go down and one float64 per pair comes back.  jlm_pool_reset forgets every state. */
+typedef struct jlm_pool jlm_pool;
+int32_t jlm_pool_create(jlm_handle* h, int64_t capacity /* states */, jlm_pool** out);
+int32_t jlm_pool_destroy(jlm_pool* p);
+int32_t jlm_pool_reset(jlm_pool* p);
+int32_t jlm_pool_step(jlm_pool* p, int32_t n, const int32_t* src, const int32_t* index, int64_t* first_slot);
+int32_t jlm_pool_nll(jlm_pool* p, int32_t n, const int32_t* slot, const int32_t* col, double* out);
+int32_t jlm_pool_get_state(jlm_pool* p, int64_t slot, int32_t count, double* h_out /* [count,H] nullable */,
+                           double* c_out /* nullable */);
+
 /* jlm_decode_texts split in two for streaming callers (a server decoding batch after batch): submit
  * builds the lattices and the plan, copies the plan to the device and enqueues every frame plus the
  * n-best device->host copy, then returns without waiting; collect waits for THAT job only, fills `out`

@@ -78,6 +78,12 @@ SYMBOLS = {
     'jlm_decode_texts_collect': (C.c_int32, [_VP, C.POINTER(TextNBest), C.POINTER(BatchInfo)]),
     'jlm_decode_texts_cancel': (C.c_int32, [_VP]),
     'jlm_batch_fetch_async': (C.c_int32, [_VP]),
+    'jlm_pool_create': (C.c_int32, [_VP, C.c_int64, C.POINTER(_VP)]),
+    'jlm_pool_destroy': (C.c_int32, [_VP]),
+    'jlm_pool_reset': (C.c_int32, [_VP]),
+    'jlm_pool_step': (C.c_int32, [_VP, C.c_int32, _i32p, _i32p, C.POINTER(C.c_int64)]),
+    'jlm_pool_nll': (C.c_int32, [_VP, C.c_int32, _i32p, _i32p, _f64p]),
+    'jlm_pool_get_state': (C.c_int32, [_VP, C.c_int64, C.c_int32, _f64p, _f64p]),
     'jlm_batch_upload': (C.c_int32, [_VP, C.POINTER(LatticeBatch), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.POINTER(_VP)]),
     'jlm_batch_run': (C.c_int32, [_VP]),

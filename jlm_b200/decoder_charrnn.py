@@ -155,11 +155,126 @@ class CharRNNDecoder(Decoder):
         self.perf_sen += 1
         return out[:topN]
 
-    def decode_batch(self, inputs, topN=10, beam_width=10, **kw):
-        """decode() per sentence (the multi-step word evaluation is sentence-local host control flow)."""
-        kw.pop('backend', None)
-        kw.pop('native_lattice', None)
-        return [self.decode(x, topN=topN, beam_width=beam_width, **kw) for x in inputs]
+    def decode_batch(self, inputs, topN=10, beam_width=10, vocab_select=False, samples=0, top_sampling=False,
+                     random_sampling=False, **kw):
+        """decode() for many sentences in lock-step over a device-resident state pool (jlm_pool_*): per frame, ONE
+        call scores every (parent state, first character) pair of every sentence, one LM step per remaining
+        character position advances every unfinished candidate of every sentence together, and one LM step
+        seats the pruned beams.  The string-keyed bookkeeping (de-duplication, pruning) stays on the host; states
+        never leave the device.  Same results as decode() sentence by sentence."""
+        import time
+        from .statepool import StatePool
+        inputs = list(inputs)
+        S = len(inputs)
+        if S == 0:
+            return []
+        lat = [self._build_lattice(x, vocab_select=vocab_select, samples=samples, top_sampling=top_sampling,
+                                   random_sampling=random_sampling) for x in inputs]
+        w2i = self.w2i
+        # states needed: every candidate takes len(word)-1 steps, every kept path one more
+        W = beam_width if beam_width is not None else 1 << 30
+        need, bc_hint = 0, []
+        for fr in lat:
+            bc = [1]
+            for t in range(1, len(fr)):
+                n_c = sum(bc[n[0]] for n in fr[t])
+                need += sum(bc[n[0]] * (self._word_length(n[2]) - 1) for n in fr[t])
+                bc.append(min(W, n_c))
+            need += sum(bc)
+        pool = getattr(self, '_pool', None)
+        if pool is None or pool.capacity < need:
+            self._pool = pool = StatePool(self.model, max(need, 1024))
+        pool.reset()
+        beams = [[] for _ in range(S)]
+        Tmax = max(len(x) for x in inputs)
+        for t in range(Tmax + 1):
+            act = [s for s in range(S) if len(inputs[s]) >= t]
+            C_ = {}
+            if t == 0:
+                for s in act:
+                    C_[s] = {'score': np.zeros(1), 'slot': np.array([-1], dtype=np.int64), 'words': [['<eos>']],
+                             'text': ['<eos>'], 'cur': [w2i['<eos>']], 'wlen': [1]}
+            else:
+                req_slot, req_col, owner = [], [], []
+                for s in act:
+                    c = {'base': [], 'slot': [], 'words': [], 'text': [], 'cur': [], 'wlen': []}
+                    seen = set()
+                    for (start, cid, disp) in lat[s][t]:
+                        par = beams[s][start]
+                        for r in range(len(par['score'])):
+                            spelled = par['text'][r] + disp
+                            if spelled in seen:                      # first spelling wins (decoder.py:293-297)
+                                continue
+                            seen.add(spelled)
+                            c['base'].append(par['score'][r])
+                            c['slot'].append(int(par['slot'][r]))
+                            c['words'].append(par['words'][r] + [disp])
+                            c['text'].append(spelled)
+                            c['cur'].append(cid)
+                            c['wlen'].append(self._word_length(disp))
+                    req_slot += c['slot']
+                    req_col += c['cur']
+                    owner.append((s, len(c['slot'])))
+                    C_[s] = c
+                t0 = time.time()
+                nll = pool.nll(req_slot, req_col)                    # Path.append_node (decoder.py:43-49)
+                self.perf_log_softmax.append(time.time() - t0)
+                o = 0
+                for s, n in owner:
+                    c = C_[s]
+                    c['score'] = np.asarray(c.pop('base'), dtype=np.float64) + nll[o:o + n]
+                    c['slot'] = np.asarray(c['slot'], dtype=np.int64)
+                    o += n
+                # remaining characters of multi-character words: one LM step per position, all sentences together
+                k = 1
+                while True:
+                    rows = [(s, a) for s in act for a in range(len(C_[s]['cur'])) if C_[s]['wlen'][a] > k]
+                    if not rows:
+                        break
+                    t0 = time.time()
+                    new = pool.step([C_[s]['slot'][a] for s, a in rows], [C_[s]['cur'][a] for s, a in rows])
+                    self.perf_log_lstm.append(time.time() - t0)
+                    nxt = [w2i[C_[s]['words'][a][-1][k]] for s, a in rows]
+                    t0 = time.time()
+                    nll = pool.nll(new, nxt)
+                    self.perf_log_softmax.append(time.time() - t0)
+                    for i, (s, a) in enumerate(rows):
+                        c = C_[s]
+                        c['slot'][a] = new[i]
+                        c['cur'][a] = nxt[i]
+                        c['score'][a] += nll[i]
+                    k += 1
+            # prune (stable sort, decoder.py:331-333), then seat the survivors with one LM step on their last character
+            keep = {}
+            src, idx = [], []
+            for s in act:
+                c = C_[s]
+                if beam_width is not None:
+                    kp = np.argsort(c['score'], kind='stable')[:beam_width]
+                else:
+                    kp = np.arange(len(c['score']))          # no sort either (decoder.py:331-333)
+                keep[s] = kp
+                src += [int(c['slot'][a]) for a in kp]
+                idx += [c['cur'][a] for a in kp]
+            t0 = time.time()
+            new = pool.step(src, idx)
+            self.perf_log_lstm.append(time.time() - t0)
+            o = 0
+            for s in act:
+                c, kp = C_[s], keep[s]
+                n = len(kp)
+                beams[s].append({'score': c['score'][kp], 'slot': new[o:o + n], 'words': [c['words'][a] for a in kp],
+                                 'text': [c['text'][a] for a in kp]})
+                o += n
+        out = []
+        for s in range(S):
+            last = beams[s][len(inputs[s])]
+            res = [(float(last['score'][r]), [w for w in last['words'][r] if w != '<eos>'])
+                   for r in range(len(last['score']))]
+            out.append(res[:topN])
+        self._last_batch_beams = beams
+        self.perf_sen += S
+        return out
 
     def decode_stream(self, *a, **kw):
         raise NotImplementedError('decode_stream is the full-softmax word decoder\'s lock-step path')

@@ -130,3 +130,67 @@ def test_gpu_charrnn_matches_oracle_on_fresh_sentences(tmp_path):
             want = O.decode_charrnn(model, frames, c2i, 5, beam)
             assert [ws for _, ws in res] == [ws for _, ws in want]
             np.testing.assert_allclose([s for s, _ in res], [s for s, _ in want], rtol=0, atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['tied', 'untied', 'dsoftmax_star'])
+def test_gpu_state_pool_matches_predict_with_context(mode, tmp_path):
+    """jlm_pool_step / jlm_pool_nll against LSTM_Model.predict_with_context (model.py:195-198) on the same rows:
+    states, and -log p of arbitrary (state, word) pairs; chained steps, zero-state rows, reset."""
+    import jlm_b200
+    from jlm_b200 import config
+    from jlm_b200.statepool import StatePool
+    synth.make_experiment(str(tmp_path), 1, 300, 48, 24, mode, seed=9, write_lexicon=False)
+    config.set_root(str(tmp_path))
+    m = jlm_b200.LSTM_Model(1)
+    pool = StatePool(m, 64)
+    rng = np.random.default_rng(0)
+    idx1 = rng.integers(0, 300, size=5)
+    (p1, _, _, _), h1, c1 = m.predict_with_context(idx1.tolist(), np.zeros((5, 48)), np.zeros((5, 48)))
+    s1 = pool.step([-1] * 5, idx1)
+    assert s1.tolist() == [0, 1, 2, 3, 4]
+    hp, cp = pool.state(0, 5)
+    np.testing.assert_allclose(hp, h1, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(cp, c1, rtol=0, atol=1e-12)
+    cols = rng.integers(0, 300, size=5)
+    np.testing.assert_allclose(pool.nll(s1, cols), -np.log(p1[np.arange(5), cols]), rtol=0, atol=1e-9)
+    # second step from a permutation of the first states plus one fresh zero-state row
+    src = [3, 0, 0, -1]
+    idx2 = rng.integers(0, 300, size=4)
+    hin = np.stack([h1[3], h1[0], h1[0], np.zeros(48)])
+    cin = np.stack([c1[3], c1[0], c1[0], np.zeros(48)])
+    (p2, _, _, _), h2, c2 = m.predict_with_context(idx2.tolist(), hin, cin)
+    s2 = pool.step(src, idx2)
+    assert s2.tolist() == [5, 6, 7, 8]
+    hp, cp = pool.state(5, 4)
+    np.testing.assert_allclose(hp, h2, rtol=0, atol=1e-12)
+    pairs_s = [5, 5, 8, 2, 7]
+    pairs_c = [0, 299, 17, 4, 4]
+    want = [-np.log(p2[0, 0]), -np.log(p2[0, 299]), -np.log(p2[3, 17]), -np.log(p1[2, 4]), -np.log(p2[2, 4])]
+    np.testing.assert_allclose(pool.nll(pairs_s, pairs_c), want, rtol=0, atol=1e-9)
+    with pytest.raises(jlm_b200._lib.JlmError):
+        pool.step([9], [1])                       # slot 9 holds no state yet
+    with pytest.raises(jlm_b200._lib.JlmError):
+        pool.step([-1] * 100, [1] * 100)          # over capacity
+    pool.reset()
+    assert pool.step([-1], [int(idx1[0])]).tolist() == [0]
+
+
+@pytest.mark.gpu
+def test_gpu_charrnn_lockstep_batch_equals_per_sentence(tmp_path):
+    import jlm_b200
+    from jlm_b200 import config
+    case = dict(CHAR_CASES['charrnn_small'], seed=5)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    config.set_root(str(tmp_path))
+    dec = jlm_b200.CharRNNDecoder(1)
+    sents = synth.make_char_sentences(lexicon, 40, min_len=4, seed=123, vocab_size=case['vocab_size'])
+    sents = [s[:3 + (i % 14)] for i, s in enumerate(sents)] + ['', 'ヰ']
+    for beam, topn in ((4, 4), (12, 3)):
+        n0 = dec.perf_sen
+        got = dec.decode_batch(sents, topN=topn, beam_width=beam)
+        assert dec.perf_sen - n0 == len(sents)
+        for sent, g in zip(sents, got):
+            want = dec.decode(sent, topN=topn, beam_width=beam)
+            assert [ws for _, ws in g] == [ws for _, ws in want], sent
+            np.testing.assert_allclose([s for s, _ in g], [s for s, _ in want], rtol=0, atol=1e-9)

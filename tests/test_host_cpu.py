@@ -240,3 +240,8 @@ def test_streaming_entry_points_reject_bad_arguments_without_a_device():
     assert lib.jlm_batch_fetch_async(None) != 0 and b'jlm_batch_fetch_async' in lib.jlm_last_error()
     rc = lib.jlm_decode_texts(None, None, 1, None, None, 5, 5, 0, 0, None, 0, 0, ctypes.byref(nb), None)
     assert rc != 0
+    # state pool: same contract
+    pool = ctypes.c_void_p()
+    assert lib.jlm_pool_create(None, 16, ctypes.byref(pool)) != 0 and b'jlm_pool_create' in lib.jlm_last_error()
+    assert lib.jlm_pool_step(None, 1, None, None, None) != 0 and lib.jlm_pool_nll(None, 1, None, None, None) != 0
+    assert lib.jlm_pool_reset(None) != 0 and lib.jlm_pool_destroy(None) == 0

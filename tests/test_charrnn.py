@@ -194,3 +194,26 @@ def test_gpu_charrnn_lockstep_batch_equals_per_sentence(tmp_path):
             want = dec.decode(sent, topN=topn, beam_width=beam)
             assert [ws for _, ws in g] == [ws for _, ws in want], sent
             np.testing.assert_allclose([s for s, _ in g], [s for s, _ in want], rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_eval_harness_runs_a_char_rnn_experiment(tmp_path):
+    """eval.py:35-44 picks CharVocab + CharRNNDecoder from config['char_rnn']; the harness must drive it (lock-step
+    batch and per-pair) and count hits on display strings.  A character LM that copies nothing still has to find
+    every target among the lattice paths when the beam is wide open on short inputs."""
+    import jlm_b200
+    from jlm_b200 import config, eval as jeval
+    case = dict(CHAR_CASES['charrnn_small'], seed=2)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    lines = synth.make_test_corpus(lexicon[:cfg['vocab_size'] - 1], 24, seed=4, min_words=1, max_words=2)
+    synth.write_test_corpus(str(tmp_path), lines)
+    config.set_root(str(tmp_path))
+    logs = []
+    for extra in ([], ['--no-batch']):
+        args = jeval.build_parser().parse_args(['-e', '1', '-es', '12', '-b', '64', '--log_dir', str(tmp_path / 'eval')] + extra)
+        ev = jeval.Evaluator(args)
+        assert isinstance(ev.decoder, jlm_b200.CharRNNDecoder)
+        best, nbest, miss, n = ev.evaluate()
+        assert n == 12 and best + nbest + miss == 12
+        logs.append(open(ev.log_path, encoding='utf-8').read().split('best_hit')[0])
+    assert logs[0] == logs[1]                     # lock-step batch and per-pair decoding write the same log

@@ -244,10 +244,10 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
     int* sc = sc_all[threadIdx.x >> 5];
     double* ov = ov_all[threadIdx.x >> 5];
     int* oc = oc_all[threadIdx.x >> 5];
-    // loads are issued eight groups at a time: a frame with thousands of candidates (one long-tailed
+    // loads are issued sixteen groups at a time: a frame with thousands of candidates (one long-tailed
     // sentence per batch sets the kernel's duration) must not pay one L2 round trip per 32 of them.
     // A lane keeps L minima (32-candidate group g goes to slot g % L) so that 32 L >= W values are ranked.
-    constexpr int UN = 8;
+    constexpr int UN = 16;
     static_assert(UN % L == 0, "slot of a group must be a compile-time function of the unroll index");
     double lmin[L];
 #pragma unroll

@@ -776,15 +776,10 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
   if (g.num_m_blocks * g.num_n_blocks <= 0) return 0;
   if constexpr (BN == 256) if (g.num_m_blocks >= 2 && h->sm_count >= 2 && tc_pair_enabled()) {
     using C = TileCfg<BN, 2>;
-    static bool configured = false;
-    if (!configured) {
-      JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
-      configured = true;
-    }
+    static int max_pairs = -1;      // co-resident CTA pairs the device can hold for this kernel (0: cannot launch it)
     const int tiles = ceil_div(g.num_m_blocks, 2) * g.num_n_blocks;
-    const int pairs = std::min(tiles, h->sm_count / 2);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
+    cfg.gridDim = dim3(2 * std::min(tiles, h->sm_count / 2));
     cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
     cfg.dynamicSmemBytes = C::SMEM + EpiCfg<EPI>::STG;
     cfg.stream = h->stream;
@@ -795,8 +790,21 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    JLM_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, EPI, 2>, Ah, Al, B.pair_hi, B.pair_lo, g));
-    return 0;
+    if (max_pairs < 0) {
+      JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
+      int n = 0;
+      // a partitioned or floor-swept device may not place two-CTA clusters: fall back to the single-CTA kernel
+      if (cudaOccupancyMaxActiveClusters(&n, k_tc_gemm<BN, EPI, 2>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+      }
+      max_pairs = n;
+    }
+    if (max_pairs > 0) {
+      cfg.gridDim = dim3(2 * std::min(tiles, std::min(h->sm_count / 2, max_pairs)));
+      JLM_CUDA(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, EPI, 2>, Ah, Al, B.pair_hi, B.pair_lo, g));
+      return 0;
+    }
   }
   using C = TileCfg<BN, 1>;
   static bool configured = false;

@@ -189,6 +189,68 @@ __global__ void k_add_base(BeamDev d, int64_t item0, int n_items, int W) {
 // displaces kept entries that are strictly worse, so equal scores keep the earlier ordinal.  The kept
 // list lives in registers, sorted, entry e at (lane e%32, register e/32), as (score, ordinal); the
 // (node, parent) of the survivors is recovered at the end by a binary search over the frame's nodes.
+// Serial selection: the W best (score, ordinal) pairs in a register-resident sorted list, entry e at
+// (lane e % 32, register e / 32); candidates are read 128 per iteration, a ballot picks the few that beat the
+// current W-th score and each is inserted with a shuffle shift.  Stable: a candidate only displaces entries
+// that are strictly worse.  One warp.
+template <int L, class ValueFn>
+__device__ __forceinline__ void serial_select(ValueFn value, int nc, int W, int lane, double (&es)[L], int (&ec)[L]) {
+  const unsigned FULL = 0xffffffffu;
+  const int kl = (W - 1) >> 5, klane = (W - 1) & 31;
+  double kth = INFINITY;
+
+  constexpr int U = 4;   // 32-candidate groups in flight per iteration
+  for (int base = 0; base < nc; base += 32 * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = base + u * 32 + lane;
+      v[u] = INFINITY;
+      if (c < nc) v[u] = value(c);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned m = __ballot_sync(FULL, v[u] < kth);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const double x = __shfl_sync(FULL, v[u], b);
+        if (!(x < kth)) continue;
+        const int xc = base + u * 32 + b;
+        int pos = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) pos += __popc(__ballot_sync(FULL, es[l] <= x));
+#pragma unroll
+        for (int l = L - 1; l >= 0; --l) {
+          const int idx = l * 32 + lane;
+          double us = __shfl_up_sync(FULL, es[l], 1);
+          int uc = __shfl_up_sync(FULL, ec[l], 1);
+          if (l > 0) {
+            const double cs = __shfl_sync(FULL, es[l > 0 ? l - 1 : 0], 31);
+            const int cc = __shfl_sync(FULL, ec[l > 0 ? l - 1 : 0], 31);
+            if (lane == 0) {
+              us = cs;
+              uc = cc;
+            }
+          }
+          if (idx > pos) {
+            es[l] = us;
+            ec[l] = uc;
+          } else if (idx == pos) {
+            es[l] = x;
+            ec[l] = xc;
+          }
+        }
+        double kv = es[0];
+#pragma unroll
+        for (int l = 1; l < L; ++l)
+          if (l == kl) kv = es[l];
+        kth = __shfl_sync(FULL, kv, klane);
+      }
+    }
+  }
+}
+
 constexpr int PRUNE_CAP = 96;   // survivors of the threshold filter a warp can rank in shared memory
 
 template <int L, bool DYN>
@@ -329,62 +391,7 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
     }
   }
 
-  if (!selected) {
-  const int kl = (W - 1) >> 5, klane = (W - 1) & 31;
-  double kth = INFINITY;
-
-  constexpr int U = 4;   // 32-candidate groups in flight per iteration
-  for (int base = 0; base < nc; base += 32 * U) {
-    double v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int c = base + u * 32 + lane;
-      v[u] = INFINITY;
-      if (c < nc) v[u] = value(c);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      unsigned m = __ballot_sync(FULL, v[u] < kth);
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const double x = __shfl_sync(FULL, v[u], b);
-        if (!(x < kth)) continue;
-        const int xc = base + u * 32 + b;
-        int pos = 0;
-#pragma unroll
-        for (int l = 0; l < L; ++l) pos += __popc(__ballot_sync(FULL, es[l] <= x));
-#pragma unroll
-        for (int l = L - 1; l >= 0; --l) {
-          const int idx = l * 32 + lane;
-          double us = __shfl_up_sync(FULL, es[l], 1);
-          int uc = __shfl_up_sync(FULL, ec[l], 1);
-          if (l > 0) {
-            const double cs = __shfl_sync(FULL, es[l > 0 ? l - 1 : 0], 31);
-            const int cc = __shfl_sync(FULL, ec[l > 0 ? l - 1 : 0], 31);
-            if (lane == 0) {
-              us = cs;
-              uc = cc;
-            }
-          }
-          if (idx > pos) {
-            es[l] = us;
-            ec[l] = uc;
-          } else if (idx == pos) {
-            es[l] = x;
-            ec[l] = xc;
-          }
-        }
-        double kv = es[0];
-#pragma unroll
-        for (int l = 1; l < L; ++l)
-          if (l == kl) kv = es[l];
-        kth = __shfl_sync(FULL, kv, klane);
-      }
-    }
-  }
-
-  }
+  if (!selected) serial_select<L>(value, nc, W, lane, es, ec);
 
   const int cnt = d.bc[fid];
   const int64_t s0 = d.slot0[fid];
@@ -406,6 +413,149 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
       d.slot_word[s0 + idx] = d.node_word[a];
       if (DYN) d.slot_cumy[s0 + idx] = d.slot_cumy[par] + d.cand_val[c];
     }
+  }
+}
+
+// Block-per-sentence form of the same selection (W <= 128): the four warps split the candidate range, so the one
+// long-tailed sentence that sets the kernel's duration (thousands of candidates) has four times the loads in
+// flight, and the grid has four times the warps of the warp-per-sentence kernel.  Steps as in k_prune: thread
+// minima -> tau (rank W-1 among the 128 minima) -> per-warp ordered compaction of the candidates <= tau (warp w owns
+// a contiguous quarter of the ordinals, so warp order is ordinal order) -> rank by counting under (score, ordinal)
+// -> kept list in shared memory -> slots.  A frame whose survivors overflow the buffers (mass ties) is finished by
+// warp 0 with the insertion list.
+constexpr int PB_CAP = 160;    // survivors per warp segment
+
+template <int L, bool DYN>
+__global__ void __launch_bounds__(128)
+k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
+  __shared__ double mins[128];
+  __shared__ double sv[4][PB_CAP];
+  __shared__ int sc[4][PB_CAP];
+  __shared__ int cnt_w[4];
+  __shared__ double tau_s;
+  __shared__ double ov[128];
+  __shared__ int oc[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned FULL = 0xffffffffu;
+  const int p = blockIdx.x;
+  const int fid = (int)d.fbase[p] + t;
+  const int lo = d.frame_lo[fid], hi = d.frame_hi[fid];
+  const int64_t c0 = d.frame_cand_lo[fid];
+  const int nc = d.frame_ncand[fid];
+  const double* val = d.cand_val + c0;
+  const int32_t* cpar = DYN ? d.cand_parent + c0 : nullptr;
+  auto value = [&](int c) -> double {
+    if (DYN) {
+      const int par = cpar[c];
+      return (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + val[c]);
+    }
+    return val[c];
+  };
+  // warp w owns ordinals [w*q, min(nc, (w+1)*q)), q a multiple of 32
+  const int q = ((nc + 127) / 128) * 32;
+  const int w_lo = warp * q, w_hi = min(nc, w_lo + q);
+  constexpr int UN = 8;
+  double tmin = INFINITY;
+  for (int base = w_lo; base < w_hi; base += 32 * UN) {
+    double v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int c = base + u * 32 + lane;
+      v[u] = c < w_hi ? value(c) : INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) tmin = fmin(tmin, v[u]);
+  }
+  mins[tid] = tmin;
+  __syncthreads();
+  {
+    int rk = 0;
+    for (int j = 0; j < 128; ++j) {
+      const double o = mins[j];
+      rk += (o < tmin || (o == tmin && j < tid)) ? 1 : 0;
+    }
+    if (rk == W - 1) tau_s = tmin;      // ranks are a permutation of 0..127 and W <= 128: exactly one writer
+  }
+  __syncthreads();
+  const double tau = tau_s;
+  int ns = 0;
+  for (int base = w_lo; base < w_hi; base += 32 * UN) {
+    double v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int c = base + u * 32 + lane;
+      v[u] = c < w_hi ? value(c) : INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int c = base + u * 32 + lane;
+      const bool keep = c < w_hi && v[u] <= tau;
+      const unsigned m = __ballot_sync(FULL, keep);
+      const int pos = ns + __popc(m & ((1u << lane) - 1u));
+      if (keep && pos < PB_CAP) {
+        sv[warp][pos] = v[u];
+        sc[warp][pos] = c;
+      }
+      ns += __popc(m);
+    }
+  }
+  if (lane == 0) cnt_w[warp] = ns;
+  __syncthreads();
+  const int n0 = cnt_w[0], n1 = cnt_w[1], n2 = cnt_w[2], n3 = cnt_w[3];
+  const bool overflow = n0 > PB_CAP || n1 > PB_CAP || n2 > PB_CAP || n3 > PB_CAP;     // block-uniform
+  if (overflow) {
+    if (warp == 0) {        // mass ties: warp 0 runs the insertion list over the whole frame
+      double es[L];
+      int ec[L];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        es[l] = INFINITY;
+        ec[l] = -1;
+      }
+      serial_select<L>(value, nc, W, lane, es, ec);
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        ov[l * 32 + lane] = es[l];
+        oc[l * 32 + lane] = ec[l];
+      }
+    }
+  }
+  const int total = overflow ? 0 : n0 + n1 + n2 + n3;
+  // survivor g of the concatenation (warp order = ordinal order): rank it against all survivors
+  for (int g = tid; g < total; g += 128) {
+    int gw = 0, gi = g;
+    if (gi >= n0) { gi -= n0; gw = 1; if (gi >= n1) { gi -= n1; gw = 2; if (gi >= n2) { gi -= n2; gw = 3; } } }
+    const double x = sv[gw][gi];
+    int r = 0, j = 0;
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) {
+      const int nw = cnt_w[ww];
+      for (int i = 0; i < nw; ++i, ++j) {
+        const double y = sv[ww][i];
+        r += (y < x || (y == x && j < g)) ? 1 : 0;
+      }
+    }
+    if (r < W) {
+      ov[r] = x;
+      oc[r] = sc[gw][gi];
+    }
+  }
+  __syncthreads();
+  const int cnt = d.bc[fid];
+  const int64_t s0 = d.slot0[fid];
+  if (tid < cnt) {
+    const int64_t c = c0 + oc[tid];
+    int a = lo, b = hi - 1;
+    while (a < b) {
+      const int mid = (a + b + 1) >> 1;
+      if (d.cand_pos[mid] <= c) a = mid; else b = mid - 1;
+    }
+    const int par = (int)(d.slot0[d.node_pfid[a]] + (c - d.cand_pos[a]));
+    d.slot_score[s0 + tid] = ov[tid];
+    d.slot_parent[s0 + tid] = par;
+    d.slot_node[s0 + tid] = a;
+    d.slot_word[s0 + tid] = d.node_word[a];
+    if (DYN) d.slot_cumy[s0 + tid] = d.slot_cumy[par] + d.cand_val[c];
   }
 }
 
@@ -992,7 +1142,18 @@ int32_t launch_prune(jlm_batch* b, int t) {
   const int L = ceil_div(b->W, 32);
   const int ul = b->use_lse ? 1 : 0;
   cudaStream_t st = b->h->stream;
-  if (L <= 1)
+  static const int block_mode = [] {
+    const char* e = getenv("JLM_PRUNE_BLOCK");
+    return e ? atoi(e) : 1;
+  }();
+  if (block_mode) {      // one CTA per sentence
+    if (L <= 1)
+      k_prune_block<1, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul);
+    else if (L <= 2)
+      k_prune_block<2, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul);
+    else
+      k_prune_block<4, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul);
+  } else if (L <= 1)
     k_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
   else if (L <= 2)
     k_prune<2, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);

@@ -276,16 +276,32 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
     const int te = threadIdx.x - 64;      // 0..ET-1
     int acc = 0;
     uint32_t acc_phase = 0;
+    // the tile's bias slice is fetched one tile ahead into registers: with short K (one or two k-blocks per
+    // tile) the epilogue is the critical path and must not start every tile with a global-load round trip
+    constexpr int BPT = (BN + ET - 1) / ET;
+    float bnext[BPT];
+    auto fetch_bias = [&](int tl) {
+      const int nb = tl / num_m_units;
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) {
+        const int c = te + i * ET;
+        const int n = nb * BN + c;
+        float v = (EPI == EPI_LSE) ? -INFINITY : 0.f;
+        if (c < BN && n < g.N) v = g.bias ? g.bias[n] : 0.f;
+        bnext[i] = v;
+      }
+    };
+    if (unit < num_tiles) fetch_bias(unit);
     for (int tile = unit; tile < num_tiles; tile += n_units) {
       const int m_blk = (tile % num_m_units) * CG + (int)rank, n_blk = tile / num_m_units;
       float* bs = bias_s + acc * BN;
-      for (int c = te; c < BN; c += ET) {
-        const int n = n_blk * BN + c;
-        float v = (EPI == EPI_LSE) ? -INFINITY : 0.f;
-        if (n < g.N) v = g.bias ? g.bias[n] : 0.f;
-        bs[c] = v;
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) {
+        const int c = te + i * ET;
+        if (c < BN) bs[c] = bnext[i];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      if (tile + n_units < num_tiles) fetch_bias(tile + n_units);
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < g.M;

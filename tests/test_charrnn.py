@@ -217,3 +217,38 @@ def test_gpu_eval_harness_runs_a_char_rnn_experiment(tmp_path):
         assert n == 12 and best + nbest + miss == 12
         logs.append(open(ev.log_path, encoding='utf-8').read().split('best_hit')[0])
     assert logs[0] == logs[1]                     # lock-step batch and per-pair decoding write the same log
+
+
+@pytest.mark.parametrize('name', sorted(CHAR_CASES))
+def test_mirror_char_lattice_matches_reference_on_cpu(name, tmp_path):
+    """CharRNNDecoder._build_lattice (host code, no device needed) against the lattices the reference class built:
+    display strings, first-character ids, per-reading de-duplication, '<unk>' fallback, order."""
+    import pickle
+    from jlm_b200 import config
+    from jlm_b200.decoder_charrnn import CharRNNDecoder
+    from jlm_b200.vocab import CharVocab
+    case, meta = _case(name)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    config.set_root(str(tmp_path))
+    dec = object.__new__(CharRNNDecoder)             # no LSTM_Model: only the host-side lattice code is exercised
+    dec.config = cfg
+    dec.full_lexicon, dec.full_reading_dict = lexicon, reading_dict
+    dec.lattice_vocab = None
+    dec._load_vocab()
+    assert isinstance(dec.vocab, CharVocab) and len(dec.w2i) == meta['n_chars']
+    for g in meta['decode']:
+        frames = dec._build_lattice(g['input'], vocab_select=case['decode_kwargs'].get('vocab_select', False))
+        assert {str(t): [[n[0], n[1], n[2]] for n in fr] for t, fr in enumerate(frames) if fr} == g['lattice']
+    # the 201-strings-per-reading cap (decoder.py:119): 260 homophones with distinct spellings
+    many = [('<eos>', 10)] + [('{}{}/ア/P'.format(chr(0x4E00 + k // 40), chr(0x4E00 + k % 40)), 5) for k in range(260)]
+    dec2 = object.__new__(CharRNNDecoder)
+    dec2.config = dict(cfg, vocab_size=len(many) + 1)
+    dec2.full_lexicon, dec2.full_reading_dict = many, {'ア': list(range(1, 261))}
+    dec2.lattice_vocab = None
+    pickle.dump(many, open(str(tmp_path / 'data' / 'lexicon.pkl'), 'wb'))
+    dec2._load_vocab()
+    fr = dec2._build_lattice('ア')
+    assert len(fr[1]) == 201
+    words, c2i = O.make_char_vocab(many, len(many) + 1)
+    assert [[n[0], n[1], n[2]] for n in fr[1]] == [[n[0], n[1], n[2]] for n in
+                                                  O.build_lattice_char('ア', words, c2i, many, {'ア': list(range(1, 261))})[1]]

@@ -252,3 +252,72 @@ def test_mirror_char_lattice_matches_reference_on_cpu(name, tmp_path):
     words, c2i = O.make_char_vocab(many, len(many) + 1)
     assert [[n[0], n[1], n[2]] for n in fr[1]] == [[n[0], n[1], n[2]] for n in
                                                   O.build_lattice_char('ア', words, c2i, many, {'ア': list(range(1, 261))})[1]]
+
+
+class _CpuModel(object):
+    """LSTM_Model surface over the numpy oracle: lets the decoder's HOST logic run without a device."""
+
+    def __init__(self, cfg, weights):
+        self.om = O.OracleModel(cfg, weights)
+        self.hidden_size = self.om.hidden_size
+
+    def predict_with_context(self, index, hidden, cell, vocab=None):
+        pred, y, h, c = self.om.predict(list(index), np.asarray(hidden), np.asarray(cell), vocab)
+        return (pred, y, 0.0, 0.0), h, c
+
+
+class _CpuPool(object):
+    """StatePool surface (step / nll / reset / capacity) over the numpy oracle."""
+
+    def __init__(self, model):
+        self.m, self.capacity = model, 1 << 30
+        self.reset()
+
+    def reset(self):
+        self.h, self.c, self.p = [], [], []
+        self.used = 0
+
+    def step(self, src, index):
+        H = self.m.hidden_size
+        hin = np.stack([self.h[s] if s >= 0 else np.zeros(H) for s in src])
+        cin = np.stack([self.c[s] if s >= 0 else np.zeros(H) for s in src])
+        (pred, _, _, _), h, c = self.m.predict_with_context([int(i) for i in index], hin, cin)
+        first = len(self.h)
+        for k in range(len(src)):
+            self.h.append(h[k]); self.c.append(c[k]); self.p.append(pred[k])
+        self.used = len(self.h)
+        return np.arange(first, first + len(src), dtype=np.int64)
+
+    def nll(self, slots, cols):
+        return np.array([-np.log(self.p[int(s)][int(c)]) for s, c in zip(slots, cols)])
+
+
+@pytest.mark.parametrize('name', sorted(CHAR_CASES))
+def test_mirror_char_decoder_host_logic_on_cpu(name, tmp_path):
+    """decode() (per-call shape) and the lock-step decode_batch() of jlm_b200.CharRNNDecoder with the LM replaced by
+    the numpy oracle: expansion order, string de-duplication, multi-step word evaluation, stable pruning and the
+    slot bookkeeping are host code and must reproduce the reference fixtures without a GPU."""
+    from jlm_b200 import config
+    from jlm_b200.decoder_charrnn import CharRNNDecoder
+    case, meta = _case(name)
+    cfg, weights, lexicon, reading_dict = _experiment(case, tmp_path)
+    config.set_root(str(tmp_path))
+    dec = object.__new__(CharRNNDecoder)
+    dec.config = cfg
+    dec.full_lexicon, dec.full_reading_dict = lexicon, reading_dict
+    dec.lattice_vocab = None
+    dec.perf_sen, dec.perf_log_lstm, dec.perf_log_softmax = 0, [], []
+    dec._load_vocab()
+    dec.model = _CpuModel(cfg, weights)
+    dec._pool = _CpuPool(dec.model)
+    kw = case['decode_kwargs']
+    sents = meta['sentences']
+    batch = dec.decode_batch(sents, **kw)
+    for sent, g, got_b in zip(sents, meta['decode'], batch):
+        got = dec.decode(sent, **kw)
+        for res in (got, got_b):
+            assert [ws for _, ws in res] == [ws for _, ws in g['nbest']]
+            np.testing.assert_allclose([s for s, _ in res], [s for s, _ in g['nbest']], rtol=0, atol=1e-9)
+        for t, gp in enumerate(g['pruned']):
+            assert dec._last_beams[t]['words'] == [[n[1] for n in p[1]] for p in gp]
+    assert dec.perf_sen == 2 * len(sents)

@@ -185,92 +185,105 @@ class CharRNNDecoder(Decoder):
         if pool is None or pool.capacity < need:
             self._pool = pool = StatePool(self.model, max(need, 1024))
         pool.reset()
+        # Per (sentence, frame) the kept paths are flat arrays: score, state slot, spelled text, and a back-pointer
+        # (start frame, rank there, display string) - word lists are only materialised for the final n-best.
         beams = [[] for _ in range(S)]
         Tmax = max(len(x) for x in inputs)
+        eos = w2i['<eos>']
         for t in range(Tmax + 1):
             act = [s for s in range(S) if len(inputs[s]) >= t]
-            C_ = {}
+            # ---- expansion: flat candidate arrays over all active sentences, sentence by sentence ----
+            off = [0]
             if t == 0:
-                for s in act:
-                    C_[s] = {'score': np.zeros(1), 'slot': np.array([-1], dtype=np.int64), 'words': [['<eos>']],
-                             'text': ['<eos>'], 'cur': [w2i['<eos>']], 'wlen': [1]}
+                n_act = len(act)
+                score = np.zeros(n_act)
+                slot = np.full(n_act, -1, dtype=np.int64)
+                cur = np.full(n_act, eos, dtype=np.int64)
+                wlen = np.ones(n_act, dtype=np.int64)
+                text = ['<eos>'] * n_act
+                disp = ['<eos>'] * n_act
+                bp_f = [-1] * n_act
+                bp_r = [0] * n_act
+                off = list(range(n_act + 1))
             else:
-                req_slot, req_col, owner = [], [], []
+                base_l, slot_l, cur_l, wlen_l, text, disp, bp_f, bp_r = [], [], [], [], [], [], [], []
                 for s in act:
-                    c = {'base': [], 'slot': [], 'words': [], 'text': [], 'cur': [], 'wlen': []}
                     seen = set()
-                    for (start, cid, disp) in lat[s][t]:
-                        par = beams[s][start]
-                        for r in range(len(par['score'])):
-                            spelled = par['text'][r] + disp
+                    frames_s = beams[s]
+                    for (start, cid, dsp) in lat[s][t]:
+                        par = frames_s[start]
+                        wl = self._word_length(dsp)
+                        ptext, pscore, pslot = par['text'], par['score'], par['slot']
+                        for r in range(len(ptext)):
+                            spelled = ptext[r] + dsp
                             if spelled in seen:                      # first spelling wins (decoder.py:293-297)
                                 continue
                             seen.add(spelled)
-                            c['base'].append(par['score'][r])
-                            c['slot'].append(int(par['slot'][r]))
-                            c['words'].append(par['words'][r] + [disp])
-                            c['text'].append(spelled)
-                            c['cur'].append(cid)
-                            c['wlen'].append(self._word_length(disp))
-                    req_slot += c['slot']
-                    req_col += c['cur']
-                    owner.append((s, len(c['slot'])))
-                    C_[s] = c
+                            text.append(spelled)
+                            base_l.append(pscore[r])
+                            slot_l.append(pslot[r])
+                            bp_r.append(r)
+                            bp_f.append(start)
+                            cur_l.append(cid)
+                            wlen_l.append(wl)
+                            disp.append(dsp)
+                    off.append(len(text))
+                slot = np.asarray(slot_l, dtype=np.int64)
+                cur = np.asarray(cur_l, dtype=np.int64)
+                wlen = np.asarray(wlen_l, dtype=np.int64)
                 t0 = time.time()
-                nll = pool.nll(req_slot, req_col)                    # Path.append_node (decoder.py:43-49)
+                score = np.asarray(base_l, dtype=np.float64) + pool.nll(slot, cur)   # Path.append_node (decoder.py:43-49)
                 self.perf_log_softmax.append(time.time() - t0)
-                o = 0
-                for s, n in owner:
-                    c = C_[s]
-                    c['score'] = np.asarray(c.pop('base'), dtype=np.float64) + nll[o:o + n]
-                    c['slot'] = np.asarray(c['slot'], dtype=np.int64)
-                    o += n
                 # remaining characters of multi-character words: one LM step per position, all sentences together
                 k = 1
-                while True:
-                    rows = [(s, a) for s in act for a in range(len(C_[s]['cur'])) if C_[s]['wlen'][a] > k]
-                    if not rows:
-                        break
+                active = np.nonzero(wlen > 1)[0]
+                while len(active):
                     t0 = time.time()
-                    new = pool.step([C_[s]['slot'][a] for s, a in rows], [C_[s]['cur'][a] for s, a in rows])
+                    new = pool.step(slot[active], cur[active])
                     self.perf_log_lstm.append(time.time() - t0)
-                    nxt = [w2i[C_[s]['words'][a][-1][k]] for s, a in rows]
+                    nxt = np.fromiter((w2i[disp[a][k]] for a in active), dtype=np.int64, count=len(active))
                     t0 = time.time()
-                    nll = pool.nll(new, nxt)
+                    score[active] += pool.nll(new, nxt)
                     self.perf_log_softmax.append(time.time() - t0)
-                    for i, (s, a) in enumerate(rows):
-                        c = C_[s]
-                        c['slot'][a] = new[i]
-                        c['cur'][a] = nxt[i]
-                        c['score'][a] += nll[i]
+                    slot[active] = new
+                    cur[active] = nxt
                     k += 1
-            # prune (stable sort, decoder.py:331-333), then seat the survivors with one LM step on their last character
-            keep = {}
-            src, idx = [], []
-            for s in act:
-                c = C_[s]
+                    active = active[wlen[active] > k]
+            # ---- prune per sentence (stable sort, decoder.py:331-333), then seat the survivors ----
+            keeps = []
+            for i in range(len(act)):
+                lo, hi = off[i], off[i + 1]
                 if beam_width is not None:
-                    kp = np.argsort(c['score'], kind='stable')[:beam_width]
+                    kp = np.argsort(score[lo:hi], kind='stable')[:beam_width] + lo
                 else:
-                    kp = np.arange(len(c['score']))          # no sort either (decoder.py:331-333)
-                keep[s] = kp
-                src += [int(c['slot'][a]) for a in kp]
-                idx += [c['cur'][a] for a in kp]
+                    kp = np.arange(lo, hi)                            # no sort either
+                keeps.append(kp)
+            allk = np.concatenate(keeps) if keeps else np.zeros(0, dtype=np.int64)
             t0 = time.time()
-            new = pool.step(src, idx)
+            new = pool.step(slot[allk], cur[allk])
             self.perf_log_lstm.append(time.time() - t0)
             o = 0
-            for s in act:
-                c, kp = C_[s], keep[s]
+            for i, s in enumerate(act):
+                kp = keeps[i]
                 n = len(kp)
-                beams[s].append({'score': c['score'][kp], 'slot': new[o:o + n], 'words': [c['words'][a] for a in kp],
-                                 'text': [c['text'][a] for a in kp]})
+                kl = kp.tolist()
+                beams[s].append({'score': score[kp], 'slot': new[o:o + n], 'text': [text[a] for a in kl],
+                                 'bp_f': [bp_f[a] for a in kl], 'bp_r': [bp_r[a] for a in kl],
+                                 'disp': [disp[a] for a in kl]})
                 o += n
         out = []
         for s in range(S):
-            last = beams[s][len(inputs[s])]
-            res = [(float(last['score'][r]), [w for w in last['words'][r] if w != '<eos>'])
-                   for r in range(len(last['score']))]
+            T = len(inputs[s])
+            last = beams[s][T]
+            res = []
+            for r in range(len(last['score'])):
+                words, f, k = [], T, r
+                while f >= 0:
+                    fr = beams[s][f]
+                    words.append(fr['disp'][k])
+                    f, k = fr['bp_f'][k], fr['bp_r'][k]
+                words.reverse()
+                res.append((float(last['score'][r]), [w for w in words if w != '<eos>']))
             out.append(res[:topN])
         self._last_batch_beams = beams
         self.perf_sen += S

@@ -245,3 +245,19 @@ def test_streaming_entry_points_reject_bad_arguments_without_a_device():
     assert lib.jlm_pool_create(None, 16, ctypes.byref(pool)) != 0 and b'jlm_pool_create' in lib.jlm_last_error()
     assert lib.jlm_pool_step(None, 1, None, None, None) != 0 and lib.jlm_pool_nll(None, 1, None, None, None) != 0
     assert lib.jlm_pool_reset(None) != 0 and lib.jlm_pool_destroy(None) == 0
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/jlm_b200.h is the FFI contract (cgo / JNI / ctypes bind against it): it must compile as C99 and as
+    C++ on its own, with no CUDA or torch types."""
+    import shutil
+    import subprocess
+    src = tmp_path / 'h.c'
+    src.write_text('#include "jlm_b200.h"\nint main(void) { return jlm_abi_version == 0; }\n')
+    inc = os.path.join(REPO, 'include')
+    hdr = open(os.path.join(inc, 'jlm_b200.h')).read()
+    assert re.findall(r'#include\s*[<"]([^>"]+)', hdr) == ['stdint.h']      # nothing but the C standard integer types
+    if shutil.which('gcc'):
+        subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-I', inc, str(src)], check=True)
+    if shutil.which('g++'):
+        subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-x', 'c++', '-I', inc, str(src)], check=True)

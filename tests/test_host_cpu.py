@@ -253,7 +253,7 @@ def test_public_header_is_plain_c(tmp_path):
     import shutil
     import subprocess
     src = tmp_path / 'h.c'
-    src.write_text('#include "jlm_b200.h"\nint main(void) { return jlm_abi_version == 0; }\n')
+    src.write_text('#include "jlm_b200.h"\nint main(void) { jlm_config c; (void)c; return (int)sizeof(jlm_nbest) == 0; }\n')
     inc = os.path.join(REPO, 'include')
     hdr = open(os.path.join(inc, 'jlm_b200.h')).read()
     assert re.findall(r'#include\s*[<"]([^>"]+)', hdr) == ['stdint.h']      # nothing but the C standard integer types

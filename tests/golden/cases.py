@@ -7,6 +7,7 @@ configs[1] and configs[2] (V=50000 H=512, standard tied / D-softmax*), two sente
 _SMALL = dict(vocab_size=1000, hidden_size=64, embed_size=32, n_sent=4, min_len=12, seed=0,
               model_probe={'index': [[1, 5, 17], [2, 900, 33]], 'vocab': [1, 3, 7, 250, 400, 650, 999]})
 _BEAM5 = dict(topN=10, beam_width=5)
+_UNSORTED = [650, 3, 999, 1, 400, 7, 250, 2, 651]
 
 
 def _c(base, **kw):
@@ -56,6 +57,21 @@ CASES = {
                           decode_kwargs=dict(topN=10, beam_width=20, vocab_select=True, samples=200,
                                              top_sampling=True),
                           model_probe={'index': [[1, 7], [40000, 12]], 'vocab': None}),
+    # --- BASELINE.json configs[4]: V=100000 H=1024 D-softmax*, the reference's default segments
+    # (train/train.py:16,30), beam 50 (two kept-path registers per lane in k_prune_block, H=1024 gate tiles) ---
+    'cfg5_dsoftmax_star': dict(vocab_size=100000, hidden_size=1024, embed_size=256, mode='dsoftmax_star',
+                               segments=[[256, 0, 4000], [128, 4000, 12000], [64, 12000, None]],
+                               n_sent=2, min_len=20, seed=0, decode_kwargs=dict(topN=10, beam_width=50),
+                               model_probe={'index': [[1, 7], [90000, 12]],
+                                            'vocab': [1, 2, 3999, 4000, 11999, 12000, 99999]}),
+    # --- vocab subsets given UNSORTED (decoder/model.py:152-158,168-179): segmented projections
+    # emit their columns segment-major while b2[vocab] keeps the caller's order; the tied softmax keeps list order ---
+    'small_tied_unsorted': _c(_SMALL, mode='tied', n_sent=1, decode_kwargs=_BEAM5,
+                              model_probe={'index': [[1, 5, 17], [2, 900, 33]], 'vocab': _UNSORTED}),
+    'small_dsoftmax_unsorted': _c(_SMALL, mode='dsoftmax', n_sent=1, decode_kwargs=_BEAM5,
+                                  model_probe={'index': [[1, 5, 17], [2, 900, 33]], 'vocab': _UNSORTED}),
+    'small_dsoftmax_star_unsorted': _c(_SMALL, mode='dsoftmax_star', n_sent=1, decode_kwargs=_BEAM5,
+                                       model_probe={'index': [[1, 5, 17], [2, 900, 33]], 'vocab': _UNSORTED}),
 }
 
 # --- char-RNN decoder (decoder/decoder.py:244-341): character LM over CharVocab, word lattice ---

@@ -24,7 +24,9 @@ STATIC_SMALL = ['small_tied', 'small_untied', 'small_dsoftmax', 'small_dsoftmax_
                 'small_dsoftmax_star_vs', 'small_dsoftmax_vs']
 DYN_SMALL = ['small_tied_dyn', 'small_tied_dyn_top', 'small_tied_dyn_rand', 'small_tied_selfnorm_dyn']
 MODEL_CASES = ['small_tied', 'small_untied', 'small_dsoftmax', 'small_dsoftmax_star', 'small_tied_selfnorm',
-               'cfg2_tied', 'cfg3_dsoftmax_star']
+               'cfg2_tied', 'cfg3_dsoftmax_star', 'cfg5_dsoftmax_star',
+               # quirk 3: unsorted vocab subsets (segment-major columns, list-order bias)
+               'small_tied_unsorted', 'small_dsoftmax_unsorted', 'small_dsoftmax_star_unsorted']
 
 _decoders = {}
 
@@ -110,7 +112,7 @@ def test_decode_exact_dynamic(name, tmp_path_factory):
     check_decode(name, EXACT, tmp_path_factory)
 
 
-@pytest.mark.parametrize('name', ['cfg2_tied', 'cfg3_dsoftmax_star', 'cfg4_tied_dyn'])
+@pytest.mark.parametrize('name', ['cfg2_tied', 'cfg3_dsoftmax_star', 'cfg4_tied_dyn', 'cfg5_dsoftmax_star'])
 def test_decode_exact_full_size(name, tmp_path_factory):
     check_decode(name, EXACT, tmp_path_factory)
 
@@ -199,7 +201,7 @@ def test_decode_tc_small(name, tmp_path_factory):
     check_decode(name, TC, tmp_path_factory)
 
 
-@pytest.mark.parametrize('name', ['cfg2_tied', 'cfg3_dsoftmax_star', 'cfg4_tied_dyn'])
+@pytest.mark.parametrize('name', ['cfg2_tied', 'cfg3_dsoftmax_star', 'cfg4_tied_dyn', 'cfg5_dsoftmax_star'])
 def test_decode_tc_full_size(name, tmp_path_factory):
     check_decode(name, TC, tmp_path_factory)
 

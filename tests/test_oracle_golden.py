@@ -67,7 +67,8 @@ def test_oracle_decode_matches_reference_full_size(name):
 
 
 @pytest.mark.parametrize('name', ['small_tied', 'small_untied', 'small_dsoftmax', 'small_dsoftmax_star',
-                                  'small_tied_selfnorm', 'cfg2_tied', 'cfg3_dsoftmax_star'])
+                                  'small_tied_selfnorm', 'cfg2_tied', 'cfg3_dsoftmax_star', 'cfg5_dsoftmax_star',
+                                  'small_tied_unsorted', 'small_dsoftmax_unsorted', 'small_dsoftmax_star_unsorted'])
 def test_oracle_model_matches_reference(name):
     """LSTM_Model.predict_with_context / project (model.py:106-198) incl. vocab subsets."""
     case, cfg, weights, lexicon, reading_dict, _ = build_case(name)

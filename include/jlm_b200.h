@@ -27,6 +27,12 @@ extern "C" {
 #define JLM_ABI_VERSION 1
 #define JLM_MAX_SEGMENTS 8
 #define JLM_MAX_BEAM 128
+/* beam_width value for the reference's beam_width=None (decoder.py:227-229 not executed): every candidate
+ * of a frame is kept, in enumeration order (node order, then parent rank); nothing is sorted.  The number of
+ * paths is exponential in the sentence length; a batch that would keep more than JLM_MAX_UNPRUNED_PATHS
+ * paths is refused with an error. */
+#define JLM_BEAM_UNLIMITED 0
+#define JLM_MAX_UNPRUNED_PATHS (4ll << 20)
 
 /* projection modes, decoder/model.py:141-193 */
 enum {
@@ -184,7 +190,7 @@ typedef struct {
 
 /* Decoder.decode / DynamicDecoder.decode (decoder.py:220-241, decoder_dynamic.py:177-194) for a
  * batch of independent sentences decoded in lock-step: plan + host->device copy + all frames +
- * device->host copy of the n-best lists.  beam_width <= JLM_MAX_BEAM. */
+ * device->host copy of the n-best lists.  1 <= beam_width <= JLM_MAX_BEAM, or JLM_BEAM_UNLIMITED. */
 int32_t jlm_decode_batch(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
                          int32_t mode, int32_t backend, jlm_nbest* out);
 
@@ -269,12 +275,15 @@ typedef struct jlm_batch_info_s {
   float ms_proj_gemm;
   int32_t n_gate_launches;
   int32_t n_proj_launches;
+  int32_t beam_width;     /* paths per frame the per-frame arrays of jlm_batch_get_beams are strided by: the
+                             beam_width of the call, or the widest frame for JLM_BEAM_UNLIMITED */
+  int32_t reserved0;
 } jlm_batch_info;
 int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info);
 int32_t jlm_batch_enable_timers(jlm_batch* b, int32_t on);
 
 /* Per-frame beams of one sentence after jlm_batch_run (+ synchronize): for frame t the entries
- * [t*beam_width, t*beam_width + count[t]).  parent_rank/parent_frame identify the back-pointer
+ * [t*beam_width, t*beam_width + count[t]) (beam_width as reported by jlm_batch_get_info).  parent_rank/parent_frame identify the back-pointer
  * (-1 for the <eos> path); node is the absolute node index; lse is the row's log-sum-exp.
  * h_out/c_out (nullable) receive the float64 state rows [ (T+1)*beam_width, H ]. */
 int32_t jlm_batch_get_beams(jlm_batch* b, int32_t sentence, int32_t* count, double* score,

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libjlm_b200.so')
 
 MAX_SEGMENTS = 8
 MAX_BEAM = 128
+BEAM_UNLIMITED = 0       # beam_width=None (decoder.py:227-229 skipped)
 PROJ_UNTIED, PROJ_TIED, PROJ_DSOFTMAX, PROJ_DSOFTMAX_STAR = 0, 1, 2, 3
 BACKEND_AUTO, BACKEND_EXACT, BACKEND_TC = 0, 1, 2
 DECODE_FULL, DECODE_STATIC_VOCAB, DECODE_DYNAMIC = 0, 1, 2
@@ -52,7 +53,8 @@ class BatchInfo(C.Structure):
                 ('n_steps', C.c_int32), ('backend', C.c_int32), ('kernel_launches', C.c_int64),
                 ('h2d_bytes', C.c_int64), ('d2h_bytes', C.c_int64), ('ms_lstm', C.c_float),
                 ('ms_softmax', C.c_float), ('ms_beam', C.c_float), ('ms_gate_gemm', C.c_float),
-                ('ms_proj_gemm', C.c_float), ('n_gate_launches', C.c_int32), ('n_proj_launches', C.c_int32)]
+                ('ms_proj_gemm', C.c_float), ('n_gate_launches', C.c_int32), ('n_proj_launches', C.c_int32),
+                ('beam_width', C.c_int32), ('reserved0', C.c_int32)]
 
 
 # every symbol include/jlm_b200.h declares: name -> (restype, argtypes)

@@ -559,6 +559,34 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
   }
 }
 
+// beam_width=None (decoder.py:227-229 not executed): every candidate of the frame becomes a kept path, in the
+// reference's enumeration order (node order, then parent rank) - nothing is sorted, nothing is dropped.
+template <bool DYN>
+__global__ void __launch_bounds__(128)
+k_keep_all(BeamDev d, int t, int tstride, int use_lse) {
+  const int p = blockIdx.x;
+  const int fid = (int)d.fbase[p] + t;
+  const int nc = d.frame_ncand[fid];
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int lo = d.frame_lo[fid], hi = d.frame_hi[fid];
+  const int64_t cg = d.frame_cand_lo[fid] + c;
+  int a = lo, b = hi - 1;
+  while (a < b) {
+    const int mid = (a + b + 1) >> 1;
+    if (d.cand_pos[mid] <= cg) a = mid; else b = mid - 1;
+  }
+  const int par = (int)(d.slot0[d.node_pfid[a]] + (cg - d.cand_pos[a]));
+  double v = d.cand_val[cg];
+  if (DYN) v = (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + v);
+  const int64_t s = d.slot0[fid] + c;
+  d.slot_score[s] = v;
+  d.slot_parent[s] = par;
+  d.slot_node[s] = a;
+  d.slot_word[s] = d.node_word[a];
+  if (DYN) d.slot_cumy[s] = d.slot_cumy[par] + d.cand_val[cg];
+}
+
 // decoder.py:237: walk the back-pointers of the best paths of the last frame.
 __global__ void k_backtrace(BeamDev d, int S, int topN, int max_len) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -783,9 +811,13 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
   nthreads = std::max(1, std::min(std::min(nthreads, 8), S / 128));
   std::vector<std::string> errs(nthreads);
   auto plo = [&](int k) { return (int)((int64_t)S * k / nthreads); };
-  const int W = b->W, V = h->V;
+  const int64_t W = b->unlimited ? ((int64_t)1 << 31) : (int64_t)b->W;
+  const int V = h->V;
+  // DECODE_STATIC_VOCAB: every lattice word must be in the sentence's (sorted) list - the reference's
+  // list.index raises ValueError otherwise (decoder.py:179-180)
+  const bool check_vocab = b->mode == JLM_DECODE_STATIC_VOCAB && lat->vocab_ptr && lat->vocab_ids;
   run_threads(nthreads, [&](int k) {
-    char msg[200];
+    char msg[320];
     for (int p = plo(k); p < plo(k + 1); ++p) {
       const int s = b->order[p];
       const int T = b->sent_T[p];
@@ -796,6 +828,10 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
         errs[k] = msg;
         return;
       }
+      // the list is sorted (decoder.py:141,151); a linear scan covers callers that pass it unsorted
+      const int32_t* v0 = check_vocab ? lat->vocab_ids + lat->vocab_ptr[s] : nullptr;
+      const int32_t* v1 = check_vocab ? lat->vocab_ids + lat->vocab_ptr[s + 1] : nullptr;
+      const bool v_sorted = check_vocab && std::is_sorted(v0, v1);
       int64_t cand = 0;
       for (int t = 0; t <= T; ++t) {
         if (fp[t + 1] < fp[t]) {
@@ -815,6 +851,14 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
             errs[k] = msg;
             return;
           }
+          if (check_vocab) {
+            const bool found = v_sorted ? std::binary_search(v0, v1, (int32_t)w) : std::find(v0, v1, (int32_t)w) != v1;
+            if (!found) {
+              snprintf(msg, sizeof(msg), "decode: %d is not in list (word of sentence %d missing from its vocabulary list)", w, s);
+              errs[k] = msg;
+              return;
+            }
+          }
           if (t == 0) continue;
           const int st = lat->node_start[n];
           if (st < 0 || st >= t) {
@@ -829,18 +873,38 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
           minpf = std::min(minpf, (int)(fb + st));
         }
         P.frame_minpf[fb + t] = minpf;
+        if (b->unlimited && ncand > JLM_MAX_UNPRUNED_PATHS) {
+          snprintf(msg, sizeof(msg), "decode: beam_width=None keeps more than %lld paths in frame %d of sentence %d: the "
+                   "unpruned search is exponential in the sentence length - pass a finite beam_width",
+                   (long long)JLM_MAX_UNPRUNED_PATHS, t, s);
+          errs[k] = msg;
+          return;
+        }
         if (ncand >= (int64_t)1 << 31) {
           errs[k] = "decode: too many candidates in one frame";
           return;
         }
         P.frame_ncand[fb + t] = (int32_t)ncand;
-        P.bc[fb + t] = t == 0 ? 1 : (int32_t)std::min<int64_t>(W, ncand);
+        P.bc[fb + t] = t == 0 ? 1 : (int32_t)std::min<int64_t>(W, ncand);      // unlimited: every candidate is kept
         cand += ncand;
       }
       P.sent_cand[p + 1] = cand;
     }
   });
   for (auto& e : errs) JLM_REQUIRE(e.empty(), "%s", e.c_str());
+  if (b->unlimited) {
+    // beam_width=None (decoder.py:227-229 skipped): nothing is sorted or pruned, paths multiply frame by frame
+    int64_t kept = 0;
+    int widest = 1;
+    for (int32_t c : P.bc) {
+      kept += c;
+      widest = std::max(widest, (int)c);
+    }
+    JLM_REQUIRE(kept <= JLM_MAX_UNPRUNED_PATHS,
+                "decode: beam_width=None keeps %lld paths for this batch (limit %lld): the unpruned search is exponential in "
+                "the sentence length - pass a finite beam_width", (long long)kept, (long long)JLM_MAX_UNPRUNED_PATHS);
+    b->W = widest;
+  }
   for (int p = 0; p < S; ++p) P.sent_cand[p + 1] += P.sent_cand[p];
   const int64_t n_cand_total = P.sent_cand[S];
   b->bc = P.bc;
@@ -1142,6 +1206,12 @@ int32_t launch_prune(jlm_batch* b, int t) {
   const int L = ceil_div(b->W, 32);
   const int ul = b->use_lse ? 1 : 0;
   cudaStream_t st = b->h->stream;
+  if (b->unlimited) {
+    k_keep_all<DYN><<<dim3(sp.nact, ceil_div(b->W, 128)), 128, 0, st>>>(b->d, t, b->Tmax + 1, ul);
+    JLM_CUDA(cudaGetLastError());
+    b->launches += 1;
+    return 0;
+  }
   static const int block_mode = [] {
     const char* e = getenv("JLM_PRUNE_BLOCK");
     return e ? atoi(e) : 1;
@@ -1177,16 +1247,19 @@ void beam_free_plan_scratch(jlm_handle* h) {
 extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
                                     int32_t mode, int32_t backend, jlm_batch** out) {
   JLM_REQUIRE(h && lat && out, "jlm_batch_upload: null argument");
-  JLM_REQUIRE(beam_width >= 1 && beam_width <= JLM_MAX_BEAM, "jlm_batch_upload: beam_width %d not in [1,%d]", beam_width,
-              JLM_MAX_BEAM);
+  JLM_REQUIRE(beam_width == JLM_BEAM_UNLIMITED || (beam_width >= 1 && beam_width <= JLM_MAX_BEAM),
+              "jlm_batch_upload: beam_width %d not in [1,%d] (or JLM_BEAM_UNLIMITED)", beam_width, JLM_MAX_BEAM);
   JLM_REQUIRE(top_n >= 1, "jlm_batch_upload: top_n must be >= 1");
   JLM_REQUIRE(mode >= 0 && mode <= 2, "jlm_batch_upload: bad mode %d", mode);
+  JLM_REQUIRE(backend == JLM_BACKEND_AUTO || backend == JLM_BACKEND_EXACT || backend == JLM_BACKEND_TC,
+              "jlm_batch_upload: bad backend %d", backend);
   JLM_CUDA(cudaSetDevice(h->device));
   *out = nullptr;
   jlm_batch* b = new jlm_batch();
   b->h = h;
-  b->W = beam_width;
-  b->topN = std::min(top_n, beam_width);
+  b->unlimited = beam_width == JLM_BEAM_UNLIMITED;
+  b->W = beam_width;      // unlimited: set by build_plan to the widest frame
+  b->topN = b->unlimited ? top_n : std::min(top_n, beam_width);
   b->mode = mode;
   b->dynamic = mode == JLM_DECODE_DYNAMIC;
   b->use_lse = h->cfg.self_norm == 0;
@@ -1207,7 +1280,6 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
   }
   const auto t_1 = now();
   if (backend == JLM_BACKEND_AUTO) backend = (b->max_rows_step >= 512) ? JLM_BACKEND_TC : JLM_BACKEND_EXACT;
-  JLM_REQUIRE(backend == JLM_BACKEND_EXACT || backend == JLM_BACKEND_TC, "jlm_batch_upload: bad backend %d", backend);
   b->backend = backend;
   int32_t rc = 0;
   Arena a;
@@ -1516,6 +1588,7 @@ extern "C" int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info) {
   info->n_steps = b->n_steps;
   info->backend = b->backend;
   info->kernel_launches = b->launches;
+  info->beam_width = b->W;
   info->h2d_bytes = b->h2d_bytes;
   info->d2h_bytes = b->d2h_bytes;
   info->ms_lstm = b->ms_lstm;

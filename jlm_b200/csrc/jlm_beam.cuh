@@ -80,6 +80,7 @@ struct jlm_batch {
   int S = 0, W = 0, topN = 0, mode = 0, backend = 0, Tmax = 0, n_steps = 0;
   bool use_lse = true;
   bool dynamic = false;
+  bool unlimited = false;        // beam_width=None: no sort, no prune (W = widest frame of the plan)
   std::vector<int> order;        // sorted position -> caller's sentence index
   std::vector<int> sent_T;       // by sorted position
   std::vector<int64_t> fbase;

@@ -855,11 +855,24 @@ struct TcWeights {
 
 constexpr int GATE_BN = 256;
 
+static void free_tc_weights(TcWeights* w);
+static int32_t tc_build_weights(jlm_handle* h, TcWeights* w);
+
+// The weights are built into a local object and published to the handle only when every upload succeeded: a
+// failed upload (e.g. out of memory at a large V) must not leave a half-initialised h->tc behind.
 int32_t tc_prepare_weights(jlm_handle* h) {
   if (h->tc) return 0;
   JLM_CUDA(cudaSetDevice(h->device));
   TcWeights* w = new TcWeights();
+  if (tc_build_weights(h, w)) {
+    free_tc_weights(w);
+    return 1;
+  }
   h->tc = w;
+  return 0;
+}
+
+static int32_t tc_build_weights(jlm_handle* h, TcWeights* w) {
   const int H = h->H, Hp = h->Hp, Kg = h->Kg, V = h->V;
   const int UPT = GATE_BN / 4;
   // pull the exact-layout weights back from the device (they are the single source of truth)
@@ -915,15 +928,18 @@ int32_t tc_prepare_weights(jlm_handle* h) {
   return 0;
 }
 
-void tc_free_weights(jlm_handle* h) {
-  if (!h->tc) return;
-  TcWeights* w = h->tc;
+static void free_tc_weights(TcWeights* w) {
   free_operand(&w->Wg);
   free_operand(&w->P1);
   free_operand(&w->Emb);
   for (auto& s : w->seg) free_operand(&s);
   cudaFree(w->bg_perm);
   delete w;
+}
+
+void tc_free_weights(jlm_handle* h) {
+  if (!h->tc) return;
+  free_tc_weights(h->tc);
   h->tc = nullptr;
 }
 

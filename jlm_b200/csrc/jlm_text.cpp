@@ -49,7 +49,7 @@ extern "C" int32_t jlm_decode_texts_submit(jlm_handle* h, const jlm_lexicon* lex
     return 1;
   }
   *out_job = nullptr;
-  const int32_t top = std::max(1, std::min(top_n, beam_width));
+  const int32_t top = beam_width == JLM_BEAM_UNLIMITED ? std::max(1, top_n) : std::max(1, std::min(top_n, beam_width));
   // Chunk boundaries.  Measured on B200 (1024 sentences, cfg 2): equal splits cost more device time
   // (smaller GEMMs, per-frame launch overheads) than the host work they hide (1.15 M chars/s with 1 chunk,
   // 1.11 M with 2, 0.74 M with 8), and a small head chunk that gets the device busy while the host prepares

@@ -78,11 +78,22 @@ class Decoder(object):
                         raise ValueError('{} is not in list'.format(n[1]))
         return lattice.PackedLattices(all_frames, vocab_lists=vocab_state), _lib.DECODE_STATIC_VOCAB
 
+    @staticmethod
+    def _beam_args(topN, beam_width):
+        """(beam_width, top) for the C ABI.  beam_width=None is the reference's unpruned search (decoder.py:227-229
+        skipped): every candidate is kept in enumeration order, nothing is sorted; the library refuses batches
+        whose path count explodes (JLM_MAX_UNPRUNED_PATHS)."""
+        if beam_width is None:
+            return _lib.BEAM_UNLIMITED, max(1, int(topN))
+        beam_width = int(beam_width)
+        if beam_width < 1:
+            # frame[i][:0] is empty in the reference, the next frame has nothing to extend and frame 0 is lost
+            raise ValueError('beam_width must be >= 1 or None')
+        return beam_width, max(1, min(int(topN), beam_width))
+
     def _run(self, packed, mode, topN, beam_width, backend, timers):
         lib, h = self._lib, self.model._handle
-        if beam_width is None:
-            beam_width = _lib.MAX_BEAM       # decoder.py:226: no pruning; bounded by the engine's list size
-        top = max(1, min(int(topN), int(beam_width)))
+        beam_width, top = self._beam_args(topN, beam_width)
         lb = packed.c_struct()
         batch = C.c_void_p()
         _lib.check(lib.jlm_batch_upload(h, C.byref(lb), int(beam_width), top, mode, backend, C.byref(batch)))
@@ -108,7 +119,7 @@ class Decoder(object):
             self.last_info = info
             self._last_batch_trace = None
             if getattr(self, '_want_trace', False):
-                self._last_batch_trace = self._collect_trace(batch, packed, int(beam_width))
+                self._last_batch_trace = self._collect_trace(batch, packed, int(info.beam_width))
         finally:
             lib.jlm_batch_destroy(batch)
         out = []
@@ -124,9 +135,7 @@ class Decoder(object):
         """jlm_decode_texts_submit: lattice build, plan, H2D and every frame enqueued; returns a pending job
         (dict) without waiting for the device."""
         lib, h = self._lib, self.model._handle
-        if beam_width is None:
-            beam_width = _lib.MAX_BEAM
-        top = max(1, min(int(topN), int(beam_width)))
+        beam_width, top = self._beam_args(topN, beam_width)
         nlex = self._native()
         S = len(texts)
         lens = np.fromiter((len(t) for t in texts), dtype=np.int64, count=S)
@@ -277,7 +286,9 @@ class Decoder(object):
         The lattices are built by the native builder (jlm_lattice_build) unless native_lattice=False or a
         vocabulary left by an earlier decode() call has to be honoured (quirk 6)."""
         inputs = list(inputs)
-        if native_lattice and inputs and (vocab_select or not self.lattice_vocab):
+        if not inputs:
+            return []
+        if native_lattice and (vocab_select or not self.lattice_vocab):
             mode = _lib.DECODE_STATIC_VOCAB if vocab_select else _lib.DECODE_FULL
             extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling) if vocab_select else None
             if not getattr(self, '_want_trace', False) and not vocab_select:

@@ -59,7 +59,9 @@ class DynamicDecoder(Decoder):
     def decode_batch(self, inputs, topN=10, beam_width=10, vocab_select=True, samples=0, top_sampling=False,
                      random_sampling=False, backend=_lib.BACKEND_AUTO, native_lattice=True):
         inputs = list(inputs)
-        if native_lattice and inputs and vocab_select:
+        if not inputs:
+            return []
+        if native_lattice and vocab_select:
             extra = self._sample_ids(len(inputs), samples, top_sampling, random_sampling)
             if not getattr(self, '_want_trace', False):
                 out = self._run_texts(inputs, _lib.DECODE_DYNAMIC, extra, topN, beam_width, backend)

@@ -99,7 +99,9 @@ def check_decode(name, backend, tmp_path_factory):
                 np.testing.assert_allclose(fr['h'][:, ::hs], arr[key + '_h'], rtol=0, atol=tol)
                 np.testing.assert_allclose(fr['c'][:, ::hs], arr[key + '_c'], rtol=0, atol=tol)
             if not case.get('self_norm') and not dyn:
-                np.testing.assert_allclose(fr['lse'], arr[key + '_lse'], rtol=0, atol=tol)
+                # LSE values reach ~20 at V=100k: the float64 back end agrees with the reference (which rounds the
+                # embedding half of the gate input to float32) to ~1e-7 relative
+                np.testing.assert_allclose(fr['lse'], arr[key + '_lse'], rtol=2e-7, atol=tol)
 
 
 @pytest.mark.parametrize('name', STATIC_SMALL)
@@ -435,3 +437,52 @@ def test_odd_shapes_both_backends_match_oracle(mode, tmp_path_factory):
         assert same == len(sents) if backend == EXACT else same >= len(sents) - 2, (backend, same)
         for g, w in zip(got, want):
             np.testing.assert_allclose(sorted(s for s, _ in g), sorted(s for s, _ in w), rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize('dyn', [False, True])
+def test_beam_width_none_is_the_unpruned_unsorted_search(dyn, tmp_path_factory):
+    """beam_width=None (decoder.py:227-229 skipped): every candidate is kept in enumeration order, the result is
+    the first topN paths of the last frame UNSORTED; the oracle follows the same lines.  Short inputs only - the
+    path count is exponential; an input whose count explodes must be refused with a clear error."""
+    from oracle import jlm_oracle as O
+    name = 'small_tied_dyn_top' if dyn else 'small_tied'
+    dec, case, sentences = get_decoder(name, tmp_path_factory)
+    _, cfg, weights, lexicon, reading_dict, _ = build_case(name)
+    ora = O.OracleDecoder(cfg, weights, lexicon, reading_dict, dynamic=dyn)
+    kw = dict(case['decode_kwargs'])
+    kw.update(topN=50, beam_width=None)
+    texts = [s[:6] for s in sentences] + [sentences[0][:1], '']
+    for backend, tol in ((EXACT, 2e-5), (TC, 1e-3)):
+        for text in texts:
+            want = ora.decode(text, **kw)
+            got = dec.decode(text, backend=backend, **kw)
+            assert [w for _, w in got] == [w for _, w in want], (backend, text)
+            np.testing.assert_allclose([s for s, _ in got], [s for s, _ in want], rtol=0, atol=tol)
+        batch = dec.decode_batch(texts, backend=backend, **kw)
+        for text, got in zip(texts, batch):
+            want = ora.decode(text, **kw)
+            assert [w for _, w in got] == [w for _, w in want], (backend, text)
+    unsorted_seen = any(sc != sorted(sc) for sc in ([s for s, _ in ora.decode(t, **kw)] for t in texts))
+    assert unsorted_seen, 'the inputs should exercise the no-sort behaviour'
+    with pytest.raises(RuntimeError, match='beam_width=None keeps'):
+        dec.decode(sentences[0] * 3, backend=EXACT, **kw)
+    with pytest.raises(ValueError):
+        dec.decode(sentences[0], beam_width=0)
+
+
+def test_static_vocab_word_missing_from_list_is_refused(tmp_path_factory):
+    """C ABI check (not only the Python wrapper): in DECODE_STATIC_VOCAB every lattice word must be in the
+    sentence's list - the reference's list.index raises ValueError (decoder.py:179-180)."""
+    import ctypes as C
+    from jlm_b200 import _lib, lattice
+    dec, case, sentences = get_decoder('small_tied_vs', tmp_path_factory)
+    frames = dec._builder.build(sentences[0])
+    words = sorted({n[1] for fr in frames for n in fr})
+    packed = lattice.PackedLattices([frames], vocab_lists=[words[:-1]])      # drop one needed word
+    lb = packed.c_struct()
+    batch = C.c_void_p()
+    rc = dec._lib.jlm_batch_upload(dec.model._handle, C.byref(lb), 5, 5, _lib.DECODE_STATIC_VOCAB, EXACT, C.byref(batch))
+    assert rc != 0 and b'is not in list' in dec._lib.jlm_last_error()
+    rc = dec._lib.jlm_batch_upload(dec.model._handle, C.byref(lb), 5, 5, _lib.DECODE_STATIC_VOCAB, 7, C.byref(batch))
+    assert rc != 0 and b'bad backend' in dec._lib.jlm_last_error()
+    assert dec.decode_batch([]) == []

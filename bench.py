@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py - kana chars/sec decoded (BASELINE.json metric) on the configuration the metric is quoted on:
-configs[1] = V=50000 H=512 embed=256, standard (tied) softmax, beam=10, 1 GPU.
+"""bench.py - kana chars/sec decoded (BASELINE.json metric).
 
-A "step" is one pass of the hot path over one batch of synthetic sentences: lattice (CSR, already
-built on the host) -> n-best lists, S sentences decoded in lock-step per GPU.  Independent
-sentences are partitioned across ranks (weak scaling: S per GPU), no collective on the data path.
+Headline = configs[1] (cfg2): V=50000 H=512 embed=256, standard (tied) softmax, beam=10, 1 GPU; the other
+BASELINE configs (cfg3 D-softmax*, cfg4 DynamicDecoder, cfg5 V=100k H=1024 beam 50) ride along as short runs in
+the `workloads` array of the same JSON line, each with its own value / e2e / roofline / parity counts.
+
+A "step" is one pass of the hot path over one batch of synthetic sentences: S sentences decoded in lock-step
+per GPU.  Independent sentences are partitioned across ranks, no collective on the data path:
+  weak scaling   (`value`, `e2e`)  : S sentences per GPU, private to the rank
+  strong scaling (`strong`, cfg4/5): ONE fixed set of S sentences through jlm_b200.shard.decode_sharded
+                                     (length-balanced partition, decode, packed NCCL all_gather of the n-best)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--sentences S] [--impl ours|reference]
+                    [--workload cfg2] [--extra cfg3,cfg4,cfg5|none] [--scaling weak|strong]
 
 Prints ONE JSON line (rank 0).  Keys follow the driver contract:
-  value      chars/s, device-resident inputs, CUDA-event time, max over ranks
-  e2e        chars/s through the C-ABI call jlm_decode_batch with HOST buffers (H2D + D2H inside)
-  roofline   the dominant kernel (output-projection GEMM + online-LSE epilogue): algorithmic FLOP/s
-             over its CUDA-event duration vs the measured bf16 peak; `gate` holds the same for the
-             LSTM gate GEMM the north star names
+  value      chars/s, lattices resident in HBM, CUDA-event time around run + n-best fetch (near-tie guard work
+             included), max over ranks
+  e2e        chars/s through jlm_decode_texts_submit/_collect with HOST buffers (H2D + D2H inside)
+  roofline   the dominant kernel (output-projection GEMM + online-LSE epilogue): algorithmic FLOP/s over its
+             CUDA-event duration vs the measured bf16 peak; `gate` holds the same for the LSTM gate GEMM
+  guard      near-tie guard statistics: flagged_fraction, pairs re-scored, sentences re-decoded in float64
   cpu_baseline  the CPU oracle (numpy port of the reference) on a bounded sample, same host
 """
 import argparse
@@ -52,6 +59,8 @@ WORKLOADS = {
                  V=100000, H=1024, E=256, mode='dsoftmax_star',
                  segments=[[256, 0, 4000], [128, 4000, 12000], [64, 12000, None]], beam=50, topn=10, dynamic=False),
 }
+CPU_NOTE = ('numpy port of the reference (oracle/jlm_oracle.py); measured equal to /root/reference on the cfg2 workload '
+            '(18.7 vs 18.9 chars/s on 8 vCPU, same top-1) - the Python reference itself cannot travel to the GPU box')
 
 
 def flops_per_row(wl):
@@ -128,12 +137,12 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def stop(self, t_lo, t_hi):
-        """Summary of the samples taken inside [t_lo, t_hi] (the GPU is under load for all of it)."""
+    def stop(self, windows):
+        """Summary of the samples taken inside the (t_lo, t_hi) windows (the GPU is under load for all of them)."""
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        rows = [r for t, r in self.rows if t_lo <= t <= t_hi]
+        rows = [r for t, r in self.rows if any(lo <= t <= hi for lo, hi in windows)]
         sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -144,87 +153,108 @@ class ClockSampler(threading.Thread):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (numpy oracle port - the Python reference
-    itself cannot travel to the GPU box) on the host cores, bounded sample of the same workload."""
+    itself cannot travel to the GPU box) on the host cores, bounded sample of the same workload.
+    Every step decodes a different slice of a pool of >= 32 sentences."""
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    TOPN, BEAM = wl['topn'], wl['beam']
-    WORKLOAD = wl['desc']
     root = tempfile.mkdtemp(prefix='jlm_bench_ref_')
-    n = max(1, args.ref_sentences)
-    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, wl, n, seed=100)
+    per_step = max(1, args.ref_sentences)
+    pool = max(32, per_step * min(args.steps, 8))
+    cfg, weights, lexicon, reading_dict, sents = make_inputs(root, wl, pool, seed=100)
     prepare, run = oracle_decoder(wl, cfg, weights, lexicon, reading_dict)
     states = [prepare(s) for s in sents]
-    chars = sum(len(s) for s in sents)
 
-    def step():
-        for st in states:
-            run(st)
+    def step(i):
+        lo = (i * per_step) % pool
+        idx = [(lo + k) % pool for k in range(per_step)]
+        for j in idx:
+            run(states[j])
+        return sum(len(sents[j]) for j in idx), idx
 
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        step()
+    for i in range(args.warmup if args.warmup < 2 else 1):
+        step(i)
+    chars, seen = 0, set()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        c, idx = step(i)
+        chars += c
+        seen.update(idx)
     dt = time.perf_counter() - t0
-    val = chars * args.steps / dt
-    sample = '%d sentences (%d chars) per step, lattice->n-best (decode minus _build_lattice)' % (n, chars)
+    val = chars / dt
+    sample = ('%d sentences per step, a different slice of a %d-sentence pool each step (%d distinct sentences, %d chars timed), '
+              'lattice->n-best (decode minus _build_lattice)' % (per_step, pool, len(seen), chars))
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'chars/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'sentences_per_step': n},
-            'cpu_baseline': {'value': val, 'unit': 'chars/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+            'config': {'workload': wl['desc'], 'sentences_per_step': per_step, 'distinct_sentences_timed': len(seen)},
+            'cpu_baseline': {'value': val, 'unit': 'chars/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample,
+                             'note': CPU_NOTE},
             'e2e': {'value': val, 'unit': 'chars/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'note': CPU_NOTE, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--sentences', type=int, default=1024, help='sentences per GPU per step (lock-step batch)')
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--ref-sentences', type=int, default=8)
-    ap.add_argument('--cpu-baseline-sentences', type=int, default=32)
-    ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
-    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
-    ap.add_argument('--chunks', type=int, default=0, help='e2e arm: pipeline chunks of jlm_decode_texts (0 = automatic)')
-    ap.add_argument('--e2e-depth', type=int, default=2, help='e2e arm: batches in flight through submit/collect')
-    ap.add_argument('--profile', action='store_true', help='1 warm-up + K plain steps only (for ncu); prints no JSON')
-    args = ap.parse_args()
+class Env(object):
+    """Process-level state shared by the workloads of one bench invocation."""
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if args.impl == 'reference':
-        run_reference(args, rank, world)
-        return
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py needs a CUDA device: libjlm_b200 has no CPU fallback')
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+            # ranks share the host: lattice / plan threads are split between them (shard.host_threads_per_rank)
+            from jlm_b200 import shard
+            os.environ.setdefault('JLM_HOST_THREADS', str(min(8, shard.host_threads_per_rank(self.world))))
+        from jlm_b200 import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.stream = torch.cuda.current_stream()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
+        self.sampler = ClockSampler(self.local) if self.rank == 0 else None
+        if self.sampler:
+            self.sampler.start()
+        self.windows = []
 
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device: libjlm_b200 has no CPU fallback')
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
+    def reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+
+def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
+    """One workload on this rank's GPU: device-resident arm, roofline pass, e2e arm, (strong-scaling arm), CPU leg."""
     import jlm_b200
-    from jlm_b200 import _lib, config, lattice
-    lib = _lib.load()
-    wl = WORKLOADS[args.workload]
+    from jlm_b200 import config, lattice, shard
+    args, lib, _lib, torch = env.args, env.lib, env._lib, env.torch
+    rank, world, local = env.rank, env.world, env.local
+    wl = WORKLOADS[name]
     TOPN, BEAM, WORKLOAD = wl['topn'], wl['beam'], wl['desc']
     MODE = _lib.DECODE_DYNAMIC if wl['dynamic'] else _lib.DECODE_FULL
-    root = tempfile.mkdtemp(prefix='jlm_bench_r%d_' % rank)
+    root = tempfile.mkdtemp(prefix='jlm_bench_%s_r%d_' % (name, rank))
     cfg, weights, lexicon, reading_dict, sents = make_inputs(root, wl, args.sentences, seed=100 + rank)
     config.set_root(root)
     dec = (jlm_b200.DynamicDecoder if wl['dynamic'] else jlm_b200.Decoder)(1, device=local)
     extra = np.tile(np.arange(wl['samples'], dtype=np.int32), (len(sents), 1)) if wl['dynamic'] else None
     n_extra = wl['samples'] if wl['dynamic'] else 0
     hdl = dec.model._handle
-    stream = torch.cuda.current_stream()
+    stream = env.stream
     _lib.check(lib.jlm_set_stream(hdl, C.c_void_p(stream.cuda_stream)))
     nlex = dec._native()
     t_lat = time.perf_counter()
@@ -243,69 +273,55 @@ def main():
     nb.scores, nb.n_paths = _lib.ptr(scores, C.c_double), _lib.ptr(n_paths, C.c_int32)
     nb.path_len, nb.path_nodes = _lib.ptr(path_len, C.c_int32), _lib.ptr(path_nodes, C.c_int32)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---------------- device-resident arm: lattices uploaded once, K timed runs ----------------
+    # ---------------- device-resident arm: lattices uploaded once, K timed (run + fetch) ----------------
     batch = C.c_void_p()
     _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(batch)))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
     if args.profile:
-        for _ in range(1 + args.steps):
+        for _ in range(1 + steps):
             _lib.check(lib.jlm_batch_run(batch))
         torch.cuda.synchronize()
         _lib.check(lib.jlm_batch_destroy(batch))
-        return
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(args.warmup, 3)):
+        return None
+    info = _lib.BatchInfo()
+    for _ in range(max(warmup, 3)):
         _lib.check(lib.jlm_batch_run(batch))
-    barrier()
+        _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
+    env.barrier()
     t_load0 = time.perf_counter()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    env.barrier()
     wall0 = time.perf_counter()
+    flagged = pairs = rerun = 0
     for a, b in ev:
-        flush.fill_(1)                     # evict weights / state from L2 between timed steps (not timed)
+        env.flush.fill_(1)                 # evict weights / state from L2 between timed steps (not timed)
         a.record(stream)
         _lib.check(lib.jlm_batch_run(batch))
+        # the n-best fetch belongs to the step: it is where the near-tie guard re-scores / re-decodes in float64
+        _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
         b.record(stream)
-    barrier()
+        _lib.check(lib.jlm_batch_get_info(batch, C.byref(info)))
+        flagged += info.n_guard_flagged
+        pairs += info.n_guard_pairs
+        rerun += info.n_guard_rerun
+    env.barrier()
     wall = time.perf_counter() - wall0
-    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
-    ms_dev = max_over_ranks(ms_dev)
-    total_chars = sum_over_ranks(float(chars))
-    value = total_chars * args.steps / (ms_dev * 1e-3)
-    info = _lib.BatchInfo()
-    _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
-    _lib.check(lib.jlm_batch_get_info(batch, C.byref(info)))
-    launches = int(info.kernel_launches) * args.steps
+    ms_dev = env.reduce(sum(a.elapsed_time(b) for a, b in ev), 'MAX')
+    total_chars = env.reduce(float(chars), 'SUM')
+    value = total_chars * steps / (ms_dev * 1e-3)
+    launches = int(info.kernel_launches) * steps
     rows_stepped = int(info.n_slots)
+    guard = {'eps': float(info.guard_eps), 'flagged_fraction': flagged / float(steps * S),
+             'flagged_sentences_per_step': flagged / float(steps), 'pairs_rescored_f64_per_step': pairs / float(steps),
+             'sentences_redecoded_f64_per_step': rerun / float(steps), 'min_gap': float(info.guard_min_gap),
+             'note': 'rank decisions resting on a score gap < eps are re-scored in float64 (jlm_pool); contradicted ones '
+                     're-decode their sentence on the float64 back end; all inside the timed region'}
 
     # ---------------- roofline pass: same K steps with per-kernel CUDA events ----------------
     _lib.check(lib.jlm_batch_enable_timers(batch, 1))
     gate_ms = proj_ms = 0.0
     n_gate = n_proj = 0
-    for _ in range(args.steps):
-        flush.fill_(1)
+    for _ in range(steps):
+        env.flush.fill_(1)
         _lib.check(lib.jlm_batch_run(batch))
         _lib.check(lib.jlm_batch_fetch(batch, C.byref(nb)))
         _lib.check(lib.jlm_batch_get_info(batch, C.byref(info)))
@@ -316,14 +332,12 @@ def main():
     _lib.check(lib.jlm_batch_destroy(batch))
 
     # ---------------- e2e arm: the public C-ABI calls with HOST buffers ----------------
-    # kana text (UTF-32, host) -> jlm_lattice_build (host C++) -> jlm_decode_batch (plan, H2D, all frames,
-    # D2H) -> n-best node ids (host).  Nothing is resident on the device when the timed region starts
-    # except the model weights.
+    # kana text (UTF-32, host) -> jlm_lattice_build (host C++) -> plan, H2D, all frames, D2H -> n-best (host).
+    # Nothing is resident on the device when the timed region starts except the model weights.
     lens = np.array([len(t) for t in sents], dtype=np.int64)
     tptr = np.zeros(len(sents) + 1, dtype=np.int64)
     np.cumsum(lens, out=tptr[1:])
     cps = np.frombuffer(''.join(sents).encode('utf-32-le'), dtype=np.uint32)
-
     tmax = int(lens.max()) + 1
     t_scores = np.empty((S, TOPN))
     t_npaths = np.empty(S, dtype=np.int32)
@@ -337,7 +351,6 @@ def main():
     tnb.path_entry, tnb.path_start = _lib.ptr(t_entry, C.c_int32), _lib.ptr(t_start, C.c_int32)
 
     def e2e_submit():
-        # public streaming call, first half: lattice build, plan, H2D, every frame + the n-best D2H enqueued
         job = C.c_void_p()
         _lib.check(lib.jlm_decode_texts_submit(hdl, nlex.handle, len(sents), _lib.ptr(tptr, C.c_int64),
                                                _lib.ptr(cps, C.c_uint32), BEAM, TOPN, MODE, n_extra,
@@ -346,14 +359,13 @@ def main():
         return job
 
     def e2e_collect(job):
-        # second half: wait for that job, n-best (lexicon entries) into host arrays
         _lib.check(lib.jlm_decode_texts_collect(job, C.byref(tnb), None))
 
     def e2e_run(n_steps, depth):
         """n_steps batches through submit/collect with at most `depth` in flight (depth 1 = the blocking
         jlm_decode_texts call); every batch is built from the host text again, copied H2D, decoded, copied
         D2H and unpacked inside the timed region."""
-        barrier()
+        env.barrier()
         t0 = time.perf_counter()
         inflight = []
         for _ in range(n_steps):
@@ -362,8 +374,8 @@ def main():
                 e2e_collect(inflight.pop(0))
         while inflight:
             e2e_collect(inflight.pop(0))
-        barrier()
-        return max_over_ranks(time.perf_counter() - t0)
+        env.barrier()
+        return env.reduce(time.perf_counter() - t0, 'MAX')
 
     for _ in range(2):
         e2e_collect(e2e_submit())
@@ -373,13 +385,11 @@ def main():
         ids = path_nodes[s_i, 0, :path_len[s_i, 0]]
         assert np.array_equal(packed.node_entry[ids], t_entry[s_i, 0, :t_len[s_i, 0]]), 'e2e paths differ'
     e2e_run(args.e2e_depth + 2, args.e2e_depth)      # untimed warm-up: the second in-flight arena is allocated here
-    e2e_s = e2e_run(args.steps, args.e2e_depth)
+    e2e_s = e2e_run(steps, args.e2e_depth)
     assert np.array_equal(t_scores, scores) and np.array_equal(t_len, path_len), 'streamed e2e arm disagrees'
-    e2e_blocking_s = e2e_run(args.steps, 1)
-    t_load1 = time.perf_counter()
-    e2e = total_chars * args.steps / e2e_s
-    e2e_blocking = total_chars * args.steps / e2e_blocking_s
-    clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+    e2e_blocking_s = e2e_run(steps, 1)
+    e2e = total_chars * steps / e2e_s
+    e2e_blocking = total_chars * steps / e2e_blocking_s
     # one more upload to read the byte counters of a single call
     b2 = C.c_void_p()
     _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(b2)))
@@ -389,9 +399,35 @@ def main():
     _lib.check(lib.jlm_batch_get_info(b2, C.byref(i2)))
     _lib.check(lib.jlm_batch_destroy(b2))
 
+    # ---------------- strong scaling: ONE fixed set sharded over the ranks (shard.decode_sharded) ----------------
+    strong = None
+    if args.scaling == 'strong' or (not headline and name in ('cfg4', 'cfg5')) or (headline and world > 1):
+        from jlm_b200 import synth
+        fixed = synth.make_sentences(lexicon, args.sentences, min_len=MIN_LEN, seed=4242, vocab_size=wl['V'])
+        kw = dict(topN=TOPN, beam_width=BEAM, backend=args.backend)
+        if wl['dynamic']:
+            kw.update(vocab_select=True, samples=wl['samples'], top_sampling=True)
+        shard.decode_sharded(dec, fixed, rank=rank, world_size=world, gather=True, **kw)      # warm-up
+        k_strong = max(2, min(steps, 5))
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_strong):
+            full = shard.decode_sharded(dec, fixed, rank=rank, world_size=world, gather=True, **kw)
+        env.barrier()
+        dt = env.reduce(time.perf_counter() - t0, 'MAX')
+        assert len(full) == len(fixed) and all(r is not None for r in full)
+        strong = {'value': sum(len(t) for t in fixed) * k_strong / dt, 'unit': 'chars/s', 'scaling': 'strong',
+                  'sentences_total': len(fixed), 'sentences_per_gpu': int(np.ceil(len(fixed) / float(world))),
+                  'steps': k_strong, 'ms_per_step': 1e3 * dt / k_strong,
+                  'call': 'jlm_b200.shard.decode_sharded: length-balanced partition, host text -> n-best per rank, packed '
+                          'all_gather_into_tensor (NCCL) of the n-best arrays, word lists rebuilt on every rank; wall clock, '
+                          'max over ranks'}
+    t_load1 = time.perf_counter()
+    env.windows.append((t_load0, t_load1))
+
     # ---------------- latency mode: one sentence per call (few rows in flight, exact float64 back end) ----------------
     lat_ms = None
-    if rank == 0:
+    if rank == 0 and headline:
         one = lattice.NativeLattices(nlex, sents[:1], MODE, extra[:1] if extra is not None else None)
         v1 = one.c_struct()
         for _ in range(3):
@@ -403,17 +439,15 @@ def main():
         _lib.check(lib.jlm_decode_batch(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(nb)))   # restore nb
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        del dec
+        return None
 
     sus, burst, hbm, src = peaks()
-    # algorithmic flops per LM row: gate 2*(E+H)*4H ; full-vocabulary output GEMMs
     f_gate_row, f_proj_row = flops_per_row(wl)
-    rows_total = rows_stepped * args.steps
+    rows_total = rows_stepped * steps
     traffic = None
     tp = os.path.join(REPO, 'profiles', 'traffic.json')
-    if os.path.exists(tp):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+    if os.path.exists(tp) and name == 'cfg2':       # dram bytes per launch from the committed ncu capture
         traffic = json.load(open(tp)).get('k_tc_gemm<256,EPI_LSE>', {}).get('dram_bytes_per_launch')
     roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': sus, 'peak_source': src + ' bf16 sustained', 'traffic': traffic}
     if proj_ms > 0 and args.backend == 2:
@@ -438,7 +472,7 @@ def main():
         roof.update({'achieved': None, 'frac': None})
 
     # ---------------- CPU baseline: oracle port on a bounded sample of the same workload ----------------
-    nb_cpu = max(1, min(args.cpu_baseline_sentences if world == 1 else 2, len(sents)))
+    nb_cpu = max(1, min(cpu_sentences if world == 1 else min(cpu_sentences, 2), len(sents)))
     try:      # all host cores for the CPU leg, whatever thread limit the launcher exported
         import threadpoolctl
         threadpoolctl.threadpool_limits(limits=os.cpu_count())
@@ -458,36 +492,81 @@ def main():
                for k in range(int(n_paths[s]))]
         top1_same += int(got[0] == cpu_out[s][0][1])
         nbest_same += int(got == [ws for _, ws in cpu_out[s]])
+    del dec
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'chars/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+        'metric': METRIC, 'value': value, 'unit': 'chars/s', 'n_gpus': world, 'steps': steps,
+        'warmup': max(warmup, 3), 'ms_per_step': ms_dev / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp16x2-split->f32' if args.backend == 2 else 'f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'sentences_per_gpu_per_step': S, 'chars_per_gpu_per_step': chars,
                    'lm_rows_per_step': rows_stepped, 'backend': 'tcgen05' if args.backend == 2 else 'exact-f64',
                    'l2': 'explicit 256 MiB flush between timed steps', 'host_lattice_build_s': t_lat,
                    'single_sentence_latency_ms': lat_ms, 'single_sentence_chars': len(sents[0]),
-                   'wall_s_timed_region': wall},
+                   'wall_s_timed_region': wall,
+                   'timed_region': 'jlm_batch_run + jlm_batch_fetch per step (frames, n-best D2H, near-tie guard)'},
         'e2e': {'value': e2e, 'unit': 'chars/s', 'h2d_bytes_per_step': int(i2.h2d_bytes),
                 'd2h_bytes_per_step': int(i2.d2h_bytes),
                 'call': 'jlm_decode_texts_submit + jlm_decode_texts_collect, %d batches in flight (host UTF-32 kana -> '
-                        'host n-best paths; per batch: lattice build, plan, H2D, frames, D2H, unpack - all inside the '
+                        'host n-best paths; per batch: lattice build, plan, H2D, frames, D2H, guard, unpack - all inside the '
                         'timed region; the host work of batch k+1 overlaps the device work of batch k)' % args.e2e_depth,
                 'blocking_value': e2e_blocking,
                 'blocking_call': 'jlm_decode_texts (one blocking call per batch, nothing overlapped)'},
         'gpu_launches': launches,
         'roofline': roof,
+        'guard': guard,
         'cpu_baseline': {'value': cpu_chars / cpu_s if world == 1 else None, 'unit': 'chars/s', 'cores': os.cpu_count(),
-                         'kind': 'port', 'note': None if world == 1 else 'timed at N=1 only; parity spot-check kept',
+                         'kind': 'port', 'note': CPU_NOTE if world == 1 else 'timed at N=1 only; parity spot-check kept',
                          'sample': 'first %d sentences (%d chars), lattice->n-best, numpy oracle' % (nb_cpu, cpu_chars),
                          'top1_identical_to_gpu': '%d/%d' % (top1_same, nb_cpu),
                          'nbest_identical_to_gpu': '%d/%d' % (nbest_same, nb_cpu)},
-        'clocks': clocks,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if strong is not None:
+        line['strong'] = strong
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--sentences', type=int, default=1024, help='sentences per GPU per step (lock-step batch)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ref-sentences', type=int, default=8, help='reference arm: sentences decoded per step')
+    ap.add_argument('--cpu-baseline-sentences', type=int, default=32)
+    ap.add_argument('--backend', type=int, default=2, help='1 exact (float64 CUDA cores), 2 tensor cores')
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--extra', default='cfg3,cfg4,cfg5',
+                    help='other BASELINE configs run for --extra-steps each and reported under "workloads" (none = skip)')
+    ap.add_argument('--extra-steps', type=int, default=3)
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='strong: also time the headline workload as ONE fixed set sharded over the ranks')
+    ap.add_argument('--chunks', type=int, default=0, help='e2e arm: pipeline chunks of jlm_decode_texts (0 = automatic)')
+    ap.add_argument('--e2e-depth', type=int, default=2, help='e2e arm: batches in flight through submit/collect')
+    ap.add_argument('--profile', action='store_true', help='1 warm-up + K plain steps only (for ncu); prints no JSON')
+    args = ap.parse_args()
+
+    if args.impl == 'reference':
+        run_reference(args, int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')))
+        return
+
+    env = Env(args)
+    line = bench_workload(env, args.workload, args.steps, args.warmup, args.cpu_baseline_sentences, headline=True)
+    extras = []
+    if not args.profile and args.extra and args.extra != 'none':
+        for name in [w for w in args.extra.split(',') if w in WORKLOADS and w != args.workload]:
+            sub = bench_workload(env, name, args.extra_steps, 3, 2 if name != 'cfg5' else 1, headline=False)
+            if sub is not None:
+                keep = ('value', 'unit', 'steps', 'ms_per_step', 'dtype', 'e2e', 'gpu_launches', 'roofline', 'guard',
+                        'cpu_baseline', 'strong')
+                extras.append(dict({'workload': name, 'config': sub['config']}, **{k: sub[k] for k in keep if k in sub}))
+    if env.rank == 0 and line is not None:
+        line['workloads'] = extras
+        line['clocks'] = env.sampler.stop(env.windows)
+        print(json.dumps(line), flush=True)
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -108,6 +108,19 @@ int32_t jlm_set_quantized_block(jlm_handle* h, int32_t segment, const uint8_t* c
 /* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*), e.g.
  * torch.cuda.current_stream().cuda_stream so torch.cuda.Event timing sees the kernels. */
 int32_t jlm_set_stream(jlm_handle* h, void* cuda_stream);
+/* Near-tie guard of the tensor-core back end.  Its path scores carry an error of a few 1e-6 per transition
+ * (fp32 state, fp32-accumulated logits), so where the reference's sort (decoder.py:227-229) separates two candidates
+ * by less than that, the tensor-core ranking is not certain to agree.  With eps > 0 every sentence in which some rank
+ * decision of some frame - two adjacent kept paths, or the last kept path against the best rejected candidate -
+ * rests on a gap < eps is checked inside jlm_batch_fetch / jlm_decode_*: the two paths of the decision are re-scored
+ * in float64 (jlm_pool kernels); if that contradicts the tensor-core ranking - or the decode mode normalises over
+ * per-frame word lists - the sentence is re-decoded on the float64 back end and that result is returned.
+ * eps = 0 switches the guard off; eps < 0 restores the default (JLM_GUARD_EPS_DEFAULT, or the JLM_GUARD_EPS
+ * environment variable read by jlm_create). */
+#define JLM_GUARD_EPS_DEFAULT 1e-4
+int32_t jlm_set_guard(jlm_handle* h, double eps);
+/* on = 0: skip the pair re-scoring and re-decode every flagged sentence in float64 (default on; JLM_GUARD_VERIFY) */
+int32_t jlm_set_guard_verify(jlm_handle* h, int32_t on);
 int32_t jlm_synchronize(jlm_handle* h);
 
 /* LSTM_Model._lstm_cell (model.py:125-139) for B rows; state in/out float64 [B,H]. */
@@ -277,7 +290,12 @@ typedef struct jlm_batch_info_s {
   int32_t n_proj_launches;
   int32_t beam_width;     /* paths per frame the per-frame arrays of jlm_batch_get_beams are strided by: the
                              beam_width of the call, or the widest frame for JLM_BEAM_UNLIMITED */
-  int32_t reserved0;
+  int32_t n_guard_flagged;/* near-tie guard (after jlm_batch_fetch): sentences with a rank decision below the bound */
+  double guard_min_gap;   /* smallest gap any rank decision of the batch rested on (guard enabled), else 0 */
+  double guard_eps;       /* the bound in force for this batch (0: guard off) */
+  int32_t n_guard_pairs;  /* near-tied rank decisions whose two paths were re-scored in float64 */
+  int32_t n_guard_rerun;  /* sentences re-decoded on the float64 back end (a re-scored pair contradicted the
+                             tensor-core ranking, mass ties, or a vocabulary-selection mode) */
 } jlm_batch_info;
 int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info);
 int32_t jlm_batch_enable_timers(jlm_batch* b, int32_t on);

@@ -54,7 +54,8 @@ class BatchInfo(C.Structure):
                 ('h2d_bytes', C.c_int64), ('d2h_bytes', C.c_int64), ('ms_lstm', C.c_float),
                 ('ms_softmax', C.c_float), ('ms_beam', C.c_float), ('ms_gate_gemm', C.c_float),
                 ('ms_proj_gemm', C.c_float), ('n_gate_launches', C.c_int32), ('n_proj_launches', C.c_int32),
-                ('beam_width', C.c_int32), ('reserved0', C.c_int32)]
+                ('beam_width', C.c_int32), ('n_guard_flagged', C.c_int32), ('guard_min_gap', C.c_double),
+                ('guard_eps', C.c_double), ('n_guard_pairs', C.c_int32), ('n_guard_rerun', C.c_int32)]
 
 
 # every symbol include/jlm_b200.h declares: name -> (restype, argtypes)
@@ -66,6 +67,8 @@ SYMBOLS = {
     'jlm_destroy': (C.c_int32, [_VP]),
     'jlm_set_quantized_block': (C.c_int32, [_VP, C.c_int32, C.POINTER(C.c_uint8), _f32p, C.c_int32]),
     'jlm_set_stream': (C.c_int32, [_VP, _VP]),
+    'jlm_set_guard': (C.c_int32, [_VP, C.c_double]),
+    'jlm_set_guard_verify': (C.c_int32, [_VP, C.c_int32]),
     'jlm_synchronize': (C.c_int32, [_VP]),
     'jlm_lstm_step': (C.c_int32, [_VP, _i32p, _f64p, _f64p, C.c_int32, _f64p, _f64p]),
     'jlm_project': (C.c_int32, [_VP, _f64p, C.c_int32, _i32p, _i32p, C.c_int32, _f64p]),

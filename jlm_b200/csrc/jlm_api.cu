@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cmath>
 
+#include <algorithm>
+
 #include "jlm_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -166,6 +168,8 @@ extern "C" int32_t jlm_create(const jlm_config* cfg, const jlm_weights* w, int32
   }
   h->own_stream = true;
   if (const char* e = getenv("JLM_Q8")) h->q8_policy = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("JLM_GUARD_EPS")) h->guard_eps = std::max(0.0, atof(e));
+  if (const char* e = getenv("JLM_GUARD_VERIFY")) h->guard_verify = atoi(e) != 0;
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (build_weights(h, w)) {
     jlm_destroy(h);
@@ -181,6 +185,7 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   tc_free_weights(h);
   beam_free_plan_scratch(h);
+  beam_free_guard(h);
   cudaFree(h->Wg);
   cudaFree(h->bg);
   cudaFree(h->b2);
@@ -246,6 +251,23 @@ extern "C" int32_t jlm_set_stream(jlm_handle* h, void* cuda_stream) {
   }
   h->stream = static_cast<cudaStream_t>(cuda_stream);
   h->own_stream = false;
+  return 0;
+}
+
+extern "C" int32_t jlm_set_guard(jlm_handle* h, double eps) {
+  JLM_REQUIRE(h, "jlm_set_guard: null handle");
+  JLM_REQUIRE(eps == eps, "jlm_set_guard: eps is NaN");
+  if (eps < 0.0) {
+    const char* e = getenv("JLM_GUARD_EPS");
+    eps = e ? std::max(0.0, atof(e)) : JLM_GUARD_EPS_DEFAULT;
+  }
+  h->guard_eps = eps;
+  return 0;
+}
+
+extern "C" int32_t jlm_set_guard_verify(jlm_handle* h, int32_t on) {
+  JLM_REQUIRE(h, "jlm_set_guard_verify: null handle");
+  h->guard_verify = on != 0;
   return 0;
 }
 

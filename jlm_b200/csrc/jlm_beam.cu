@@ -12,6 +12,7 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <unordered_map>
 
 #include "jlm_beam.cuh"
 
@@ -32,6 +33,9 @@ __global__ void k_init_frame0(BeamDev d, int S) {
   d.slot_node[s0] = node;
   d.slot_word[s0] = d.node_word[node];
   if (d.slot_cumy) d.slot_cumy[s0] = 0.0;
+  d.guard_gap[p] = INFINITY;
+  d.guard_flag[p] = 0;
+  if (p == 0) *d.guard_n = 0;
 }
 
 __global__ void k_build_items(BeamDev d) {
@@ -427,14 +431,15 @@ constexpr int PB_CAP = 160;    // survivors per warp segment
 
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
-k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
+k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_eps) {
   __shared__ double mins[128];
   __shared__ double sv[4][PB_CAP];
   __shared__ int sc[4][PB_CAP];
   __shared__ int cnt_w[4];
   __shared__ double tau_s;
-  __shared__ double ov[128];
-  __shared__ int oc[128];
+  __shared__ double ov[129];       // ranks 0..W (entry W: the best rejected candidate, for the near-tie guard)
+  __shared__ int oc[129];
+  __shared__ int minc[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned FULL = 0xffffffffu;
   const int p = blockIdx.x;
@@ -479,6 +484,8 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
   __syncthreads();
   const double tau = tau_s;
   int ns = 0;
+  double above = INFINITY;      // guard: smallest (score, ordinal) beyond tau - the best rejected one when exactly W survive
+  int above_c = -1;
   for (int base = w_lo; base < w_hi; base += 32 * UN) {
     double v[UN];
 #pragma unroll
@@ -490,6 +497,10 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
     for (int u = 0; u < UN; ++u) {
       const int c = base + u * 32 + lane;
       const bool keep = c < w_hi && v[u] <= tau;
+      if (!keep && v[u] < above) {      // ordinals ascend within a thread: strict < keeps the earliest of equals
+        above = v[u];
+        above_c = c;
+      }
       const unsigned m = __ballot_sync(FULL, keep);
       const int pos = ns + __popc(m & ((1u << lane) - 1u));
       if (keep && pos < PB_CAP) {
@@ -500,6 +511,25 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
     }
   }
   if (lane == 0) cnt_w[warp] = ns;
+  if (guard_eps > 0.0) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const double xv = __shfl_xor_sync(FULL, above, o);
+      const int xc = __shfl_xor_sync(FULL, above_c, o);
+      if (xv < above || (xv == above && xc >= 0 && (above_c < 0 || xc < above_c))) {
+        above = xv;
+        above_c = xc;
+      }
+    }
+    if (lane == 0) {      // mins[] is free again: tau has been published
+      mins[warp] = above;
+      minc[warp] = above_c;
+    }
+    if (tid == 0) {
+      ov[W] = INFINITY;
+      oc[W] = -1;
+    }
+  }
   __syncthreads();
   const int n0 = cnt_w[0], n1 = cnt_w[1], n2 = cnt_w[2], n3 = cnt_w[3];
   const bool overflow = n0 > PB_CAP || n1 > PB_CAP || n2 > PB_CAP || n3 > PB_CAP;     // block-uniform
@@ -538,11 +568,55 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
     if (r < W) {
       ov[r] = x;
       oc[r] = sc[gw][gi];
+    } else if (r == W && guard_eps > 0.0) {
+      ov[W] = x;
+      oc[W] = sc[gw][gi];
     }
   }
   __syncthreads();
   const int cnt = d.bc[fid];
   const int64_t s0 = d.slot0[fid];
+  if (guard_eps > 0.0) {
+    // every rank decision of the frame: kept[i] vs kept[i+1], and the last kept path vs the best rejected candidate
+    // (rank W among the survivors, else the smallest score beyond tau).  Mass ties (overflow) are flagged outright.
+    double gap = INFINITY;
+    bool full = overflow;      // the sentence needs the float64 re-decode: no record can describe the decision
+    if (!overflow && tid < cnt) {
+      double next = INFINITY;
+      int next_c = -1;
+      if (tid + 1 < cnt) {
+        next = ov[tid + 1];
+        next_c = oc[tid + 1];
+      } else if (cnt == W) {      // best rejected candidate: rank W among the survivors, else the smallest beyond tau
+        next = ov[W];
+        next_c = oc[W];
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4)
+          if (minc[w4] >= 0 && (mins[w4] < next || (mins[w4] == next && (next_c < 0 || minc[w4] < next_c)))) {
+            next = mins[w4];
+            next_c = minc[w4];
+          }
+      }
+      gap = next - ov[tid];
+      if (gap < guard_eps) {
+        const int slot = atomicAdd(d.guard_n, 1);
+        if (slot < d.guard_cap) d.guard_rec[slot] = make_int4(p, t, oc[tid], next_c);
+        else full = true;
+      }
+    }
+    const int near = __syncthreads_or(gap < guard_eps);
+    const int any_full = __syncthreads_or(full);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) gap = fmin(gap, __shfl_xor_sync(FULL, gap, o));
+    __shared__ double gap_w[4];
+    if (lane == 0) gap_w[warp] = gap;
+    __syncthreads();
+    if (tid == 0) {
+      const double gmin = overflow ? 0.0 : fmin(fmin(gap_w[0], gap_w[1]), fmin(gap_w[2], gap_w[3]));
+      if (gmin < d.guard_gap[p]) d.guard_gap[p] = gmin;      // one CTA per sentence, frames are stream-ordered
+      if (near || any_full) d.guard_flag[p] |= (near ? 1 : 0) | (any_full ? 2 : 0);
+    }
+  }
   if (tid < cnt) {
     const int64_t c = c0 + oc[tid];
     int a = lo, b = hi - 1;
@@ -557,6 +631,36 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse) {
     d.slot_word[s0 + tid] = d.node_word[a];
     if (DYN) d.slot_cumy[s0 + tid] = d.slot_cumy[par] + d.cand_val[c];
   }
+}
+
+// Near-tie guard: the node sequences of the two candidates of every queued record, so the host can re-score both
+// paths in float64 (guard_resolve).  A candidate is (node, parent rank); its parent's slots hold the rest of the path.
+__global__ void k_guard_paths(BeamDev d, int max_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(*d.guard_n, d.guard_cap);
+  if (i >= 2 * n) return;
+  const int4 rec = d.guard_rec[i >> 1];
+  const int c = (i & 1) ? rec.w : rec.z;
+  int32_t* out = d.guard_paths + (int64_t)i * (max_len + 1);
+  if (c < 0) {
+    out[0] = 0;
+    return;
+  }
+  const int fid = (int)d.fbase[rec.x] + rec.y;
+  const int64_t cg = d.frame_cand_lo[fid] + c;
+  int a = d.frame_lo[fid], b = d.frame_hi[fid] - 1;
+  while (a < b) {
+    const int mid = (a + b + 1) >> 1;
+    if (d.cand_pos[mid] <= cg) a = mid; else b = mid - 1;
+  }
+  const int par = (int)(d.slot0[d.node_pfid[a]] + (cg - d.cand_pos[a]));
+  int len = 1;
+  for (int s = par; s >= 0; s = d.slot_parent[s]) ++len;
+  out[0] = len;
+  int q = len - 1;
+  out[1 + q] = a;
+  --q;
+  for (int s = par; s >= 0 && q >= 0; s = d.slot_parent[s], --q) out[1 + q] = d.slot_node[s];
 }
 
 // beam_width=None (decoder.py:227-229 not executed): every candidate of the frame becomes a kept path, in the
@@ -1071,6 +1175,12 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   }
   d.cand_val = a.take<double>(ncd);
   d.items = a.take<ScoreItem>((size_t)std::max<int64_t>(d.n_items, 1));
+  d.guard_gap = a.take<double>((size_t)b->S);          // guard + n-best blocks are consecutive: one D2H copy
+  d.guard_flag = a.take<int32_t>((size_t)b->S);
+  d.guard_n = a.take<int32_t>(1);
+  d.guard_cap = b->guard_eps > 0.0 ? std::max(64, b->S) : 1;
+  d.guard_rec = a.take<int4>((size_t)d.guard_cap);
+  d.guard_paths = a.take<int32_t>((size_t)d.guard_cap * 2 * (b->max_len + 1));
   d.out_score = a.take<double>((size_t)b->S * b->topN);
   d.out_npaths = a.take<int32_t>((size_t)b->S);
   d.out_len = a.take<int32_t>((size_t)b->S * b->topN);
@@ -1216,13 +1326,13 @@ int32_t launch_prune(jlm_batch* b, int t) {
     const char* e = getenv("JLM_PRUNE_BLOCK");
     return e ? atoi(e) : 1;
   }();
-  if (block_mode) {      // one CTA per sentence
+  if (block_mode || b->guard_eps > 0.0) {      // one CTA per sentence (the near-tie guard lives in this kernel)
     if (L <= 1)
-      k_prune_block<1, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul);
+      k_prune_block<1, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps);
     else if (L <= 2)
-      k_prune_block<2, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul);
+      k_prune_block<2, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps);
     else
-      k_prune_block<4, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul);
+      k_prune_block<4, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps);
   } else if (L <= 1)
     k_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
   else if (L <= 2)
@@ -1235,6 +1345,299 @@ int32_t launch_prune(jlm_batch* b, int t) {
 }
 
 }  // namespace
+
+// Host copy of a lattice batch: jlm_batch_fetch may have to re-decode a few sentences (near-tie guard) long
+// after the caller's arrays are gone.  ~8 bytes per node, a fraction of a millisecond per 1024 sentences.
+struct GuardLattice {
+  std::vector<int32_t> sent_len, node_start, node_word, vocab_ids, vocab_frame_ptr, dup_ids;
+  std::vector<int64_t> frame_ptr_off, frame_ptr, vocab_ptr, dup_ptr;
+  // the sub-batch of the flagged sentences (arrays a jlm_lattice_batch view points into)
+  std::vector<int32_t> f_sent_len, f_node_start, f_node_word, f_vocab_ids, f_vocab_frame_ptr, f_dup_ids;
+  std::vector<int64_t> f_frame_ptr_off, f_frame_ptr, f_vocab_ptr, f_dup_ptr;
+  std::vector<int64_t> f_node_delta;      // original node index - sub-batch node index, per flagged sentence
+  // its n-best lists
+  std::vector<double> r_score;
+  std::vector<int32_t> r_npaths, r_len, r_nodes;
+  int r_max_len = 0;
+
+  void copy_from(const jlm_lattice_batch* lat, int mode) {
+    const int S = lat->n_sent;
+    sent_len.assign(lat->sent_len, lat->sent_len + S);
+    frame_ptr_off.assign(lat->frame_ptr_off, lat->frame_ptr_off + S);
+    int64_t fp_end = 0, n_nodes = 0;
+    for (int s = 0; s < S; ++s) {
+      fp_end = std::max(fp_end, lat->frame_ptr_off[s] + lat->sent_len[s] + 2);
+      n_nodes = std::max(n_nodes, lat->frame_ptr[lat->frame_ptr_off[s] + lat->sent_len[s] + 1]);
+    }
+    frame_ptr.assign(lat->frame_ptr, lat->frame_ptr + fp_end);
+    node_start.assign(lat->node_start, lat->node_start + n_nodes);
+    node_word.assign(lat->node_word, lat->node_word + n_nodes);
+    vocab_ptr.clear();
+    dup_ptr.clear();
+    if (mode != JLM_DECODE_FULL) {
+      vocab_ptr.assign(lat->vocab_ptr, lat->vocab_ptr + S + 1);
+      vocab_ids.assign(lat->vocab_ids, lat->vocab_ids + lat->vocab_ptr[S]);
+      if (mode == JLM_DECODE_DYNAMIC) {
+        vocab_frame_ptr.assign(lat->vocab_frame_ptr, lat->vocab_frame_ptr + fp_end);
+        dup_ptr.assign(lat->dup_ptr, lat->dup_ptr + S + 1);
+        dup_ids.assign(lat->dup_ids, lat->dup_ids + lat->dup_ptr[S]);
+      }
+    }
+  }
+
+  // view over the sentences `which` (caller's indices), node indices renumbered from 0
+  jlm_lattice_batch subset(const std::vector<int>& which, int mode) {
+    f_sent_len.clear(); f_node_start.clear(); f_node_word.clear(); f_vocab_ids.clear(); f_vocab_frame_ptr.clear();
+    f_dup_ids.clear(); f_frame_ptr_off.clear(); f_frame_ptr.clear(); f_node_delta.clear();
+    f_vocab_ptr.assign(1, 0);
+    f_dup_ptr.assign(1, 0);
+    for (int s : which) {
+      const int T = sent_len[s];
+      const int64_t* fp = &frame_ptr[frame_ptr_off[s]];
+      const int64_t n0 = fp[0], n1 = fp[T + 1];
+      const int64_t base = (int64_t)f_node_start.size();
+      f_sent_len.push_back(T);
+      f_frame_ptr_off.push_back((int64_t)f_frame_ptr.size());
+      f_node_delta.push_back(n0 - base);
+      for (int t = 0; t <= T + 1; ++t) f_frame_ptr.push_back(fp[t] - n0 + base);
+      f_node_start.insert(f_node_start.end(), node_start.begin() + n0, node_start.begin() + n1);
+      f_node_word.insert(f_node_word.end(), node_word.begin() + n0, node_word.begin() + n1);
+      if (mode != JLM_DECODE_FULL) {
+        f_vocab_ids.insert(f_vocab_ids.end(), vocab_ids.begin() + vocab_ptr[s], vocab_ids.begin() + vocab_ptr[s + 1]);
+        f_vocab_ptr.push_back((int64_t)f_vocab_ids.size());
+        if (mode == JLM_DECODE_DYNAMIC) {
+          const int32_t* vf = &vocab_frame_ptr[frame_ptr_off[s]];
+          f_vocab_frame_ptr.insert(f_vocab_frame_ptr.end(), vf, vf + T + 2);
+          f_dup_ids.insert(f_dup_ids.end(), dup_ids.begin() + dup_ptr[s], dup_ids.begin() + dup_ptr[s + 1]);
+          f_dup_ptr.push_back((int64_t)f_dup_ids.size());
+        }
+      }
+    }
+    jlm_lattice_batch v{};
+    v.n_sent = (int32_t)which.size();
+    v.sent_len = f_sent_len.data();
+    v.frame_ptr_off = f_frame_ptr_off.data();
+    v.frame_ptr = f_frame_ptr.data();
+    v.node_start = f_node_start.data();
+    v.node_word = f_node_word.data();
+    if (mode != JLM_DECODE_FULL) {
+      v.vocab_ptr = f_vocab_ptr.data();
+      v.vocab_ids = f_vocab_ids.data();
+      if (mode == JLM_DECODE_DYNAMIC) {
+        v.vocab_frame_ptr = f_vocab_frame_ptr.data();
+        v.dup_ptr = f_dup_ptr.data();
+        v.dup_ids = f_dup_ids.data();
+      }
+    }
+    return v;
+  }
+};
+
+static void guard_drop_rerun(jlm_batch* b) {
+  if (b->rerun) jlm_batch_destroy(b->rerun);
+  b->rerun = nullptr;
+  b->rerun_index.clear();
+  b->n_flagged = b->n_pairs = b->n_rerun = 0;
+}
+
+// Tier 1 of the near-tie guard: re-score the two paths of every queued rank decision in float64.
+// A path's score depends on its word sequence only (Path.append_node, decoder.py:43-49: sum of -log softmax along
+// the path), so all paths of all sentences go into ONE trie of word prefixes; each trie node is a state of the
+// float64 LM pool (jlm_pool: exact back end kernels), stepped level by level, with one log-sum-exp GEMM over all
+// nodes at the end.  A decision is confirmed when the float64 scores order the pair the way the tensor-core scores
+// did (equal scores: by enumeration ordinal, the stable sort's rule); a contradicted decision sends its sentence to
+// tier 2, the float64 re-decode.  Runs on its own stream, beside whatever the main stream holds.
+static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, const int32_t* paths, std::vector<char>& need_full) {
+  jlm_handle* h = b->h;
+  const GuardLattice& G = *b->guard_lat;
+  const int L = b->max_len + 1;
+  struct TNode { int parent, word, depth; int64_t slot; };
+  std::vector<TNode> trie;
+  std::unordered_map<uint64_t, int> index;          // (parent + 1) << 32 | word -> trie node
+  auto child = [&](int parent, int word) {
+    const uint64_t key = ((uint64_t)(uint32_t)(parent + 1) << 32) | (uint32_t)word;
+    auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    const int id = (int)trie.size();
+    trie.push_back(TNode{parent, word, parent < 0 ? 0 : trie[parent].depth + 1, -1});
+    index.emplace(key, id);
+    return id;
+  };
+  struct Query { int node, word; };                 // -log p(word | state of trie node)
+  std::vector<Query> queries;
+  std::unordered_map<uint64_t, int> qindex;
+  struct PathRef { std::vector<int> q; };
+  std::vector<PathRef> refs((size_t)2 * n_rec);
+  std::vector<char> need_lse;                       // per trie node
+  for (int r = 0; r < n_rec; ++r) {
+    if (need_full[rec[r].x]) continue;
+    const int32_t* pa = paths + ((int64_t)2 * r) * L;
+    const int32_t* pb = pa + L;
+    if (pa[0] <= 0 || pb[0] <= 0 || pa[0] > b->max_len || pb[0] > b->max_len) {   // no second candidate recorded
+      need_full[rec[r].x] = 1;
+      continue;
+    }
+    // The two paths share their first `common` words: those transitions are the SAME float64 terms in both scores
+    // and are not evaluated; at the first differing word both still read the same state, so its log-normaliser
+    // cancels as well.  Only states that contain a differing word need their full-vocabulary log-sum-exp.
+    int common = 0;
+    while (common < pa[0] && common < pb[0] && G.node_word[pa[1 + common]] == G.node_word[pb[1 + common]]) ++common;
+    for (int which = 0; which < 2; ++which) {
+      const int32_t* pth = which ? pb : pa;
+      const int len = pth[0];
+      int node = -1;
+      PathRef& pr = refs[(size_t)2 * r + which];
+      for (int j = 0; j < len; ++j) {
+        const int w = G.node_word[pth[1 + j]];
+        if (j >= common && j > 0) {                 // transition into word j from the state of words 0..j-1
+          const uint64_t qk = ((uint64_t)(uint32_t)node << 32) | (uint32_t)w;
+          auto it = qindex.find(qk);
+          if (it == qindex.end()) {
+            it = qindex.emplace(qk, (int)queries.size()).first;
+            queries.push_back(Query{node, w});
+          }
+          pr.q.push_back(it->second);
+          if (j > common) {
+            if ((int)need_lse.size() < (int)trie.size()) need_lse.resize(trie.size(), 0);
+            need_lse[node] = 1;
+          }
+        }
+        if (j + 1 < len) node = child(node, w);     // the last word's state is never consumed
+      }
+    }
+  }
+  need_lse.resize(trie.size(), 0);
+  if (queries.empty()) {
+    // every pair is a pair of identical word sequences (duplicate lattice nodes): equal float64 scores, and the
+    // record's order (rank i before rank i+1 of a stable sort) already is the enumeration order
+    for (int r = 0; r < n_rec; ++r)
+      if (!need_full[rec[r].x]) b->n_pairs += 1;
+    return 0;
+  }
+  constexpr int64_t POOL_CAP = 8192;
+  if ((int64_t)trie.size() > POOL_CAP) {            // pathological batch: let tier 2 handle every flagged sentence
+    for (int r = 0; r < n_rec; ++r) need_full[rec[r].x] = 1;
+    return 0;
+  }
+  if (!h->guard_stream) JLM_CUDA(cudaStreamCreateWithFlags(&h->guard_stream, cudaStreamNonBlocking));
+  if (!h->guard_pool) JLM_TRY(jlm_pool_create(h, POOL_CAP, &h->guard_pool));
+  // the pool works on the handle's stream: lend it the guard stream for the duration of the check
+  cudaStream_t main_stream = h->stream;
+  h->stream = h->guard_stream;
+  int32_t rc = jlm_pool_reset(h->guard_pool);
+  int max_depth = 0;
+  for (auto& t : trie) max_depth = std::max(max_depth, t.depth);
+  std::vector<std::vector<int>> by_depth(max_depth + 1);
+  for (int i = 0; i < (int)trie.size(); ++i) by_depth[trie[i].depth].push_back(i);
+  std::vector<int32_t> src, idx;
+  for (int dpt = 0; dpt <= max_depth && !rc; ++dpt) {
+    src.clear();
+    idx.clear();
+    for (int i : by_depth[dpt]) {
+      src.push_back(trie[i].parent < 0 ? -1 : (int32_t)trie[trie[i].parent].slot);
+      idx.push_back(trie[i].word);
+    }
+    int64_t first = 0;
+    rc = pool_step_rows(h->guard_pool, (int32_t)src.size(), src.data(), idx.data(), &first, false);
+    for (size_t k = 0; k < by_depth[dpt].size(); ++k) trie[by_depth[dpt][k]].slot = first + (int64_t)k;
+  }
+  {
+    std::vector<int32_t> lse_slots;
+    for (size_t i = 0; i < trie.size(); ++i)
+      if (need_lse[i]) lse_slots.push_back((int32_t)trie[i].slot);
+    if (!rc && !lse_slots.empty()) rc = pool_lse_slots(h->guard_pool, lse_slots.data(), (int32_t)lse_slots.size());
+    b->n_lse_rows = (int)lse_slots.size();
+  }
+  std::vector<int32_t> qs(queries.size()), qw(queries.size());
+  std::vector<double> nll(queries.size());
+  for (size_t i = 0; i < queries.size(); ++i) {
+    qs[i] = (int32_t)trie[queries[i].node].slot;
+    qw[i] = queries[i].word;
+  }
+  if (!rc) rc = jlm_pool_nll(h->guard_pool, (int32_t)queries.size(), qs.data(), qw.data(), nll.data());
+  h->stream = main_stream;
+  if (rc) return rc;
+  for (int r = 0; r < n_rec; ++r) {
+    if (need_full[rec[r].x]) continue;
+    double sc[2];
+    for (int which = 0; which < 2; ++which) {
+      double v = 0.0;                               // Path.__init__: neg_log_prob = 0, then += per node (decoder.py:34,49)
+      for (int q : refs[(size_t)2 * r + which].q) v += nll[q];
+      sc[which] = v;
+    }
+    b->n_pairs += 1;
+    // the tensor-core ranking put candidate z before candidate w; the stable sort agrees iff score_z < score_w, or
+    // the scores are equal and z comes first in enumeration order
+    const bool ok = sc[0] < sc[1] || (sc[0] == sc[1] && rec[r].z < rec[r].w);
+    if (!ok) need_full[rec[r].x] = 1;
+  }
+  return 0;
+}
+
+// Near-tie guard, host side (once per run; later fetches reuse the result).  Tier 1 re-scores the queued pairs
+// (full-softmax decoding; the vocabulary-selection modes normalise over per-frame word lists the pool does not
+// know); tier 2 re-decodes, on the float64 back end, the sentences tier 1 could not confirm.
+static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
+  if (b->guard_eps <= 0.0 || !b->guard_lat || !b->rerun_index.empty()) return 0;
+  auto at = [&](const void* dev) { return host + (reinterpret_cast<const char*>(dev) - src); };
+  const double* gap = reinterpret_cast<const double*>(at(b->d.guard_gap));
+  const int32_t* flag = reinterpret_cast<const int32_t*>(at(b->d.guard_flag));
+  const int n_rec = std::min(*reinterpret_cast<const int32_t*>(at(b->d.guard_n)), b->d.guard_cap);
+  const int4* rec = reinterpret_cast<const int4*>(at(b->d.guard_rec));
+  const int32_t* paths = reinterpret_cast<const int32_t*>(at(b->d.guard_paths));
+  b->rerun_index.assign(b->S, -1);
+  std::vector<char> need_full(b->S, 0);             // by sorted position
+  double mg = INFINITY;
+  b->n_flagged = b->n_pairs = b->n_rerun = 0;
+  for (int p = 0; p < b->S; ++p) {
+    mg = std::min(mg, gap[p]);
+    if (flag[p]) b->n_flagged += 1;
+    if ((flag[p] & 2) || (flag[p] && b->mode != JLM_DECODE_FULL)) need_full[p] = 1;
+  }
+  b->min_gap = mg;
+  if (b->n_flagged == 0) return 0;
+  static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
+  const auto t_0 = std::chrono::steady_clock::now();
+  if (b->mode == JLM_DECODE_FULL && b->h->guard_verify) {
+    JLM_TRY(guard_verify_pairs(b, n_rec, rec, paths, need_full));
+    if (dbg)
+      fprintf(stderr, "[jlm] guard: %d sentences flagged, %d records, %d pairs re-scored, %d lse rows, %.3f ms\n", b->n_flagged,
+              n_rec, b->n_pairs, b->n_lse_rows,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_0).count());
+  } else {
+    for (int p = 0; p < b->S; ++p)
+      if (flag[p]) need_full[p] = 1;
+  }
+  std::vector<int> which;
+  for (int p = 0; p < b->S; ++p)
+    if (need_full[p]) which.push_back(b->order[p]);
+  b->n_rerun = (int)which.size();
+  if (which.empty()) return 0;
+  std::sort(which.begin(), which.end());
+  GuardLattice& G = *b->guard_lat;
+  const jlm_lattice_batch sub = G.subset(which, b->mode);
+  jlm_batch* r = nullptr;
+  JLM_TRY(jlm_batch_upload(b->h, &sub, b->unlimited ? JLM_BEAM_UNLIMITED : b->W, b->topN, b->mode, JLM_BACKEND_EXACT, &r));
+  b->rerun = r;
+  JLM_TRY(jlm_batch_run(r));
+  const size_t n = which.size() * (size_t)r->topN;
+  G.r_max_len = r->max_len;
+  G.r_score.resize(n);
+  G.r_npaths.resize(which.size());
+  G.r_len.resize(n);
+  G.r_nodes.resize(n * r->max_len);
+  jlm_nbest nb{r->topN, r->max_len, G.r_score.data(), G.r_npaths.data(), G.r_len.data(), G.r_nodes.data()};
+  JLM_TRY(jlm_batch_fetch(r, &nb));
+  for (size_t k = 0; k < which.size(); ++k) b->rerun_index[which[k]] = (int)k;
+  return 0;
+}
+
+void beam_free_guard(jlm_handle* h) {
+  if (h->guard_pool) jlm_pool_destroy(h->guard_pool);
+  h->guard_pool = nullptr;
+  if (h->guard_stream) cudaStreamDestroy(h->guard_stream);
+  h->guard_stream = nullptr;
+}
 
 void beam_free_plan_scratch(jlm_handle* h) {
   delete static_cast<HostPlan*>(h->plan_scratch);
@@ -1281,6 +1684,12 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
   const auto t_1 = now();
   if (backend == JLM_BACKEND_AUTO) backend = (b->max_rows_step >= 512) ? JLM_BACKEND_TC : JLM_BACKEND_EXACT;
   b->backend = backend;
+  // near-tie guard: tensor-core back end only (the float64 back end IS the fallback); nothing to rank when unpruned
+  b->guard_eps = (backend == JLM_BACKEND_TC && !b->unlimited) ? h->guard_eps : 0.0;
+  if (b->guard_eps > 0.0) {
+    b->guard_lat = new GuardLattice();
+    b->guard_lat->copy_from(lat, mode);
+  }
   int32_t rc = 0;
   Arena a;
   a.begin_plan();
@@ -1375,6 +1784,7 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   JLM_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   b->launches = 0;
+  guard_drop_rerun(b);
   if (b->backend == JLM_BACKEND_TC && score_overlap_enabled()) {
     if (!h->side_stream) JLM_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     if (!b->ev_fork) JLM_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -1429,6 +1839,11 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
     }
   }
   if (b->timers) cudaEventRecord(b->events[3 * (size_t)b->n_steps], st);
+  if (b->guard_eps > 0.0) {
+    k_guard_paths<<<ceil_div(2 * (int64_t)b->d.guard_cap, 128), 128, 0, st>>>(b->d, b->max_len);
+    JLM_CUDA(cudaGetLastError());
+    b->launches += 1;
+  }
   k_backtrace<<<ceil_div((int64_t)b->S * b->topN, 128), 128, 0, st>>>(b->d, b->S, b->topN, b->max_len);
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
@@ -1449,8 +1864,8 @@ extern "C" int32_t jlm_batch_fetch_async(jlm_batch* b) {
   jlm_handle* h = b->h;
   JLM_CUDA(cudaSetDevice(h->device));
   const size_t n = (size_t)b->S * b->topN;
-  const char* src = reinterpret_cast<const char*>(b->d.out_score);
-  // out_score .. out_nodes are consecutive 256-aligned arena blocks: copy them in one transfer
+  const char* src = reinterpret_cast<const char*>(b->d.guard_gap);
+  // guard_gap, guard_flag, out_score .. out_nodes are consecutive 256-aligned arena blocks: one transfer
   const size_t total = (reinterpret_cast<const char*>(b->d.out_nodes) - src) + n * b->max_len * sizeof(int32_t);
   if (!b->out_host.p && !h->out_pool.empty()) {
     int pick = 0;   // smallest pooled buffer that fits, else the largest
@@ -1479,14 +1894,35 @@ extern "C" int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out) {
   JLM_CUDA(cudaSetDevice(h->device));
   JLM_TRY(jlm_batch_fetch_async(b));
   JLM_CUDA(cudaEventSynchronize(b->done));   // this batch only: later batches keep running
-  const char* src = reinterpret_cast<const char*>(b->d.out_score);
+  const char* src = reinterpret_cast<const char*>(b->d.guard_gap);
   const char* host = b->out_host.as<char>();
-  const double* sc = reinterpret_cast<const double*>(host);
+  const double* sc = reinterpret_cast<const double*>(host + (reinterpret_cast<const char*>(b->d.out_score) - src));
   const int32_t* np_ = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_npaths) - src));
   const int32_t* ln = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_len) - src));
   const int32_t* nd = reinterpret_cast<const int32_t*>(host + (reinterpret_cast<const char*>(b->d.out_nodes) - src));
+  JLM_TRY(guard_resolve(b, host, src));
   for (int p = 0; p < b->S; ++p) {
     const int s = b->order[p];
+    const int fk = b->rerun_index.empty() ? -1 : b->rerun_index[s];
+    if (fk >= 0) {      // flagged by the near-tie guard: the float64 re-decode replaces the tensor-core lists
+      const GuardLattice& G = *b->guard_lat;
+      const int rt = b->rerun->topN, rl = G.r_max_len;
+      out->n_paths[s] = G.r_npaths[fk];
+      for (int k = 0; k < out->top_n; ++k) {
+        const size_t o = (size_t)s * out->top_n + k;
+        if (k < rt) {
+          const size_t i = (size_t)fk * rt + k;
+          out->scores[o] = G.r_score[i];
+          out->path_len[o] = G.r_len[i];
+          for (int q = 0; q < std::min(G.r_len[i], rl); ++q)
+            out->path_nodes[o * out->max_len + q] = (int32_t)(G.r_nodes[i * rl + q] + G.f_node_delta[fk]);
+        } else {
+          out->scores[o] = INFINITY;
+          out->path_len[o] = 0;
+        }
+      }
+      continue;
+    }
     out->n_paths[s] = np_[p];
     for (int k = 0; k < out->top_n; ++k) {
       const size_t o = (size_t)s * out->top_n + k;
@@ -1549,6 +1985,9 @@ extern "C" int32_t jlm_batch_destroy(jlm_batch* b) {
   } else {
     cudaStreamSynchronize(b->h->stream);
   }
+  guard_drop_rerun(b);
+  delete b->guard_lat;
+  b->guard_lat = nullptr;
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->out_host.p) {
@@ -1589,6 +2028,11 @@ extern "C" int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info) {
   info->backend = b->backend;
   info->kernel_launches = b->launches;
   info->beam_width = b->W;
+  info->n_guard_flagged = b->n_flagged;
+  info->n_guard_pairs = b->n_pairs;
+  info->n_guard_rerun = b->n_rerun;
+  info->guard_min_gap = b->guard_eps > 0.0 ? b->min_gap : 0.0;
+  info->guard_eps = b->guard_eps;
   info->h2d_bytes = b->h2d_bytes;
   info->d2h_bytes = b->d2h_bytes;
   info->ms_lstm = b->ms_lstm;
@@ -1612,6 +2056,19 @@ extern "C" int32_t jlm_batch_get_beams(jlm_batch* b, int32_t sentence, int32_t* 
                                        double* h_out, double* c_out) {
   JLM_REQUIRE(b && b->ran, "jlm_batch_get_beams: run the batch first");
   JLM_REQUIRE(sentence >= 0 && sentence < b->S, "jlm_batch_get_beams: sentence out of range");
+  if (b->rerun && !b->rerun_index.empty() && b->rerun_index[sentence] >= 0) {
+    // flagged by the near-tie guard: the beams that produced the returned n-best are the float64 re-decode's
+    const int fk = b->rerun_index[sentence];
+    JLM_TRY(jlm_batch_get_beams(b->rerun, fk, count, score, parent_frame, parent_rank, node, lse, h_out, c_out));
+    if (node) {      // node indices of the sub-batch -> the caller's lattice
+      const jlm_batch* r = b->rerun;
+      int q = 0;
+      while (r->order[q] != fk) ++q;
+      for (int t = 0; t <= r->sent_T[q]; ++t)
+        for (int k = 0; k < r->bc[r->fbase[q] + t]; ++k) node[(size_t)t * r->W + k] += (int32_t)b->guard_lat->f_node_delta[fk];
+    }
+    return 0;
+  }
   jlm_handle* h = b->h;
   JLM_CUDA(cudaSetDevice(h->device));
   JLM_CUDA(cudaStreamSynchronize(h->stream));

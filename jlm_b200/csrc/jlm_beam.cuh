@@ -66,6 +66,13 @@ struct BeamDev {
   // (node order, then parent rank): candidate cand_pos[n] + r extends parent rank r with node n
   double* cand_val = nullptr;       // static: full path score ; dynamic: the transition's logit
   int32_t* cand_parent = nullptr;   // dynamic only: global slot of the candidate's parent path
+  // ---- near-tie guard (tensor-core back end): per sorted sentence, written by the prune kernel ----
+  double* guard_gap = nullptr;      // smallest gap between adjacent ranks 0..W of any frame (kept vs kept, kept vs best rejected)
+  int32_t* guard_flag = nullptr;    // bit 0: some gap fell below the bound (records queued); bit 1: re-decode in float64
+  int32_t* guard_n = nullptr;       // [1] near-tie records queued by the prune kernel
+  int4* guard_rec = nullptr;        // [guard_cap] {sorted sentence, frame, candidate ordinal ranked first, ... second}
+  int32_t* guard_paths = nullptr;   // [guard_cap][2][max_len + 1] {length, node ids first..last} of both candidates
+  int32_t guard_cap = 0;
   // ---- n-best output ----
   double* out_score = nullptr;
   int32_t* out_npaths = nullptr;
@@ -81,6 +88,20 @@ struct jlm_batch {
   bool use_lse = true;
   bool dynamic = false;
   bool unlimited = false;        // beam_width=None: no sort, no prune (W = widest frame of the plan)
+  // Near-tie guard.  The tensor-core back end carries fp32 state and fp32-accumulated logits, so two candidates
+  // whose float64 scores differ by less than its error can come out in the other order.  With guard_eps > 0 the
+  // prune kernel flags every sentence in which a rank decision (adjacent kept paths, or the last kept path against
+  // the best rejected candidate) rests on a gap below guard_eps; jlm_batch_fetch re-decodes exactly those sentences
+  // on the float64 back end and splices their results in.
+  double guard_eps = 0.0;
+  struct GuardLattice* guard_lat = nullptr;   // host copy of the lattice arrays (caller's buffers may be gone by fetch)
+  jlm_batch* rerun = nullptr;                 // the float64 batch of the flagged sentences (kept for jlm_batch_get_beams)
+  std::vector<int> rerun_index;               // caller's sentence index -> sentence of `rerun`, -1 = not flagged
+  int n_flagged = 0;             // sentences with at least one near-tie
+  int n_pairs = 0;               // near-tied rank decisions re-scored in float64 (jlm_pool path scores)
+  int n_lse_rows = 0;            // float64 log-sum-exp rows the re-scoring needed
+  int n_rerun = 0;               // sentences re-decoded in float64 (a re-scored pair contradicted the ranking, or no cheap check applies)
+  double min_gap = 0.0;
   std::vector<int> order;        // sorted position -> caller's sentence index
   std::vector<int> sent_T;       // by sorted position
   std::vector<int64_t> fbase;

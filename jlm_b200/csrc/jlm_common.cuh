@@ -142,6 +142,10 @@ struct jlm_handle {
   uint8_t* Wq_store[JLM_MAX_SEGMENTS] = {};
   float* cb_store[JLM_MAX_SEGMENTS] = {};
   int q8_policy = -1;   // -1 auto, 0 never, 1 always (JLM_Q8)
+  double guard_eps = JLM_GUARD_EPS_DEFAULT;   // near-tie guard bound of tensor-core batches (jlm_set_guard, JLM_GUARD_EPS)
+  bool guard_verify = true;                   // tier 1 (re-score the near-tied pairs) before tier 2 (re-decode the sentence)
+  jlm_pool* guard_pool = nullptr;             // float64 state pool the guard re-scores near-tied paths with
+  cudaStream_t guard_stream = nullptr;        // ... on its own stream, beside the next batch's kernels
   void* plan_scratch = nullptr;   // host vectors of the last batch plan, reused by the next upload (jlm_beam.cu)
   TcWeights* tc = nullptr;
   // scratch for the model-level API and the batch engine
@@ -225,6 +229,12 @@ int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t
                       int n_jobs, int max_cols, const int32_t* cols, const int32_t* bias_idx, double* out);
 
 void beam_free_plan_scratch(jlm_handle* h);   // jlm_beam.cu
+void beam_free_guard(jlm_handle* h);          // jlm_beam.cu: the near-tie verifier's state pool and stream
+
+// ---------------------------------------------------------------- LM state pool internals (jlm_pool.cu)
+int32_t pool_step_rows(jlm_pool* p, int32_t n, const int32_t* src, const int32_t* index, int64_t* first_slot, bool with_lse);
+int32_t pool_lse_rows(jlm_pool* p, int64_t first, int64_t count);
+int32_t pool_lse_slots(jlm_pool* p, const int32_t* slots, int32_t n);
 
 // ---------------------------------------------------------------- tensor-core back end (jlm_tc.cu)
 int32_t tc_prepare_weights(jlm_handle* h);

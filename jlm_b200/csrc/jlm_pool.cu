@@ -49,6 +49,19 @@ k_pool_nll(SegTable seg, const double* __restrict__ T, int64_t ldt, const double
   }
 }
 
+__global__ void k_pool_gather_T(const double* __restrict__ T, int64_t ldt, const int32_t* __restrict__ slots, int n,
+                                double* __restrict__ out) {
+  const int64_t total = (int64_t)n * ldt;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = T[(int64_t)slots[i / ldt] * ldt + i % ldt];
+}
+
+__global__ void k_pool_scatter_lse(const double* __restrict__ tmp, const int32_t* __restrict__ slots, int n,
+                                   double* __restrict__ lse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lse[slots[i]] = tmp[i];
+}
+
 }  // namespace
 
 extern "C" int32_t jlm_pool_create(jlm_handle* h, int64_t capacity, jlm_pool** out) {
@@ -100,7 +113,64 @@ extern "C" int32_t jlm_pool_reset(jlm_pool* p) {
   return 0;
 }
 
+// log-normalisers of the states in slots [first, first + count): full-vocabulary logits reduced to their log-sum-exp
+int32_t pool_lse_rows(jlm_pool* p, int64_t first, int64_t count) {
+  jlm_handle* h = p->h;
+  if (h->cfg.self_norm || count <= 0) return 0;
+  cudaStream_t st = h->stream;
+  const double* Trow = p->T + first * p->ldt;
+  const int n = (int)count;
+  JLM_TRY(p->part.reserve(sizeof(double2) * (size_t)n * p->tiles));
+  double2* part = p->part.as<double2>();
+  int tile0 = 0;
+  for (int i = 0; i < h->n_seg; ++i) {
+    const SegDev& s = h->seg[i];
+    const int Vi = s.end - s.start;
+    JLM_TRY(exact_gemm_f32w(st, Trow + s.koff, p->ldt, s.W, s.kpad, h->b2 + s.start, nullptr, 0, n, Vi, s.kpad, part,
+                            p->tiles, tile0));
+    tile0 += exact_tiles_n(Vi);
+  }
+  JLM_TRY(exact_lse_merge(st, part, p->tiles, p->tiles, n, p->lse + first, 0));
+  return 0;
+}
+
+// the same for a scattered list of slots (host array): their stage-1 rows are gathered into a dense block first
+int32_t pool_lse_slots(jlm_pool* p, const int32_t* slots, int32_t n) {
+  jlm_handle* h = p->h;
+  if (h->cfg.self_norm || n <= 0) return 0;
+  cudaStream_t st = h->stream;
+  JLM_TRY(p->idx.reserve(sizeof(int32_t) * (size_t)n));
+  JLM_TRY(p->G.reserve(sizeof(double) * ((size_t)n * p->ldt + (size_t)n)));
+  JLM_TRY(p->part.reserve(sizeof(double2) * (size_t)n * p->tiles));
+  int32_t* d_slots = p->idx.as<int32_t>();
+  double* Tg = p->G.as<double>();
+  double* lse_tmp = Tg + (size_t)n * p->ldt;
+  JLM_CUDA(cudaMemcpyAsync(d_slots, slots, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  k_pool_gather_T<<<ceil_div((int64_t)n * p->ldt, 256), 256, 0, st>>>(p->T, p->ldt, d_slots, n, Tg);
+  JLM_CUDA(cudaGetLastError());
+  double2* part = p->part.as<double2>();
+  int tile0 = 0;
+  for (int i = 0; i < h->n_seg; ++i) {
+    const SegDev& s = h->seg[i];
+    const int Vi = s.end - s.start;
+    JLM_TRY(exact_gemm_f32w(st, Tg + s.koff, p->ldt, s.W, s.kpad, h->b2 + s.start, nullptr, 0, n, Vi, s.kpad, part,
+                            p->tiles, tile0));
+    tile0 += exact_tiles_n(Vi);
+  }
+  JLM_TRY(exact_lse_merge(st, part, p->tiles, p->tiles, n, lse_tmp, 0));
+  k_pool_scatter_lse<<<ceil_div(n, 256), 256, 0, st>>>(lse_tmp, d_slots, n, p->lse);
+  JLM_CUDA(cudaGetLastError());
+  JLM_CUDA(cudaStreamSynchronize(st));      // d_slots (p->idx) is reused by the next call
+  return 0;
+}
+
 extern "C" int32_t jlm_pool_step(jlm_pool* p, int32_t n, const int32_t* src, const int32_t* index, int64_t* first_slot) {
+  return pool_step_rows(p, n, src, index, first_slot, true);
+}
+
+// with_lse = false leaves the log-normalisers to a later pool_lse_rows call over a range of slots (one GEMM over
+// many rows instead of one per step: the near-tie verifier, jlm_beam.cu)
+int32_t pool_step_rows(jlm_pool* p, int32_t n, const int32_t* src, const int32_t* index, int64_t* first_slot, bool with_lse) {
   JLM_REQUIRE(p && src && index && first_slot && n > 0, "jlm_pool_step: bad argument");
   jlm_handle* h = p->h;
   JLM_REQUIRE(p->used + n <= p->cap, "jlm_pool_step: pool full (%lld used + %d > %lld)", (long long)p->used, n,
@@ -128,25 +198,9 @@ extern "C" int32_t jlm_pool_step(jlm_pool* p, int32_t n, const int32_t* src, con
   JLM_TRY(exact_lstm_pointwise(st, h, p->G.as<double>(), p->cx, d_src, n, hrow, crow));
   // project (model.py:141-193): stage-1 rows are kept (needed-word logits are dots against them), the full
   // vocabulary is only reduced to its log-sum-exp
-  const double* Trow = hrow;
-  if (!h->untied) {
-    double* t = p->T + s0 * h->Kt;
-    JLM_TRY(exact_gemm_f64w(st, hrow, h->Hp, h->P1, h->Hp, t, h->Kt, n, h->Kt, h->Hp));
-    Trow = t;
-  }
-  if (!h->cfg.self_norm) {
-    JLM_TRY(p->part.reserve(sizeof(double2) * (size_t)n * p->tiles));
-    double2* part = p->part.as<double2>();
-    int tile0 = 0;
-    for (int i = 0; i < h->n_seg; ++i) {
-      const SegDev& s = h->seg[i];
-      const int Vi = s.end - s.start;
-      JLM_TRY(exact_gemm_f32w(st, Trow + s.koff, p->ldt, s.W, s.kpad, h->b2 + s.start, nullptr, 0, n, Vi, s.kpad, part,
-                              p->tiles, tile0));
-      tile0 += exact_tiles_n(Vi);
-    }
-    JLM_TRY(exact_lse_merge(st, part, p->tiles, p->tiles, n, p->lse + s0, 0));
-  }
+  if (!h->untied) JLM_TRY(exact_gemm_f64w(st, hrow, h->Hp, h->P1, h->Hp, p->T + s0 * h->Kt, h->Kt, n, h->Kt, h->Hp));
+  if (with_lse) JLM_TRY(pool_lse_rows(p, s0, n));
+  else JLM_CUDA(cudaMemsetAsync(p->lse + s0, 0, sizeof(double) * (size_t)n, st));   // "no normaliser": jlm_pool_nll returns -y
   // the index staging buffer is reused by the next call: order it behind this one's kernels
   JLM_CUDA(cudaStreamSynchronize(st));
   p->used += n;

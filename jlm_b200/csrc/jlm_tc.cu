@@ -73,7 +73,11 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // 256 x BN tile - each CTA stages its own 128 rows of A and HALF of the B tile, so a stage is 64 KB
 // instead of 96 KB and the per-MMA shared-memory traffic (operand reads + TMA writes), which is what
 // caps the single-CTA kernel at ~88 % tensor-pipe, drops from 20 KB to 13.3 KB per 128 cycles.
-template <int BN, int CG = 1>
+// KS > 1: the K range is cut into KS chunks, each accumulated into its OWN TMEM accumulator, and the epilogue adds
+// the partials in float64.  tcgen05 accumulates in fp32 with truncation (measured, scripts/tc_bias_probe.py: the
+// error of C = A.B^T grows linearly with K, -3e-9 K relative, biased toward zero), so a short chain per
+// accumulator is what buys accuracy; used for the stage-1 projection h.PM whose error every logit inherits.
+template <int BN, int CG = 1, int KS = 1>
 struct TileCfg {
   static constexpr int B_TILE = (BN / CG) * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
@@ -81,7 +85,9 @@ struct TileCfg {
   static constexpr int BIAS_BYTES = 2 * BN * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM = STAGES * STAGE + BIAS_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int ACC_COLS = BN * KS;          // TMEM columns of one accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512, "two accumulator stages must fit the 512 TMEM columns");
 };
 
 struct GemmArgs {
@@ -108,6 +114,8 @@ struct GemmArgs {
   int64_t ld_state;
 };
 
+__device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
+
 // 16 consecutive values -> two 32-byte runs (hi, lo): x*scale = hi + lo in fp16
 __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const float* v, float scale) {
   uint32_t ph[8], pl[8];
@@ -128,11 +136,12 @@ __device__ __forceinline__ void split_store16(__half* hi, __half* lo, const floa
   dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int KS = 1>
 __global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
           const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const GemmArgs g) {
-  using C = TileCfg<BN, CG>;
+  using C = TileCfg<BN, CG, KS>;
+  static_assert(KS == 1 || EPI == EPI_STORE, "partial accumulators are summed by the store epilogue only");
   // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tmem-empty barriers that count)
   const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-loop index of this CTA (pair)
@@ -235,23 +244,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       for (int tile = unit; tile < num_tiles; tile += n_units) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int kchunk = ceil_div_dev(num_kb, KS);      // k-blocks per partial accumulator
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint32_t sa = base + stage * C::STAGE;
+          const int part = (KS == 1) ? 0 : kb / kchunk;
+          const bool fresh = (KS == 1) ? kb == 0 : kb % kchunk == 0;
+          const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS + part * BN;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ah = ptx::umma_desc_sw128(sa + k * 32);
             const uint64_t al = ptx::umma_desc_sw128(sa + A_TILE + k * 32);
             const uint64_t bh = ptx::umma_desc_sw128(sa + 2 * A_TILE + k * 32);
             const uint64_t bl = ptx::umma_desc_sw128(sa + 2 * A_TILE + C::B_TILE + k * 32);
+            const uint32_t accum = (fresh && k == 0) ? 0u : 1u;
             if (CG == 2) {
-              ptx::mma_f16_ss_pair(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss_pair(d_tmem, ah, bl, idesc, accum);
               ptx::mma_f16_ss_pair(d_tmem, al, bh, idesc, 1u);
               ptx::mma_f16_ss_pair(d_tmem, ah, bh, idesc, 1u);
             } else {
-              ptx::mma_f16_ss(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss(d_tmem, ah, bl, idesc, accum);
               ptx::mma_f16_ss(d_tmem, al, bh, idesc, 1u);
               ptx::mma_f16_ss(d_tmem, ah, bh, idesc, 1u);
             }
@@ -302,7 +315,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       }
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       if (tile + n_units < num_tiles) fetch_bias(tile + n_units);
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * C::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
       // LSTM: the parent's cell row does not depend on the MMAs - fetch it while they run
@@ -373,15 +386,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
         }
         if (row_ok) g.part[(int64_t)row * g.part_ld + g.part_tile0 + n_blk] = make_float2(c_run, s_run);
       } else if (EPI == EPI_STORE) {
+        const int n_part = (KS == 1) ? 1 : ceil_div_dev(num_kb, ceil_div_dev(num_kb, KS));   // partials the MMA warp filled
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
           ptx::tmem_ld_x32(taddr + c0, r);
           ptx::tmem_ld_wait();
+          double sum[KS > 1 ? 32 : 1];
+          if (KS > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = (double)__uint_as_float(r[j]);
+            for (int pp = 1; pp < n_part; ++pp) {
+              ptx::tmem_ld_x32(taddr + pp * BN + c0, r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] += (double)__uint_as_float(r[j]);
+            }
+          }
           const int n0 = n_blk * BN + c0;
           if (row_ok && n0 < g.N) {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
+            for (int j = 0; j < 32; ++j)
+              v[j] = (KS > 1) ? (float)fma(sum[j], (double)g.inv_scale, (double)bs[c0 + j])
+                              : fmaf(__uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
             if (n0 + 32 <= g.N && (g.ldc & 3) == 0) {
               if (g.C32) {
                 float4* dst = reinterpret_cast<float4*>(g.C32 + (int64_t)row * g.ldc + n0);
@@ -784,8 +811,9 @@ static bool tc_narrow_enabled() {
   return v != 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int KS = 1>
 int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al, const TcOperand& B, GemmArgs g) {
+  static_assert(KS == 1 || BN < 256, "partial accumulators: the CTA-pair tiles fill TMEM with their two stages");
   JLM_REQUIRE(g.K % BK == 0 && g.K > 0, "tc gemm: K=%d must be a positive multiple of %d", g.K, BK);
   g.num_m_blocks = ceil_div(g.M, BM);
   g.num_n_blocks = ceil_div(g.N, BN);
@@ -822,17 +850,17 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
       return 0;
     }
   }
-  using C = TileCfg<BN, 1>;
+  using C = TileCfg<BN, 1, KS>;
   static bool configured = false;
   if (!configured) {
-    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
+    JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 1, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
     configured = true;
   }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
   // 64-column tiles read B through the quarter-box maps (operands are uploaded with 256-row boxes)
-  k_tc_gemm<BN, EPI, 1><<<grid, EpiCfg<EPI>::THREADS, C::SMEM + EpiCfg<EPI>::STG, h->stream>>>(Ah, Al, BN == 64 ? B.q_hi : B.map_hi,
-                                                                           BN == 64 ? B.q_lo : B.map_lo, g);
+  k_tc_gemm<BN, EPI, 1, KS><<<grid, EpiCfg<EPI>::THREADS, C::SMEM + EpiCfg<EPI>::STG, h->stream>>>(Ah, Al, BN == 64 ? B.q_hi : B.map_hi,
+                                                                               BN == 64 ? B.q_lo : B.map_lo, g);
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -854,6 +882,26 @@ struct TcWeights {
 };
 
 constexpr int GATE_BN = 256;
+
+// First-order compensation of the tensor core's truncating fp32 accumulate.  Measured on B200
+// (scripts/tc_bias_probe.py, profiles/r02/tc_bias_probe.txt): C_tc - C_f64 = -beta.C + noise with beta proportional to
+// the length K of the accumulation chain - 3.0e-9 K when the partial sums wander around zero (zero-mean products:
+// gate pre-activations, stage-1 rows) and 6.8e-9 K when they drift monotonically toward a large final value (the few
+// large logits that carry a softmax denominator).  The un-scale factor of each epilogue is multiplied by
+// (1 + beta K).  JLM_TC_DEBIAS is a bit mask (1 gate, 2 stage-1, 4 output GEMMs; default 6).  The gate GEMM is left
+// alone: measured against the float64 back end (scripts/tc_error_probe.py, profiles/r02) its compensation moves h
+// AWAY from the float64 state (sum|h| error -1.5e-5 -> +3.3e-5), while the output-GEMM factor alone takes the mean
+// log-sum-exp error from -2.3e-5 to +1.7e-7 (std 2.1e-6).
+constexpr double RZ_WANDER = 3.0e-9, RZ_DRIFT = 6.8e-9;
+enum { RZ_GATE = 1, RZ_STAGE1 = 2, RZ_OUT = 4 };      // JLM_TC_DEBIAS bit mask: which GEMMs are compensated
+static float rz_comp(int which, double per_k, int chain_k) {
+  static const int mask = [] {
+    const char* e = getenv("JLM_TC_DEBIAS");
+    return e ? atoi(e) : (RZ_STAGE1 | RZ_OUT);
+  }();
+  return (mask & which) ? (float)(1.0 + per_k * chain_k) : 1.f;
+}
+constexpr int STAGE1_KS = 4;      // partial accumulators of the stage-1 projection GEMM (TileCfg)
 
 static void free_tc_weights(TcWeights* w);
 static int32_t tc_build_weights(jlm_handle* h, TcWeights* w);
@@ -1031,7 +1079,7 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
     g.M = M;
     g.N = 4 * h->Hp;
     g.K = h->Kg;
-    g.inv_scale = 1.f / (w->sA * w->Wg.scale);
+    g.inv_scale = rz_comp(RZ_GATE, RZ_WANDER, h->Kg) / (w->sA * w->Wg.scale);
     g.bias = w->bg_perm;
     g.c_src = s->c32;
     g.parent = parent;
@@ -1055,7 +1103,7 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
     g.M = M;
     g.N = h->Kt;
     g.K = h->Hp;
-    g.inv_scale = 1.f / (w->sA * w->P1.scale);
+    g.inv_scale = 1.f / (w->sA * w->P1.scale);     // compensation factor chosen with the kernel below
     g.a_row0 = (int)sp.row0;
     g.C32 = s->T32;
     g.ldc = h->Kt;
@@ -1066,11 +1114,18 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
     // h.PM has few output columns (Kt = E): 256-column tiles give ceil(M/128) CTAs, each with an epilogue
     // nothing overlaps.  64-column tiles quadruple the tile count so every SM works and the store
     // epilogue of one tile runs under the MMAs of the next.
+    // Every logit inherits the error of these rows, so the narrow kernel also cuts K into STAGE1_KS accumulation
+    // chains summed in float64 by its epilogue (TileCfg): 4x shorter chains, 4x less truncation error.
     const int tiles256 = ceil_div(M, BM) * ceil_div(h->Kt, 256);
-    if (tiles256 < 2 * h->sm_count && tc_narrow_enabled())
-      JLM_TRY((launch_gemm<64, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
-    else
+    if (tc_narrow_enabled()) {
+      const int chain = ceil_div(h->Hp / BK, STAGE1_KS) * BK;
+      g.inv_scale *= rz_comp(RZ_STAGE1, RZ_WANDER, chain);
+      JLM_TRY((launch_gemm<64, EPI_STORE, STAGE1_KS>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
+    } else {
+      g.inv_scale *= rz_comp(RZ_STAGE1, RZ_WANDER, h->Hp);
       JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mHs_hi, s->mHs_lo, w->P1, g)));
+    }
+    (void)tiles256;
     b->launches += 1;
     T32 = s->T32;
     ldt = h->Kt;
@@ -1098,7 +1153,7 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
       g.M = M;
       g.N = sg.end - sg.start;
       g.K = sg.kpad;
-      g.inv_scale = 1.f / (w->sT * w->seg[i].scale);
+      g.inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, sg.kpad) / (w->sT * w->seg[i].scale);
       g.bias = h->b2 + sg.start;
       g.part = s->part;
       g.part_ld = w->lse_tiles;
@@ -1160,7 +1215,7 @@ int32_t tc_vocab_logits(jlm_batch* b, int t, double* out) {
     configured = true;
   }
   const int gx = ceil_div(sp.max_vocab_cols, VT_M);
-  const float inv_scale = 1.f / (w->sT * w->seg[0].scale);
+  const float inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, h->seg[0].kpad) / (w->sT * w->seg[0].scale);
   for (int j0 = 0; j0 < sp.nstep; j0 += 65535) {
     const int nj = std::min(sp.nstep - j0, 65535);
     k_tc_vocab_logits<<<dim3(gx, nj), 128, VT_SMEM, h->stream>>>(

@@ -163,6 +163,12 @@ extern "C" int32_t jlm_decode_texts_collect(jlm_text_job* job, jlm_text_nbest* o
       info->ms_proj_gemm += bi.ms_proj_gemm;
       info->n_gate_launches += bi.n_gate_launches;
       info->n_proj_launches += bi.n_proj_launches;
+      info->beam_width = std::max(info->beam_width, bi.beam_width);
+      info->n_guard_flagged += bi.n_guard_flagged;
+      info->n_guard_pairs += bi.n_guard_pairs;
+      info->n_guard_rerun += bi.n_guard_rerun;
+      info->guard_eps = bi.guard_eps;
+      info->guard_min_gap = (c == 0) ? bi.guard_min_gap : std::min(info->guard_min_gap, bi.guard_min_gap);
     }
     for (int32_t s = 0; s < ck.n; ++s) {
       const int64_t gs = ck.s0 + s;

@@ -154,8 +154,10 @@ class Decoder(object):
                                                int(n_chunks), 1, C.byref(job)))
         return {'job': job, 'texts': texts, 'top': top, 'topN': topN, 'max_len': int(lens.max()) + 1}
 
-    def _collect_texts(self, pending):
-        """jlm_decode_texts_collect: waits for that job only and turns its n-best block into word lists."""
+    def _collect_texts_arrays(self, pending):
+        """jlm_decode_texts_collect: waits for that job only; the n-best block as arrays
+        {'scores' [S,top] f64, 'n_paths' [S], 'path_len' [S,top], 'path_entry' / 'path_start' [S,top,max_len] i32}
+        (paths as lexicon entries: -1 '<eos>', -2 '<unk>' whose word is the kana at path_start)."""
         lib = self._lib
         texts, top, max_len = pending['texts'], pending['top'], pending['max_len']
         S = len(texts)
@@ -173,17 +175,43 @@ class Decoder(object):
         job, pending['job'] = pending['job'], None       # collect consumes the job, also on error
         _lib.check(lib.jlm_decode_texts_collect(job, C.byref(nb), C.byref(info)))
         self.last_info = info
+        return {'scores': scores, 'n_paths': n_paths, 'path_len': path_len, 'path_entry': path_entry,
+                'path_start': path_start}
+
+    def words_from_arrays(self, texts, arrays, topN=None):
+        """n-best word lists [(neg_log_prob, [word, ...])] from the array form (decoder.py:237-241)."""
         ew = self._native().entry_words
+        scores, n_paths, path_len = arrays['scores'], arrays['n_paths'], arrays['path_len']
+        path_entry, path_start = arrays['path_entry'], arrays['path_start']
         out = []
-        for s in range(S):
-            res, text = [], texts[s]
+        for s, text in enumerate(texts):
+            res = []
             for k in range(int(n_paths[s])):
                 n = int(path_len[s, k])
                 ents, starts = path_entry[s, k, :n].tolist(), path_start[s, k, :n].tolist()
                 # '<eos>' (-1) is dropped (decoder.py:237); '<unk>' (-2) carries the raw kana (decoder.py:130)
                 res.append((float(scores[s, k]), [ew[e] if e >= 0 else text[st] for e, st in zip(ents, starts) if e != -1]))
-            out.append(res[:pending['topN']])
+            out.append(res[:topN] if topN is not None else res)
         return out
+
+    def _collect_texts(self, pending):
+        """jlm_decode_texts_collect: waits for that job only and turns its n-best block into word lists."""
+        return self.words_from_arrays(pending['texts'], self._collect_texts_arrays(pending), pending['topN'])
+
+    def decode_batch_arrays(self, inputs, topN=10, beam_width=10, backend=_lib.BACKEND_AUTO, **sampling):
+        """decode_batch() returning the n-best block as arrays (see _collect_texts_arrays) instead of Python
+        word lists: what a sharded caller exchanges between ranks (jlm_b200/shard.py).  Static full-softmax
+        decoding for Decoder; DynamicDecoder overrides the mode."""
+        inputs = list(inputs)
+        mode, extra = self._array_mode(len(inputs), **sampling)
+        arrays = self._collect_texts_arrays(self._submit_texts(inputs, mode, extra, topN, beam_width, backend))
+        self._log_batch_perf(len(inputs), last_frame_stepped=not self.dynamic)
+        return arrays
+
+    def _array_mode(self, n_sent, vocab_select=False, samples=0, top_sampling=False, random_sampling=False):
+        if vocab_select:
+            return _lib.DECODE_STATIC_VOCAB, self._sample_ids(n_sent, samples, top_sampling, random_sampling)
+        return _lib.DECODE_FULL, None
 
     def _run_texts(self, texts, mode, extra, topN, beam_width, backend, n_chunks=0):
         """One jlm_decode_texts call: kana strings in, n-best word lists out."""

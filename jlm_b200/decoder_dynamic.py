@@ -56,6 +56,11 @@ class DynamicDecoder(Decoder):
         self.perf_sen += 1
         return out[0]
 
+    def _array_mode(self, n_sent, vocab_select=True, samples=0, top_sampling=False, random_sampling=False):
+        if not vocab_select:
+            raise AttributeError("'NoneType' object has no attribute 'index' (DynamicDecoder needs vocab_select=True)")
+        return _lib.DECODE_DYNAMIC, self._sample_ids(n_sent, samples, top_sampling, random_sampling)
+
     def decode_batch(self, inputs, topN=10, beam_width=10, vocab_select=True, samples=0, top_sampling=False,
                      random_sampling=False, backend=_lib.BACKEND_AUTO, native_lattice=True):
         inputs = list(inputs)

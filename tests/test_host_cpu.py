@@ -124,7 +124,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Weights) == 8 * (4 + 4 + 4 + 4 + 8 + 8)
     assert ctypes.sizeof(_lib.LatticeBatch) == 8 * 11
     assert ctypes.sizeof(_lib.NBest) == 8 + 8 * 4
-    assert ctypes.sizeof(_lib.BatchInfo) == 8 * 3 + 4 * 2 + 8 * 3 + 4 * 3 + 4 * 4 + 4 * 2 + 4
+    assert ctypes.sizeof(_lib.BatchInfo) == 8 * 3 + 4 * 2 + 8 * 3 + 4 * 3 + 4 * 4 + 4 * 2 + 4 + 8 * 2 + 4 * 2
 
 
 def test_product_fails_loudly_without_gpu(tmp_path):

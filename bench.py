@@ -331,6 +331,37 @@ def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
         n_proj += info.n_proj_launches
     _lib.check(lib.jlm_batch_destroy(batch))
 
+    # ---------------- the same K steps with the near-tie guard switched off (what the certification costs) ----------------
+    if float(guard['eps']) > 0.0:
+        _lib.check(lib.jlm_set_guard(hdl, 0.0))
+        b3 = C.c_void_p()
+        _lib.check(lib.jlm_batch_upload(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(b3)))
+        _lib.check(lib.jlm_set_guard(hdl, -1.0))
+        nb_off = (np.empty((S, TOPN)), np.empty(S, dtype=np.int32), np.empty((S, TOPN), dtype=np.int32),
+                  np.zeros((S, TOPN, max_len), dtype=np.int32))
+        nbo = _lib.NBest()
+        nbo.top_n, nbo.max_len = TOPN, max_len
+        nbo.scores, nbo.n_paths = _lib.ptr(nb_off[0], C.c_double), _lib.ptr(nb_off[1], C.c_int32)
+        nbo.path_len, nbo.path_nodes = _lib.ptr(nb_off[2], C.c_int32), _lib.ptr(nb_off[3], C.c_int32)
+        _lib.check(lib.jlm_batch_run(b3))
+        _lib.check(lib.jlm_batch_fetch(b3, C.byref(nbo)))
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        env.barrier()
+        for a, b in ev3:
+            env.flush.fill_(1)
+            a.record(stream)
+            _lib.check(lib.jlm_batch_run(b3))
+            _lib.check(lib.jlm_batch_fetch(b3, C.byref(nbo)))
+            b.record(stream)
+        env.barrier()
+        ms_off = env.reduce(sum(a.elapsed_time(b) for a, b in ev3), 'MAX')
+        _lib.check(lib.jlm_batch_destroy(b3))
+        guard['value_guard_off'] = total_chars * steps / (ms_off * 1e-3)
+        guard['ms_per_step_guard_off'] = ms_off / steps
+        guard['nbest_changed_by_guard'] = int(S - sum(
+            int(n_paths[s] == nb_off[1][s] and np.array_equal(path_len[s], nb_off[2][s]) and
+                np.array_equal(path_nodes[s], nb_off[3][s])) for s in range(S)))
+
     # ---------------- e2e arm: the public C-ABI calls with HOST buffers ----------------
     # kana text (UTF-32, host) -> jlm_lattice_build (host C++) -> plan, H2D, all frames, D2H -> n-best (host).
     # Nothing is resident on the device when the timed region starts except the model weights.

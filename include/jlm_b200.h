@@ -119,6 +119,10 @@ int32_t jlm_set_stream(jlm_handle* h, void* cuda_stream);
  * environment variable read by jlm_create). */
 #define JLM_GUARD_EPS_DEFAULT 1e-4
 int32_t jlm_set_guard(jlm_handle* h, double eps);
+/* Which rank decisions are guarded.  0 (default): those that can change what decode() returns - the kept/rejected
+ * boundary of every frame and the order of the last frame's paths.  1: every adjacent pair of every frame, so the
+ * per-frame rank order reported by jlm_batch_get_beams is certified too (JLM_GUARD_ALL). */
+int32_t jlm_set_guard_scope(jlm_handle* h, int32_t all_decisions);
 /* on = 0: skip the pair re-scoring and re-decode every flagged sentence in float64 (default on; JLM_GUARD_VERIFY) */
 int32_t jlm_set_guard_verify(jlm_handle* h, int32_t on);
 int32_t jlm_synchronize(jlm_handle* h);

@@ -69,6 +69,7 @@ SYMBOLS = {
     'jlm_set_stream': (C.c_int32, [_VP, _VP]),
     'jlm_set_guard': (C.c_int32, [_VP, C.c_double]),
     'jlm_set_guard_verify': (C.c_int32, [_VP, C.c_int32]),
+    'jlm_set_guard_scope': (C.c_int32, [_VP, C.c_int32]),
     'jlm_synchronize': (C.c_int32, [_VP]),
     'jlm_lstm_step': (C.c_int32, [_VP, _i32p, _f64p, _f64p, C.c_int32, _f64p, _f64p]),
     'jlm_project': (C.c_int32, [_VP, _f64p, C.c_int32, _i32p, _i32p, C.c_int32, _f64p]),

@@ -170,6 +170,7 @@ extern "C" int32_t jlm_create(const jlm_config* cfg, const jlm_weights* w, int32
   if (const char* e = getenv("JLM_Q8")) h->q8_policy = atoi(e) ? 1 : 0;
   if (const char* e = getenv("JLM_GUARD_EPS")) h->guard_eps = std::max(0.0, atof(e));
   if (const char* e = getenv("JLM_GUARD_VERIFY")) h->guard_verify = atoi(e) != 0;
+  if (const char* e = getenv("JLM_GUARD_ALL")) h->guard_all = atoi(e) != 0;
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   if (build_weights(h, w)) {
     jlm_destroy(h);
@@ -262,6 +263,12 @@ extern "C" int32_t jlm_set_guard(jlm_handle* h, double eps) {
     eps = e ? std::max(0.0, atof(e)) : JLM_GUARD_EPS_DEFAULT;
   }
   h->guard_eps = eps;
+  return 0;
+}
+
+extern "C" int32_t jlm_set_guard_scope(jlm_handle* h, int32_t all_decisions) {
+  JLM_REQUIRE(h, "jlm_set_guard_scope: null handle");
+  h->guard_all = all_decisions != 0;
   return 0;
 }
 

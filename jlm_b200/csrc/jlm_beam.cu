@@ -431,7 +431,7 @@ constexpr int PB_CAP = 160;    // survivors per warp segment
 
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
-k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_eps) {
+k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_eps, int guard_all, int topN) {
   __shared__ double mins[128];
   __shared__ double sv[4][PB_CAP];
   __shared__ int sc[4][PB_CAP];
@@ -581,7 +581,13 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_ep
     // (rank W among the survivors, else the smallest score beyond tau).  Mass ties (overflow) are flagged outright.
     double gap = INFINITY;
     bool full = overflow;      // the sentence needs the float64 re-decode: no record can describe the decision
-    if (!overflow && tid < cnt) {
+    // Which decisions are guarded.  guard_all: every adjacent pair of every frame (the per-frame rank order too).
+    // Otherwise those that can change what decode() returns: the kept/rejected boundary of every frame (the SET of
+    // kept paths) and, in the sentence's last frame, the pairs that order the first topN paths (the returned list).
+    // Two kept paths swapping ranks inside an intermediate frame only renumber later candidates, which the stable
+    // sort consults for exactly equal scores alone.
+    const bool mine = guard_all || (t == d.sent_T[p] && tid < topN) || (tid == cnt - 1 && cnt == W);
+    if (!overflow && tid < cnt && mine) {
       double next = INFINITY;
       int next_c = -1;
       if (tid + 1 < cnt) {
@@ -1178,7 +1184,7 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   d.guard_gap = a.take<double>((size_t)b->S);          // guard + n-best blocks are consecutive: one D2H copy
   d.guard_flag = a.take<int32_t>((size_t)b->S);
   d.guard_n = a.take<int32_t>(1);
-  d.guard_cap = b->guard_eps > 0.0 ? std::max(64, b->S) : 1;
+  d.guard_cap = b->guard_eps > 0.0 ? std::max(64, 4 * b->S) : 1;
   d.guard_rec = a.take<int4>((size_t)d.guard_cap);
   d.guard_paths = a.take<int32_t>((size_t)d.guard_cap * 2 * (b->max_len + 1));
   d.out_score = a.take<double>((size_t)b->S * b->topN);
@@ -1328,11 +1334,11 @@ int32_t launch_prune(jlm_batch* b, int t) {
   }();
   if (block_mode || b->guard_eps > 0.0) {      // one CTA per sentence (the near-tie guard lives in this kernel)
     if (L <= 1)
-      k_prune_block<1, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps);
+      k_prune_block<1, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN);
     else if (L <= 2)
-      k_prune_block<2, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps);
+      k_prune_block<2, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN);
     else
-      k_prune_block<4, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps);
+      k_prune_block<4, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN);
   } else if (L <= 1)
     k_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
   else if (L <= 2)
@@ -1514,7 +1520,7 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
       if (!need_full[rec[r].x]) b->n_pairs += 1;
     return 0;
   }
-  constexpr int64_t POOL_CAP = 8192;
+  constexpr int64_t POOL_CAP = 16384;
   if ((int64_t)trie.size() > POOL_CAP) {            // pathological batch: let tier 2 handle every flagged sentence
     for (int r = 0; r < n_rec; ++r) need_full[rec[r].x] = 1;
     return 0;
@@ -1686,6 +1692,7 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
   b->backend = backend;
   // near-tie guard: tensor-core back end only (the float64 back end IS the fallback); nothing to rank when unpruned
   b->guard_eps = (backend == JLM_BACKEND_TC && !b->unlimited) ? h->guard_eps : 0.0;
+  b->guard_all = h->guard_all;
   if (b->guard_eps > 0.0) {
     b->guard_lat = new GuardLattice();
     b->guard_lat->copy_from(lat, mode);

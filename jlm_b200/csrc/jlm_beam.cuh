@@ -94,6 +94,7 @@ struct jlm_batch {
   // the best rejected candidate) rests on a gap below guard_eps; jlm_batch_fetch re-decodes exactly those sentences
   // on the float64 back end and splices their results in.
   double guard_eps = 0.0;
+  bool guard_all = false;        // guard every rank decision, not only those that can change the returned n-best
   struct GuardLattice* guard_lat = nullptr;   // host copy of the lattice arrays (caller's buffers may be gone by fetch)
   jlm_batch* rerun = nullptr;                 // the float64 batch of the flagged sentences (kept for jlm_batch_get_beams)
   std::vector<int> rerun_index;               // caller's sentence index -> sentence of `rerun`, -1 = not flagged

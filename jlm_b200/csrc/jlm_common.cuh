@@ -143,6 +143,7 @@ struct jlm_handle {
   float* cb_store[JLM_MAX_SEGMENTS] = {};
   int q8_policy = -1;   // -1 auto, 0 never, 1 always (JLM_Q8)
   double guard_eps = JLM_GUARD_EPS_DEFAULT;   // near-tie guard bound of tensor-core batches (jlm_set_guard, JLM_GUARD_EPS)
+  bool guard_all = false;                     // JLM_GUARD_ALL / jlm_set_guard_scope: every rank decision of every frame
   bool guard_verify = true;                   // tier 1 (re-score the near-tied pairs) before tier 2 (re-decode the sentence)
   jlm_pool* guard_pool = nullptr;             // float64 state pool the guard re-scores near-tied paths with
   cudaStream_t guard_stream = nullptr;        // ... on its own stream, beside the next batch's kernels

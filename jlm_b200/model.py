@@ -151,13 +151,18 @@ class LSTM_Model(object):
             self._lib.jlm_destroy(h)
             self._handle = None
 
-    def set_guard(self, eps, verify=True):
+    def set_guard(self, eps, verify=True, scope='output'):
         """Near-tie guard of the tensor-core back end (jlm_set_guard): rank decisions that rest on a score gap below
         `eps` are re-scored in float64 and, if contradicted, their sentence is re-decoded in float64.  eps = 0
         switches it off, a negative value restores the default; verify=False skips the re-scoring tier and
-        re-decodes every flagged sentence."""
+        re-decodes every flagged sentence; scope='output' guards the decisions that can change the returned n-best
+        (kept/rejected boundary of every frame, order of the last frame), scope='all' every adjacent pair of every
+        frame (the per-frame traces too)."""
+        if scope not in ('output', 'all'):
+            raise ValueError("scope must be 'output' or 'all'")
         _lib.check(self._lib.jlm_set_guard(self._handle, float(eps)))
         _lib.check(self._lib.jlm_set_guard_verify(self._handle, 1 if verify else 0))
+        _lib.check(self._lib.jlm_set_guard_scope(self._handle, 1 if scope == 'all' else 0))
 
     def _load_model(self, experiment_id=0, comp=0):
         # decoder/model.py:73-104 (comp>0 loads the already-decoded k-means pickle, quirk 11)

@@ -41,6 +41,7 @@ def get_decoder(name, tmp_path_factory):
         config.set_root(str(root))
         cls = jlm_b200.DynamicDecoder if case.get('dynamic') else jlm_b200.Decoder
         dec = cls(1)
+        dec.model.set_guard(-1.0, scope='all')     # the per-frame traces are compared too: certify every rank decision
         dec._want_trace = True
         _decoders[name] = (dec, case, sentences)
     return _decoders[name]
@@ -501,7 +502,7 @@ def test_near_tie_guard_reruns_flagged_sentences_in_float64(tmp_path_factory):
     try:
         want = dec.decode_batch(sents, topN=5, beam_width=5, backend=EXACT, native_lattice=False)
         want_trace = dec._last_batch_trace
-        m.set_guard(1e9, verify=False)                                   # every sentence flagged -> float64 re-decode
+        m.set_guard(1e9, verify=False, scope='all')                                 # every sentence flagged -> float64 re-decode
         got = dec.decode_batch(sents, topN=5, beam_width=5, backend=TC, native_lattice=False)
         info = dec.last_info
         assert info.n_guard_flagged == len(sents) and info.n_guard_rerun == len(sents) and info.guard_eps == 1e9
@@ -515,7 +516,7 @@ def test_near_tie_guard_reruns_flagged_sentences_in_float64(tmp_path_factory):
         assert dec.last_info.n_guard_flagged == len(sents)
         # tier 1 on: the near-tied pairs are re-scored in float64 (LM state pool) and confirmed pair by pair; with a
         # bound this loose some sentences overflow the record queue (-> re-decode)
-        m.set_guard(5e-3, verify=True)
+        m.set_guard(5e-3, verify=True, scope='all')
         got = dec.decode_batch(sents, topN=5, beam_width=5, backend=TC)
         info = dec.last_info
         assert 0 < info.n_guard_flagged <= len(sents) and info.n_guard_pairs > 0
@@ -542,11 +543,11 @@ def test_near_tie_guard_reruns_flagged_sentences_in_float64(tmp_path_factory):
         kw = dict(dcase['decode_kwargs'])
         dd._want_trace = False
         wantd = dd.decode_batch(sents[:64], backend=EXACT, **kw)
-        dd.model.set_guard(1e9)                                          # vocabulary-selection modes: tier 2 only
+        dd.model.set_guard(1e9, scope='all')                               # vocabulary-selection modes: tier 2 only
         assert dd.decode_batch(sents[:64], backend=TC, **kw) == wantd
         assert dd.last_info.n_guard_flagged == 64 and dd.last_info.n_guard_rerun == 64
-        dd.model.set_guard(-1.0)
+        dd.model.set_guard(-1.0, scope='all')
         dd._want_trace = True
     finally:
-        m.set_guard(-1.0)
+        m.set_guard(-1.0, scope='all')
         dec._want_trace = True

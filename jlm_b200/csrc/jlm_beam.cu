@@ -721,13 +721,22 @@ __global__ void k_backtrace(BeamDev d, int S, int topN, int max_len) {
 }
 
 // static vocab_select: one warp per LM row, LSE over the sentence's lattice_vocab logits.
+// logit j of a job row: the first n_shared columns live in the dense shared block (float32), the rest in the job's own
+struct RowLogits {
+  const double* p;
+  const float* y0;
+  int n_shared;
+  __device__ __forceinline__ double operator[](int j) const { return j < n_shared ? (double)y0[j] : p[j]; }
+};
+
 __global__ void __launch_bounds__(128)
-k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv, double* __restrict__ lse_out) {
+k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv, double* __restrict__ lse_out,
+               const float* __restrict__ y0, int ldy0, int n_shared) {
   const SubsetJob job = jobs[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= job.rows) return;
-  const double* p = yv + job.out0 + (int64_t)r * job.ncols;
+  const RowLogits p{yv + job.out0 + (int64_t)r * job.ncols, y0 + (job.row0 + r) * ldy0, n_shared};
   double mx = -INFINITY;
   for (int j = lane; j < job.ncols; j += 32) mx = fmax(mx, p[j]);
 #pragma unroll
@@ -748,13 +757,14 @@ constexpr int DYN_CAP = 1024;   // columns of a sentence's cumulative word list 
 __global__ void __launch_bounds__(128)
 k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restrict__ info,
                  const int32_t* __restrict__ vfp, const double* __restrict__ yv, double* __restrict__ dyn_lse,
-                 double* dyn_chain, const int32_t* __restrict__ slot_parent, int64_t slot_base, int k, int tstride) {
+                 double* dyn_chain, const int32_t* __restrict__ slot_parent, int64_t slot_base, int k, int tstride,
+                 const float* __restrict__ y0, int ldy0, int n_shared, int fast_exp) {
   const SubsetJob job = jobs[blockIdx.y];
   const DynJobInfo inf = info[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= job.rows) return;
-  const double* p = yv + job.out0 + (int64_t)r * job.ncols;
+  const RowLogits p{yv + job.out0 + (int64_t)r * job.ncols, y0 + (job.row0 + r) * ldy0, n_shared};
   const int64_t slot = slot_base + job.row0 + r;
   const int par = slot_parent[slot];
   // Fast path: one maximum over every column the row will ever be scored under, then ONE pass of
@@ -773,16 +783,19 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
       for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) gmax = fmax(gmax, p[j]);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    // tensor-core back end: the logits are float32-accurate, so exp(y - max) is taken with the float32 exp2 (relative
+    // error 1e-7, against 1e-6 in the logits themselves) and only summed in float64
+    auto ex = [&](double d) { return fast_exp ? (double)exp2f((float)(d * 1.4426950408889634)) : exp(d); };
     double sdup = 0.0;
     if (dup) {
-      for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) sdup += exp(p[j] - gmax);
+      for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) sdup += ex(p[j] - gmax);
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) sdup += __shfl_xor_sync(0xffffffffu, sdup, o);
     }
     double carry = 0.0;
     for (int base = 0; base < n_all; base += 32) {
       const int j = base + lane;
-      double e = j < n_all ? exp(p[j] - gmax) : 0.0;
+      double e = j < n_all ? ex(p[j] - gmax) : 0.0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const double up = __shfl_up_sync(0xffffffffu, e, o);
@@ -1112,6 +1125,17 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
       for (int s = 0; s < S; ++s) tot += lat->sent_len[s] + 2;
       P.vfp.assign(lat->vocab_frame_ptr, lat->vocab_frame_ptr + tot);
     }
+    // longest prefix of word ids common to all sentences' lists
+    int64_t shared = lat->vocab_ptr[1] - lat->vocab_ptr[0];
+    const int32_t* first = lat->vocab_ids + lat->vocab_ptr[0];
+    for (int s = 1; s < S && shared > 0; ++s) {
+      const int32_t* ids = lat->vocab_ids + lat->vocab_ptr[s];
+      const int64_t n = std::min<int64_t>(shared, lat->vocab_ptr[s + 1] - lat->vocab_ptr[s]);
+      int64_t k = 0;
+      while (k < n && ids[k] == first[k]) ++k;
+      shared = k;
+    }
+    b->n_shared = (S >= 8 && shared >= 32) ? (int)std::min<int64_t>(shared, 1024) : 0;
   }
   int64_t job = 0;
   for (int t = 0; t < b->n_steps; ++t) {
@@ -1248,11 +1272,13 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
       JLM_TRY(subset_logits<TT>(st, h, T, ldt, d.vocab_jobs + sp.job0, sp.nstep, sp.max_vocab_cols, d.vocab_cols, nullptr,
                                 b->yv));
     dim3 grid(ceil_div(b->W, 4), sp.nstep);
+    const int ns = (on_tc == 0) ? b->n_shared : 0;      // the shared block exists only when the tensor-core kernel ran
     if (b->dynamic)
       k_dyn_prefix_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse,
-                                             d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1);
+                                             d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1, b->y0, b->ldy0, ns,
+                                             on_tc == 0 ? 1 : 0);
     else
-      k_job_rows_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0);
+      k_job_rows_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0, b->y0, b->ldy0, ns);
     JLM_CUDA(cudaGetLastError());
     b->launches += 2;
   }
@@ -1446,6 +1472,17 @@ static void guard_drop_rerun(jlm_batch* b) {
   b->n_flagged = b->n_pairs = b->n_rerun = 0;
 }
 
+// The guard's float64 work runs beside the NEXT batch's kernels (a streaming caller has already enqueued them on the
+// main stream): its own stream, at the highest priority, so that its short dependent kernels are picked ahead of the
+// next long tensor-core kernel whenever SMs free up instead of queueing behind the whole batch.
+static int32_t guard_stream_create(jlm_handle* h) {
+  if (h->guard_stream) return 0;
+  int lo = 0, hi = 0;
+  JLM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi is the numerically lowest = highest priority
+  JLM_CUDA(cudaStreamCreateWithPriority(&h->guard_stream, cudaStreamNonBlocking, hi));
+  return 0;
+}
+
 // Tier 1 of the near-tie guard: re-score the two paths of every queued rank decision in float64.
 // A path's score depends on its word sequence only (Path.append_node, decoder.py:43-49: sum of -log softmax along
 // the path), so all paths of all sentences go into ONE trie of word prefixes; each trie node is a state of the
@@ -1472,7 +1509,16 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
   struct Query { int node, word; };                 // -log p(word | state of trie node)
   std::vector<Query> queries;
   std::unordered_map<uint64_t, int> qindex;
-  struct PathRef { std::vector<int> q; };
+  // Vocabulary-selection modes: the softmax of a state runs over a word list that depends on the sentence (static:
+  // its lattice_vocab, decoder.py:137-151) and, for DynamicDecoder, on the frame the candidate ends at (every
+  // transition of a path is re-normalised over lattice_vocab[t], decoder_dynamic.py:150-175) - one log-sum-exp
+  // request per (state, sentence, frame).
+  const bool subset = b->mode != JLM_DECODE_FULL;
+  struct LseReq { int node, sent, frame; };
+  std::vector<LseReq> reqs;
+  std::unordered_map<uint64_t, int> rindex;
+  auto req_key = [&](int node, int p, int t) { return ((uint64_t)(uint32_t)node << 40) ^ ((uint64_t)(uint32_t)p << 12) ^ (uint64_t)(uint32_t)t; };
+  struct PathRef { std::vector<int> q; std::vector<int> lse; };
   std::vector<PathRef> refs((size_t)2 * n_rec);
   std::vector<char> need_lse;                       // per trie node
   for (int r = 0; r < n_rec; ++r) {
@@ -1503,10 +1549,22 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
             queries.push_back(Query{node, w});
           }
           pr.q.push_back(it->second);
-          if (j > common) {
-            if ((int)need_lse.size() < (int)trie.size()) need_lse.resize(trie.size(), 0);
-            need_lse[node] = 1;
+          int req = -1;
+          if (j > common && b->use_lse) {
+            if (subset) {
+              const uint64_t rk = req_key(node, rec[r].x, rec[r].y);
+              auto rt = rindex.find(rk);
+              if (rt == rindex.end()) {
+                rt = rindex.emplace(rk, (int)reqs.size()).first;
+                reqs.push_back(LseReq{node, rec[r].x, rec[r].y});
+              }
+              req = rt->second;
+            } else {
+              if ((int)need_lse.size() < (int)trie.size()) need_lse.resize(trie.size(), 0);
+              need_lse[node] = 1;
+            }
           }
+          pr.lse.push_back(req);
         }
         if (j + 1 < len) node = child(node, w);     // the last word's state is never consumed
       }
@@ -1525,7 +1583,7 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
     for (int r = 0; r < n_rec; ++r) need_full[rec[r].x] = 1;
     return 0;
   }
-  if (!h->guard_stream) JLM_CUDA(cudaStreamCreateWithFlags(&h->guard_stream, cudaStreamNonBlocking));
+  JLM_TRY(guard_stream_create(h));
   if (!h->guard_pool) JLM_TRY(jlm_pool_create(h, POOL_CAP, &h->guard_pool));
   // the pool works on the handle's stream: lend it the guard stream for the duration of the check
   cudaStream_t main_stream = h->stream;
@@ -1547,12 +1605,29 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
     rc = pool_step_rows(h->guard_pool, (int32_t)src.size(), src.data(), idx.data(), &first, false);
     for (size_t k = 0; k < by_depth[dpt].size(); ++k) trie[by_depth[dpt][k]].slot = first + (int64_t)k;
   }
-  {
+  std::vector<double> req_lse(reqs.size(), 0.0);
+  if (!subset) {
     std::vector<int32_t> lse_slots;
     for (size_t i = 0; i < trie.size(); ++i)
       if (need_lse[i]) lse_slots.push_back((int32_t)trie[i].slot);
     if (!rc && !lse_slots.empty()) rc = pool_lse_slots(h->guard_pool, lse_slots.data(), (int32_t)lse_slots.size());
     b->n_lse_rows = (int)lse_slots.size();
+  } else if (!reqs.empty()) {
+    std::vector<int32_t> rslots(reqs.size()), rcols;
+    std::vector<int64_t> rptr(reqs.size() + 1, 0);
+    for (size_t i = 0; i < reqs.size(); ++i) {
+      const int s = b->order[reqs[i].sent];
+      const int32_t* ids = &G.vocab_ids[G.vocab_ptr[s]];
+      int64_t n_list = G.vocab_ptr[s + 1] - G.vocab_ptr[s];
+      if (b->dynamic) n_list = G.vocab_frame_ptr[G.frame_ptr_off[s] + reqs[i].frame + 1];   // lattice_vocab[frame]
+      rcols.insert(rcols.end(), ids, ids + n_list);
+      if (b->dynamic && trie[reqs[i].node].depth == 0)      // the <eos> row also counts lattice_vocab[0]'s duplicates (quirk 4)
+        rcols.insert(rcols.end(), G.dup_ids.begin() + G.dup_ptr[s], G.dup_ids.begin() + G.dup_ptr[s + 1]);
+      rslots[i] = (int32_t)trie[reqs[i].node].slot;
+      rptr[i + 1] = (int64_t)rcols.size();
+    }
+    if (!rc) rc = pool_lse_subsets(h->guard_pool, (int32_t)reqs.size(), rslots.data(), rptr.data(), rcols.data(), req_lse.data());
+    b->n_lse_rows = (int)reqs.size();
   }
   std::vector<int32_t> qs(queries.size()), qw(queries.size());
   std::vector<double> nll(queries.size());
@@ -1568,7 +1643,8 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
     double sc[2];
     for (int which = 0; which < 2; ++which) {
       double v = 0.0;                               // Path.__init__: neg_log_prob = 0, then += per node (decoder.py:34,49)
-      for (int q : refs[(size_t)2 * r + which].q) v += nll[q];
+      const PathRef& pr = refs[(size_t)2 * r + which];
+      for (size_t k = 0; k < pr.q.size(); ++k) v += nll[pr.q[k]] + (pr.lse[k] >= 0 ? req_lse[pr.lse[k]] : 0.0);
       sc[which] = v;
     }
     b->n_pairs += 1;
@@ -1598,13 +1674,13 @@ static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
   for (int p = 0; p < b->S; ++p) {
     mg = std::min(mg, gap[p]);
     if (flag[p]) b->n_flagged += 1;
-    if ((flag[p] & 2) || (flag[p] && b->mode != JLM_DECODE_FULL)) need_full[p] = 1;
+    if (flag[p] & 2) need_full[p] = 1;
   }
   b->min_gap = mg;
   if (b->n_flagged == 0) return 0;
   static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
   const auto t_0 = std::chrono::steady_clock::now();
-  if (b->mode == JLM_DECODE_FULL && b->h->guard_verify) {
+  if (b->h->guard_verify) {
     JLM_TRY(guard_verify_pairs(b, n_rec, rec, paths, need_full));
     if (dbg)
       fprintf(stderr, "[jlm] guard: %d sentences flagged, %d records, %d pairs re-scored, %d lse rows, %.3f ms\n", b->n_flagged,
@@ -1622,18 +1698,27 @@ static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
   std::sort(which.begin(), which.end());
   GuardLattice& G = *b->guard_lat;
   const jlm_lattice_batch sub = G.subset(which, b->mode);
+  // tier 2 on the guard stream as well: on the main stream it would wait behind every batch already enqueued
+  jlm_handle* h = b->h;
+  JLM_TRY(guard_stream_create(h));
+  cudaStream_t main_stream = h->stream;
+  h->stream = h->guard_stream;
   jlm_batch* r = nullptr;
-  JLM_TRY(jlm_batch_upload(b->h, &sub, b->unlimited ? JLM_BEAM_UNLIMITED : b->W, b->topN, b->mode, JLM_BACKEND_EXACT, &r));
+  int32_t rc = jlm_batch_upload(h, &sub, b->unlimited ? JLM_BEAM_UNLIMITED : b->W, b->topN, b->mode, JLM_BACKEND_EXACT, &r);
   b->rerun = r;
-  JLM_TRY(jlm_batch_run(r));
-  const size_t n = which.size() * (size_t)r->topN;
-  G.r_max_len = r->max_len;
-  G.r_score.resize(n);
-  G.r_npaths.resize(which.size());
-  G.r_len.resize(n);
-  G.r_nodes.resize(n * r->max_len);
-  jlm_nbest nb{r->topN, r->max_len, G.r_score.data(), G.r_npaths.data(), G.r_len.data(), G.r_nodes.data()};
-  JLM_TRY(jlm_batch_fetch(r, &nb));
+  if (!rc) rc = jlm_batch_run(r);
+  if (!rc) {
+    const size_t n = which.size() * (size_t)r->topN;
+    G.r_max_len = r->max_len;
+    G.r_score.resize(n);
+    G.r_npaths.resize(which.size());
+    G.r_len.resize(n);
+    G.r_nodes.resize(n * r->max_len);
+    jlm_nbest nb{r->topN, r->max_len, G.r_score.data(), G.r_npaths.data(), G.r_len.data(), G.r_nodes.data()};
+    rc = jlm_batch_fetch(r, &nb);
+  }
+  h->stream = main_stream;
+  if (rc) return rc;
   for (size_t k = 0; k < which.size(); ++k) b->rerun_index[which[k]] = (int)k;
   return 0;
 }

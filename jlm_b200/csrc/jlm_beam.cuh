@@ -112,6 +112,12 @@ struct jlm_batch {
   int64_t F = 0, N = 0, n_slots = 0, n_cand = 0, n_jobs = 0;
   int max_rows_step = 0;
   int64_t max_yv = 0;
+  // Vocabulary-selection modes: the first n_shared entries of EVERY sentence's word list are the same ids (the
+  // `samples` top words of top_sampling, decoder.py:144-149 / decoder_dynamic.py:37-43): their logits come from one
+  // dense tensor-core GEMM per step (y0, row stride ldy0, float32, bias included) instead of a gather per sentence.
+  int n_shared = 0;
+  const float* y0 = nullptr;
+  int ldy0 = 0;
   int max_len = 0;
   DevBuf mem;
   BeamDev d;

@@ -236,6 +236,7 @@ void beam_free_guard(jlm_handle* h);          // jlm_beam.cu: the near-tie verif
 int32_t pool_step_rows(jlm_pool* p, int32_t n, const int32_t* src, const int32_t* index, int64_t* first_slot, bool with_lse);
 int32_t pool_lse_rows(jlm_pool* p, int64_t first, int64_t count);
 int32_t pool_lse_slots(jlm_pool* p, const int32_t* slots, int32_t n);
+int32_t pool_lse_subsets(jlm_pool* p, int32_t n, const int32_t* slots, const int64_t* col_ptr, const int32_t* cols, double* out);
 
 // ---------------------------------------------------------------- tensor-core back end (jlm_tc.cu)
 int32_t tc_prepare_weights(jlm_handle* h);

@@ -5,6 +5,8 @@
 // here.  These kernels are weight-streaming (HBM/L2 bound): every weight element is read once per
 // LM step and used for all rows of the step.  Large lock-step batches use the tensor-core back end
 // (jlm_tc.cu); this one doubles as its on-device float64 cross-check.
+#include <algorithm>
+
 #include "jlm_common.cuh"
 
 namespace {
@@ -229,6 +231,131 @@ k_skinny_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, in
       for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
       if (lane == 0) part[(int64_t)m * part_ld + part_tile0 + blockIdx.x] = make_double2(mx, sm);
     }
+  }
+}
+
+// Weight-streaming GEMM for few rows, float32 weights with K <= 256 (the output blocks: K = E or a D-softmax segment
+// width) - the kernel behind single-sentence latency, the near-tie guard's float64 re-scoring and its re-decodes.
+// k_skinny_f64 reads a weight row per LANE (32 different 128-byte lines per load instruction), which holds it to
+// ~1 TB/s out of an L2-resident block.  Here a persistent CTA copies whole 64-column weight tiles into shared
+// memory with cp.async - every warp reads 512 contiguous bytes of ONE weight row, 16-byte pieces stored XOR-swizzled
+// by row so that the per-column reads below are conflict-free - double-buffered: tile i+1 lands while tile i is
+// multiplied.  Compute as before: thread = 2 columns x one K slice, all rows accumulate in float64 registers against
+// broadcast reads of A; the K slices are summed through shared memory in a fixed order; 64-column (max, sum exp)
+// partials for the log-sum-exp.  Same products, same summation order as k_skinny_f64<.., 64, 2, KG=4>.
+constexpr int ST_COLS = 64;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MT, int ST_KG>
+__global__ void __launch_bounds__(32 * ST_KG)
+k_stream_f64(const double* __restrict__ A, int lda, const float* __restrict__ B, int ldb, const float* __restrict__ bias,
+             double* __restrict__ C, int64_t ldc, int M, int N, int K, double2* __restrict__ part, int part_ld,
+             int part_tile0) {
+  constexpr int ST_THREADS = 32 * ST_KG;
+  extern __shared__ __align__(128) unsigned char smem_st[];
+  const int tile_bytes = ST_COLS * K * 4;
+  float* Wt[2] = {reinterpret_cast<float*>(smem_st), reinterpret_cast<float*>(smem_st + tile_bytes)};
+  double* As = reinterpret_cast<double*>(smem_st + 2 * tile_bytes);   // [M][K]
+  double* Ps = As + (size_t)M * K;                                    // [KG][MT][COLS]
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int n_tiles = (N + ST_COLS - 1) / ST_COLS;
+  const int cpr = K / 4;                                              // 16-byte pieces per weight row
+  auto issue = [&](int tile, float* dst) {
+    // piece j of column c goes to c*K*4 + (j & ~7 | (j ^ c) & 7) * 16: lanes reading piece j of 8 consecutive columns
+    // then touch 8 different 16-byte bank groups
+    const int n0 = tile * ST_COLS;
+    for (int c = g; c < ST_COLS; c += ST_KG) {                        // a warp copies whole weight rows
+      const float* src = B + (int64_t)min(n0 + c, N - 1) * ldb;       // columns past N repeat the last row; never stored
+      char* drow = reinterpret_cast<char*>(dst) + (size_t)c * K * 4;
+      for (int j = lane; j < cpr; j += 32) cp_async16(drow + (((j & ~7) | ((j ^ c) & 7)) << 4), src + j * 4);
+    }
+    cp_async_commit();
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles) issue(tile, Wt[0]);
+  for (int i = tid * 2; i < M * K; i += ST_THREADS * 2) {
+    const int m = i / K, k = i % K;
+    *reinterpret_cast<double2*>(&As[i]) = *reinterpret_cast<const double2*>(A + (int64_t)m * lda + k);
+  }
+  const int kq = K / ST_KG;                                           // this thread's K slice [g*kq, (g+1)*kq)
+  int buf = 0;
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) {
+      issue(next, Wt[buf ^ 1]);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                                                  // tile (and, first time, A) visible to all
+    double acc[2][MT];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) acc[j][m] = 0.0;
+    const char* w0 = reinterpret_cast<const char*>(Wt[buf]) + (size_t)lane * K * 4;
+    const char* w1 = w0 + (size_t)32 * K * 4;                         // column lane + 32: same (c & 7)
+    const double* arow = As + g * kq;
+    for (int k = 0; k < kq; k += 4) {
+      const int j = (g * kq + k) >> 2;
+      const int off = ((j & ~7) | ((j ^ lane) & 7)) << 4;
+      const float4 a0 = *reinterpret_cast<const float4*>(w0 + off);
+      const float4 a1 = *reinterpret_cast<const float4*>(w1 + off);
+      const double w[2][4] = {{(double)a0.x, (double)a0.y, (double)a0.z, (double)a0.w},
+                              {(double)a1.x, (double)a1.y, (double)a1.z, (double)a1.w}};
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+#pragma unroll
+          for (int i = 0; i < 4; i += 2) {
+            const double2 a2 = *reinterpret_cast<const double2*>(arow + m * K + k + i);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              acc[jj][m] = fma(a2.x, w[jj][i], acc[jj][m]);
+              acc[jj][m] = fma(a2.y, w[jj][i + 1], acc[jj][m]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) Ps[(g * MT + m) * ST_COLS + lane + 32 * j] = acc[j][m];
+    __syncthreads();
+    for (int i = tid; i < M * ST_COLS; i += ST_THREADS) {
+      const int m = i / ST_COLS, cc = i % ST_COLS;
+      const int nn = tile * ST_COLS + cc;
+      double v = -INFINITY;
+      if (nn < N) {
+        v = 0.0;
+#pragma unroll
+        for (int q = 0; q < ST_KG; ++q) v += Ps[(q * MT + m) * ST_COLS + cc];
+        if (bias) v += (double)bias[nn];
+        if (C) C[(int64_t)m * ldc + nn] = v;
+      }
+      Ps[m * ST_COLS + cc] = v;                                       // slice 0's slot of (m, cc): read by no other thread before the sync
+    }
+    if (part) {
+      __syncthreads();
+      for (int m = g; m < M; m += ST_KG) {                            // one warp per row: 64 columns, 2 per lane
+        const double v0 = Ps[m * ST_COLS + lane], v1 = Ps[m * ST_COLS + 32 + lane];
+        double mx = fmax(v0, v1);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double sm = (v0 == -INFINITY ? 0.0 : exp(v0 - mx)) + (v1 == -INFINITY ? 0.0 : exp(v1 - mx));
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        if (lane == 0) part[(int64_t)m * part_ld + part_tile0 + tile] = make_double2(mx, sm);
+      }
+    }
+    __syncthreads();                                                  // Ps and Wt[buf] are free for the next round
   }
 }
 
@@ -460,11 +587,64 @@ bool skinny_ok(int M, int K) {
   return M >= 1 && M <= 16 && K % 128 == 0 && ((size_t)M * K + 16 * 16 * 32 + 256) * sizeof(double) <= 200 * 1024;
 }
 
+// k_stream_f64 for up to 16 rows; more rows go through it 16 at a time (the weight block is L2-resident: re-streaming
+// it per chunk beats the register-tiled k_gemm_f64 up to a few hundred rows)
+template <int MT>
+int32_t launch_stream_mt(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias, double* C,
+                         int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0, int sm_count) {
+  // eight K slices (eight warps) while their partial sums fit beside the two weight tiles and A; four for 16 rows
+  constexpr int KG = (MT <= 12) ? 8 : 4;
+  static bool configured = false;
+  if (!configured) {
+    JLM_CUDA(cudaFuncSetAttribute(k_stream_f64<MT, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  const size_t smem = (size_t)2 * ST_COLS * K * 4 + ((size_t)M * K + (size_t)KG * MT * ST_COLS) * sizeof(double);
+  const int grid = std::min(ceil_div(N, ST_COLS), sm_count);
+  k_stream_f64<MT, KG><<<grid, 32 * KG, smem, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  JLM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool stream_ok(int M, int N, int K) {
+  static const int on = [] {
+    const char* e = getenv("JLM_STREAM_GEMM");
+    return e ? atoi(e) : 1;
+  }();
+  return on && M >= 1 && M <= 512 && K <= 256 && K % 64 == 0 && N >= 1024;      // K / 8 slices of whole 16-byte pieces
+}
+
+int32_t launch_stream(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias, double* C,
+                      int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    const int mc = std::min(16, M - m0);
+    const double* Ac = A + (int64_t)m0 * lda;
+    double* Cc = C ? C + (int64_t)m0 * ldc : nullptr;
+    double2* pc = part ? part + (int64_t)m0 * part_ld : nullptr;
+    if (mc <= 4) JLM_TRY(launch_stream_mt<4>(st, Ac, lda, B, ldb, bias, Cc, ldc, mc, N, K, pc, part_ld, part_tile0, sm_count));
+    else if (mc <= 8) JLM_TRY(launch_stream_mt<8>(st, Ac, lda, B, ldb, bias, Cc, ldc, mc, N, K, pc, part_ld, part_tile0, sm_count));
+    else if (mc <= 12) JLM_TRY(launch_stream_mt<12>(st, Ac, lda, B, ldb, bias, Cc, ldc, mc, N, K, pc, part_ld, part_tile0, sm_count));
+    else JLM_TRY(launch_stream_mt<16>(st, Ac, lda, B, ldb, bias, Cc, ldc, mc, N, K, pc, part_ld, part_tile0, sm_count));
+  }
+  return 0;
+}
+
 template <typename TB>
 int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* bias, double* C,
                     int64_t ldc, int M, int N, int K, double2* part, int part_ld, int part_tile0) {
   JLM_REQUIRE(K % BK == 0 && lda % 2 == 0 && ldb % 4 == 0, "exact gemm: unaligned K=%d lda=%d ldb=%d", K, lda, ldb);
   if (M <= 0 || N <= 0) return 0;
+  if constexpr (sizeof(TB) == 4) {
+    if (stream_ok(M, N, K))
+      return launch_stream(st, A, lda, reinterpret_cast<const float*>(B), ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  }
   if (skinny_ok(M, K)) {
     // weight-streaming path for one sentence's rows
     JLM_TRY(skinny_dispatch<TB>(st, A, lda, B, ldb, nullptr, bias, C, ldc, M, N, K, part, part_ld, part_tile0));

@@ -62,6 +62,50 @@ __global__ void k_pool_scatter_lse(const double* __restrict__ tmp, const int32_t
   if (i < n) lse[slots[i]] = tmp[i];
 }
 
+// log-sum-exp of a state's logits over an explicit word list (vocabulary-selection modes: the softmax runs over the
+// sentence's lattice_vocab, decoder.py:137-151 / decoder_dynamic.py:93-148).  One CTA per request; a warp per word
+// (float64 dot against the stage-1 row), online (max, sum) per warp, merged through shared memory.
+__global__ void __launch_bounds__(128)
+k_pool_lse_subset(SegTable seg, const double* __restrict__ T, int64_t ldt, const float* __restrict__ b2,
+                  const int32_t* __restrict__ slots, const int64_t* __restrict__ col_ptr, const int32_t* __restrict__ cols,
+                  double* __restrict__ out) {
+  __shared__ double wm[4], ws[4];
+  const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c0 = col_ptr[r], c1 = col_ptr[r + 1];
+  const double* trow0 = T + (int64_t)slots[r] * ldt;
+  double mx = -INFINITY, sm = 0.0;
+  for (int64_t c = c0 + warp; c < c1; c += 4) {
+    const int w = cols[c];
+    int sg = 0;
+#pragma unroll
+    for (int k = 1; k < JLM_MAX_SEGMENTS; ++k)
+      if (k < seg.n && w >= seg.start[k]) sg = k;
+    const int kpad = seg.kpad[sg];
+    const float* wrow = seg.W[sg] + (int64_t)(w - seg.start[sg]) * kpad;
+    const double* trow = trow0 + seg.koff[sg];
+    double acc = 0.0;
+    for (int k = lane; k < kpad; k += 32) acc = fma(trow[k], (double)wrow[k], acc);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double y = acc + (double)b2[w];
+    const double nm = fmax(mx, y);
+    sm = sm * exp(mx - nm) + exp(y - nm);
+    mx = nm;
+  }
+  if (lane == 0) {
+    wm[warp] = mx;
+    ws[warp] = sm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = fmax(fmax(wm[0], wm[1]), fmax(wm[2], wm[3]));
+    double t = 0.0;
+    for (int k = 0; k < 4; ++k)
+      if (wm[k] > -INFINITY) t += ws[k] * exp(wm[k] - m);
+    out[r] = m + log(t);
+  }
+}
+
 }  // namespace
 
 extern "C" int32_t jlm_pool_create(jlm_handle* h, int64_t capacity, jlm_pool** out) {
@@ -160,7 +204,28 @@ int32_t pool_lse_slots(jlm_pool* p, const int32_t* slots, int32_t n) {
   JLM_TRY(exact_lse_merge(st, part, p->tiles, p->tiles, n, lse_tmp, 0));
   k_pool_scatter_lse<<<ceil_div(n, 256), 256, 0, st>>>(lse_tmp, d_slots, n, p->lse);
   JLM_CUDA(cudaGetLastError());
-  JLM_CUDA(cudaStreamSynchronize(st));      // d_slots (p->idx) is reused by the next call
+  return 0;      // asynchronous: later users of p->idx / p->G enqueue behind these kernels on the same stream
+}
+
+// out[r] = log-sum-exp over the words cols[col_ptr[r] .. col_ptr[r+1]) of the logits of the state in slots[r] (host arrays)
+int32_t pool_lse_subsets(jlm_pool* p, int32_t n, const int32_t* slots, const int64_t* col_ptr, const int32_t* cols, double* out) {
+  jlm_handle* h = p->h;
+  if (n <= 0) return 0;
+  cudaStream_t st = h->stream;
+  const int64_t nc = col_ptr[n];
+  JLM_TRY(p->G.reserve(sizeof(int64_t) * (size_t)(n + 1) + sizeof(int32_t) * (size_t)(n + nc) + sizeof(double) * (size_t)n + 64));
+  char* base = p->G.as<char>();
+  int64_t* d_ptr = reinterpret_cast<int64_t*>(base);
+  double* d_out = reinterpret_cast<double*>(base + sizeof(int64_t) * (size_t)(n + 1));
+  int32_t* d_slots = reinterpret_cast<int32_t*>(d_out + n);
+  int32_t* d_cols = d_slots + n;
+  JLM_CUDA(cudaMemcpyAsync(d_ptr, col_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+  JLM_CUDA(cudaMemcpyAsync(d_slots, slots, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  JLM_CUDA(cudaMemcpyAsync(d_cols, cols, sizeof(int32_t) * (size_t)nc, cudaMemcpyHostToDevice, st));
+  k_pool_lse_subset<<<n, 128, 0, st>>>(make_seg_table(h), p->T, p->ldt, h->b2, d_slots, d_ptr, d_cols, d_out);
+  JLM_CUDA(cudaGetLastError());
+  JLM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  JLM_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -201,8 +266,10 @@ int32_t pool_step_rows(jlm_pool* p, int32_t n, const int32_t* src, const int32_t
   if (!h->untied) JLM_TRY(exact_gemm_f64w(st, hrow, h->Hp, h->P1, h->Hp, p->T + s0 * h->Kt, h->Kt, n, h->Kt, h->Hp));
   if (with_lse) JLM_TRY(pool_lse_rows(p, s0, n));
   else JLM_CUDA(cudaMemsetAsync(p->lse + s0, 0, sizeof(double) * (size_t)n, st));   // "no normaliser": jlm_pool_nll returns -y
-  // the index staging buffer is reused by the next call: order it behind this one's kernels
-  JLM_CUDA(cudaStreamSynchronize(st));
+  // Public entry: return with the step finished.  The verifier's chain of steps (with_lse = false) stays asynchronous:
+  // the index copies above are in stream order behind the kernels that read the previous indices, the host arrays are
+  // pageable (staged before cudaMemcpyAsync returns), and jlm_pool_nll synchronises at the end of the chain.
+  if (with_lse) JLM_CUDA(cudaStreamSynchronize(st));
   p->used += n;
   *first_slot = s0;
   return 0;

@@ -523,6 +523,265 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-stationary output GEMM + online log-sum-exp for SHORT K (D-softmax* tail segments, K = 64 / 128).
+//
+// With K = 64 a 256 x 256 tile is 12 MMAs (1536 cycles) but needs 128 KB of operands: fed tile by tile
+// (k_tc_gemm) the pair asks L2 for 64 B/clk, the chip for ~8 TB/s - the segment is L2-bound, not tensor-bound.
+// Here a CTA pair owns a contiguous range of tiles in (row block, column block) order, keeps the A operand of
+// its current 256-row block RESIDENT in shared memory (32 KB per k-block per CTA) and streams only the weight
+// tiles through the ring, so the operand traffic per tile halves.  The epilogue warps own fixed rows, so the
+// running (max, sum exp) of a row also stays in registers across the column blocks of the run and one partial
+// per (row, run) is written instead of one per (row, tile): 392 -> 2..3 partials per row at V = 100k.
+// K is issued in 16-wide steps up to round_up(width, 16): the zero padding up to 64 is never multiplied.
+template <int KB>
+struct RsCfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = KB * 2 * A_TILE;                 // hi + lo, 128 rows x 64 per k-block
+  static constexpr int B_HALF = (BN / 2) * BK * 2;                // one k-block of this CTA's half of the N tile
+  static constexpr int B_STAGE = KB * 2 * B_HALF;
+  static constexpr int STAGES = (KB == 1) ? 4 : 2;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + BIAS_BYTES + BAR_BYTES + 1024;
+  // Eight epilogue warps, two per TMEM lane quarter (each takes half of the tile's columns): with one exp per logit
+  // the epilogue paces the short-K tiles, and a lone warp per scheduler leaves every TMEM-load and MUFU latency exposed.
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
+
+struct RsArgs {
+  int M, N, K16;            // K16: K rounded up to the MMA's 16
+  int num_m_units, num_n_blocks;
+  int a_row0;
+  float inv_scale;
+  const float* bias;
+  float2* part;
+  int part_ld, part_col0, n_slots;
+};
+
+template <int KB>
+__global__ void __launch_bounds__(RsCfg<KB>::THREADS, 1)
+k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+            const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const RsArgs g) {
+  using C = RsCfg<KB>;
+  constexpr int BN = C::BN;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), n_units = (int)(gridDim.x >> 1);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + C::A_BYTES;
+  float* bias_s = reinterpret_cast<float*>(gen + C::A_BYTES + C::STAGES * C::B_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + C::A_BYTES + C::STAGES * C::B_STAGE + C::BIAS_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 6);
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t afull_bar = bar0 + 8u * (2 * C::STAGES + 4), aempty_bar = bar0 + 8u * (2 * C::STAGES + 5);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&mAh);
+    ptx::prefetch_tensormap(&mAl);
+    ptx::prefetch_tensormap(&mBh);
+    ptx::prefetch_tensormap(&mBl);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < C::STAGES; ++s) {
+        ptx::mbar_init(full_bar(s), 1);
+        ptx::mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(tfull_bar(a), 1);
+        ptx::mbar_init(tempty_bar(a), 2 * C::EPI_WARPS);      // both CTAs' epilogue warps arrive on the leader's
+      }
+      ptx::mbar_init(afull_bar, 1);
+      ptx::mbar_init(aempty_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), 2 * BN);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  // this pair's contiguous tile range, tile id = m_unit * NT + n_blk
+  const int NT = g.num_n_blocks;
+  const int64_t T = (int64_t)g.num_m_units * NT;
+  const int t_lo = (int)(T * unit / n_units), t_hi = (int)(T * (unit + 1) / n_units);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int stage = 0, cur_m = -1;
+      uint32_t phase = 0, a_phase = 0;
+      for (int tile = t_lo; tile < t_hi; ++tile) {
+        const int m_unit = tile / NT, n_blk = tile - m_unit * NT;
+        if (m_unit != cur_m) {      // new row block: wait until the MMAs of the previous one have read A
+          ptx::mbar_wait(aempty_bar, a_phase ^ 1u);
+          a_phase ^= 1u;
+          if (rank == 0) ptx::mbar_expect_tx(afull_bar, 2 * C::A_BYTES);
+          const int row = g.a_row0 + (m_unit * 2 + (int)rank) * BM;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::tma_load_2d_pair(a_base + kb * 2 * A_TILE, &mAh, afull_bar, kb * BK, row);
+            ptx::tma_load_2d_pair(a_base + kb * 2 * A_TILE + A_TILE, &mAl, afull_bar, kb * BK, row);
+          }
+          cur_m = m_unit;
+        }
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::B_STAGE);
+        const uint32_t sb = b_base + stage * C::B_STAGE;
+        const int b_row = n_blk * BN + (int)rank * (BN / 2);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::tma_load_2d_pair(sb + kb * 2 * C::B_HALF, &mBh, full_bar(stage), kb * BK, b_row);
+          ptx::tma_load_2d_pair(sb + kb * 2 * C::B_HALF + C::B_HALF, &mBl, full_bar(stage), kb * BK, b_row);
+        }
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(2 * BM, BN);
+      int stage = 0, acc = 0, cur_m = -1;
+      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      for (int tile = t_lo; tile < t_hi; ++tile) {
+        const int m_unit = tile / NT;
+        if (m_unit != cur_m) {
+          ptx::mbar_wait(afull_bar, a_phase);
+          a_phase ^= 1u;
+          cur_m = m_unit;
+        }
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t sb = b_base + stage * C::B_STAGE;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            if (kb * BK + k * 16 < g.K16) {
+              const uint64_t ah = ptx::umma_desc_sw128(a_base + kb * 2 * A_TILE + k * 32);
+              const uint64_t al = ptx::umma_desc_sw128(a_base + kb * 2 * A_TILE + A_TILE + k * 32);
+              const uint64_t bh = ptx::umma_desc_sw128(sb + kb * 2 * C::B_HALF + k * 32);
+              const uint64_t bl = ptx::umma_desc_sw128(sb + kb * 2 * C::B_HALF + C::B_HALF + k * 32);
+              ptx::mma_f16_ss_pair(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss_pair(d_tmem, al, bh, idesc, 1u);
+              ptx::mma_f16_ss_pair(d_tmem, ah, bh, idesc, 1u);
+            }
+          }
+        }
+        ptx::tc_commit_pair(empty_bar(stage), 3);
+        // last tile of this row block in our range: once its MMAs are done the A operand may be overwritten
+        if (tile + 1 == t_hi || (tile + 1) / NT != m_unit) ptx::tc_commit_pair(aempty_bar, 3);
+        ptx::tc_commit_pair(tfull_bar(acc), 3);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps: online (max, sum exp) per row, carried across the run =====================
+    constexpr int ET = 32 * C::EPI_WARPS;
+    constexpr int HALF = BN / 2;
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;          // which half of the tile's columns
+    const int te = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float bnext = -INFINITY;
+    auto fetch_bias = [&](int tl) {
+      const int n = (tl % NT) * BN + te;
+      bnext = (n < g.N) ? (g.bias ? g.bias[n] : 0.f) : -INFINITY;
+    };
+    if (t_lo < t_hi) fetch_bias(t_lo);
+    float m_run = -INFINITY, c_run = -INFINITY, s_run = 0.f;
+    for (int tile = t_lo; tile < t_hi; ++tile) {
+      const int m_unit = tile / NT;
+      float* bs = bias_s + acc * BN;
+      bs[te] = bnext;
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      if (tile + 1 < t_hi) fetch_bias(tile + 1);
+      const uint32_t taddr = tmem_base + acc * BN + half * HALF + (static_cast<uint32_t>(q * 32) << 16);
+      const float* bh = bs + half * HALF;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      // TMEM loads are issued one 32-column chunk ahead of the math
+      uint32_t r[2][32];
+      ptx::tmem_ld_x32(taddr, r[0]);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int ch = 0; ch < HALF / 32; ++ch) {
+        if (ch + 1 < HALF / 32) ptx::tmem_ld_x32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+        uint32_t(&rc)[32] = r[ch & 1];
+        float v[32];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = fmaf(__uint_as_float(rc[j]), g.inv_scale, bh[ch * 32 + j]);
+          cm = fmaxf(cm, v[j]);
+        }
+        if (cm > -INFINITY) {
+          const float m_new = fmaxf(m_run, cm);
+          const float c_new = m_new * LOG2E;
+          s_run *= ex2_approx(c_run - c_new);      // ex2.approx.ftz: 2^-inf = 0, arguments below -126 flush to 0
+          float part = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += ex2_approx(fmaf(v[j], LOG2E, -c_new));
+          s_run += part;
+          m_run = m_new;
+          c_run = c_new;
+        }
+        if (ch + 1 < HALF / 32) ptx::tmem_ld_wait();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+      if (tile + 1 == t_hi || (tile + 1) / NT != m_unit) {
+        // end of this pair's run over the row block: one partial per (row, column half).  Slot = how many pairs before
+        // this one also work on the block; the pair that finishes the block neutralises the slots nobody writes.
+        const int row = (m_unit * 2 + (int)rank) * BM + q * 32 + lane;
+        const int64_t t0 = (int64_t)m_unit * NT;
+        const int u_first = (int)(((t0 + 1) * n_units + T - 1) / T) - 1;
+        const int slot = unit - u_first;
+        if (row < g.M) {
+          float2* p = g.part + (int64_t)row * g.part_ld + g.part_col0;
+          if (slot < g.n_slots) p[2 * slot + half] = make_float2(c_run, s_run);
+          if (tile + 1 == (m_unit + 1) * NT)
+            for (int k = slot + 1; k < g.n_slots; ++k) p[2 * k + half] = make_float2(-INFINITY, 0.f);
+        }
+        m_run = -INFINITY;
+        c_run = -INFINITY;
+        s_run = 0.f;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
+}
+
 // A = [ h[parent] | LM_in[word] ] as fp16 hi/lo at the gate-input scale: pure 16-byte row copies - the LSTM
 // epilogue leaves h as its split per slot and the embedding table is split once at load time (same formula, same
 // bits as splitting on the fly).
@@ -574,13 +833,13 @@ __global__ void __launch_bounds__(128, 2)
 k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_lo, int64_t ldw,
                   const __half* __restrict__ T_hi, const __half* __restrict__ T_lo, int64_t ldt, int K,
                   const SubsetJob* __restrict__ jobs, const int32_t* __restrict__ cols, const float* __restrict__ b2,
-                  float inv_scale, double* __restrict__ out) {
+                  float inv_scale, double* __restrict__ out, int col_skip) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ int32_t wid[VT_M];
   __shared__ uint64_t bar_s;
   __shared__ uint32_t tmem_slot;
   const SubsetJob job = jobs[blockIdx.y];
-  const int c0 = blockIdx.x * VT_M;
+  const int c0 = col_skip + blockIdx.x * VT_M;      // the first col_skip words are shared by all sentences: dense GEMM
   if (c0 >= job.ncols) return;
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -682,8 +941,34 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
   if (warp == 0) ptx::tmem_dealloc(tmem_base, VT_N);
 }
 
-// partial (c = max*log2e, s = sum 2^(v*log2e - c)) per 256-column tile -> natural-log LSE in float64
-__global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, int n_tiles, int M,
+// rows ids[0..n) of the split weight block and their biases -> dense operand (zero rows up to n_pad)
+__global__ void k_tc_gather_shared(const __half* __restrict__ W_hi, const __half* __restrict__ W_lo, int64_t ldw,
+                                   const float* __restrict__ b2, const int32_t* __restrict__ ids, int n, int n_pad,
+                                   __half* __restrict__ S_hi, __half* __restrict__ S_lo, float* __restrict__ bias) {
+  const int64_t total = (int64_t)n_pad * (ldw / 8);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (ldw / 8)), k = (int)(i % (ldw / 8)) * 8;
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+    if (r < n) {
+      const int64_t o = (int64_t)ids[r] * ldw + k;
+      vh = *reinterpret_cast<const uint4*>(W_hi + o);
+      vl = *reinterpret_cast<const uint4*>(W_lo + o);
+    }
+    *reinterpret_cast<uint4*>(S_hi + (int64_t)r * ldw + k) = vh;
+    *reinterpret_cast<uint4*>(S_lo + (int64_t)r * ldw + k) = vl;
+    if (k == 0) bias[r] = r < n ? b2[ids[r]] : 0.f;
+  }
+}
+
+// partial (c = max*log2e, s = sum 2^(v*log2e - c)) per 256-column tile (k_tc_gemm) or per run (k_tc_lse_rs) ->
+// natural-log LSE in float64.  Each output segment owns a fixed column range of the partial array and says how many
+// of its columns this step's launch wrote.
+struct LseCols {
+  int nseg;
+  int col0[JLM_MAX_SEGMENTS], cnt[JLM_MAX_SEGMENTS];
+};
+
+__global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, LseCols cols, int M,
                                double* __restrict__ lse) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -693,23 +978,37 @@ __global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, int
   constexpr int PL = 8;
   float2 v[PL];
   float mx = -INFINITY;
+  int held = 0;          // partials this lane keeps in registers (the first PL it meets)
+  for (int sg = 0; sg < cols.nseg; ++sg) {
+    const float2* ps = p + cols.col0[sg];
+    for (int t = lane; t < cols.cnt[sg]; t += 32) {
+      const float2 w = ps[t];
+      mx = fmaxf(mx, w.x);
 #pragma unroll
-  for (int i = 0; i < PL; ++i) {
-    const int t = lane + 32 * i;
-    v[i] = t < n_tiles ? p[t] : make_float2(-INFINITY, 0.f);
-    mx = fmaxf(mx, v[i].x);
+      for (int i = 0; i < PL; ++i)
+        if (i == held) v[i] = w;
+      ++held;
+    }
   }
-  for (int t = lane + 32 * PL; t < n_tiles; t += 32) mx = fmaxf(mx, p[t].x);
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   // 2^(c_tile - c_max) in fp32 (the tile sums themselves are fp32); products and the sum in float64
   double s = 0.0;
 #pragma unroll
   for (int i = 0; i < PL; ++i)
-    if (v[i].x > -INFINITY) s += (double)v[i].y * (double)exp2f(v[i].x - mx);
-  for (int t = lane + 32 * PL; t < n_tiles; t += 32) {
-    const float2 w = p[t];
-    if (w.x > -INFINITY) s += (double)w.y * (double)exp2f(w.x - mx);
+    if (i < held && v[i].x > -INFINITY) s += (double)v[i].y * (double)exp2f(v[i].x - mx);
+  if (held > PL) {       // very wide vocabularies: the rest is read again
+    int seen = 0;
+    for (int sg = 0; sg < cols.nseg; ++sg) {
+      const float2* ps = p + cols.col0[sg];
+      for (int t = lane; t < cols.cnt[sg]; t += 32) {
+        if (seen >= PL) {
+          const float2 w = ps[t];
+          if (w.x > -INFINITY) s += (double)w.y * (double)exp2f(w.x - mx);
+        }
+        ++seen;
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -865,6 +1164,59 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
   return 0;
 }
 
+static bool tc_rs_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_TC_RS");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+// Row-stationary launch (k_tc_lse_rs).  Returns the number of partial slots per row it writes through *n_slots,
+// or 0 there when the shape / device cannot take this kernel and the caller must use k_tc_gemm<EPI_LSE>.
+template <int KB>
+int32_t launch_lse_rs(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al, const TcOperand& B, RsArgs g, int max_slots,
+                      int* n_slots) {
+  using C = RsCfg<KB>;
+  *n_slots = 0;
+  g.num_m_units = ceil_div(g.M, 2 * BM);
+  g.num_n_blocks = ceil_div(g.N, C::BN);
+  const int64_t T = (int64_t)g.num_m_units * g.num_n_blocks;
+  if (T <= 0 || h->sm_count < 2) return 0;
+  static int max_pairs = -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(T, h->sm_count / 2));
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_pairs < 0) {
+    JLM_CUDA(cudaFuncSetAttribute(k_tc_lse_rs<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_tc_lse_rs<KB>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    max_pairs = n;
+  }
+  if (max_pairs <= 0) return 0;
+  const int U = (int)std::min<int64_t>(T, std::min(h->sm_count / 2, max_pairs));
+  const int64_t L = T / U;                                   // tiles per pair (some get one more)
+  const int slots = (int)std::min<int64_t>(std::min<int64_t>(g.num_n_blocks, U), (g.num_n_blocks + L - 1) / L + 1);
+  if (2 * slots > max_slots) return 0;      // two partials per (row, run): one per column half
+  g.n_slots = slots;
+  cfg.gridDim = dim3(2 * U);
+  JLM_CUDA(cudaLaunchKernelEx(&cfg, k_tc_lse_rs<KB>, Ah, Al, B.pair_hi, B.pair_lo, g));
+  *n_slots = 2 * slots;
+  return 0;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -878,7 +1230,9 @@ struct TcWeights {
   TcOperand Emb;                      // [V, Ep] input embedding, split at the gate-input scale sA
   float sA = 1.f;                     // gate-input scale: h (kept per slot as its fp16 split) and embedding share it
   float sT = 1.f;                     // stage-1 output scale
-  int lse_tiles = 0;
+  int lse_tiles = 0;                  // partial slots per row: sum of lse_cnt
+  int lse_col0[JLM_MAX_SEGMENTS] = {}; // first partial slot of each output segment
+  int lse_cnt[JLM_MAX_SEGMENTS] = {};  // slots reserved for it: one per 256-column tile (+1: row-stationary runs)
 };
 
 constexpr int GATE_BN = 256;
@@ -971,7 +1325,9 @@ static int32_t tc_build_weights(jlm_handle* h, TcWeights* w) {
     JLM_CUDA(cudaMemcpy(Wf.data(), s.W, Wf.size() * sizeof(float), cudaMemcpyDeviceToHost));
     std::vector<double> Wd(Wf.begin(), Wf.end());
     JLM_TRY(upload_split(&w->seg[i], Wd, Vi, s.kpad, 256));
-    w->lse_tiles += ceil_div(Vi, 256);
+    w->lse_col0[i] = w->lse_tiles;
+    w->lse_cnt[i] = ceil_div(Vi, 256) + 1;
+    w->lse_tiles += w->lse_cnt[i];
   }
   return 0;
 }
@@ -1003,6 +1359,12 @@ struct TcBatchState {
   __half *Ts_hi = nullptr, *Ts_lo = nullptr;   // [Mpad, Kt]
   float2* part = nullptr;
   int64_t Mpad = 0;
+  // vocabulary-selection modes: the word rows every sentence's list starts with, gathered once per run into a dense
+  // operand (jlm_batch::n_shared), and their logits for the step's rows
+  TcOperand Sh;                       // [n_shared_pad, kpad] views into the arena (not owned)
+  float* sh_bias = nullptr;           // [n_shared_pad] b2 of those words
+  float* Y0 = nullptr;                // [Mpad, ldy0]
+  int n_shared_pad = 0;
   CUtensorMap mAg_hi, mAg_lo, mHs_hi, mHs_lo;
   CUtensorMap mTs_hi[JLM_MAX_SEGMENTS], mTs_lo[JLM_MAX_SEGMENTS];
 };
@@ -1031,7 +1393,34 @@ int32_t tc_batch_plan(jlm_batch* b, Arena& a) {
     s->Ts_lo = s->Hs_lo;
   }
   s->part = (b->mode == JLM_DECODE_FULL && b->use_lse) ? a.take<float2>(mp * h->tc->lse_tiles) : nullptr;
+  // shared word rows: only where the tensor-core vocabulary kernel runs (tc_vocab_logits)
+  if (b->mode == JLM_DECODE_FULL || h->untied || h->n_seg != 1 || b->W > VT_N || h->seg[0].kpad % BK != 0 || !b->use_lse)
+    b->n_shared = 0;
+  s->n_shared_pad = (int)round_up64(b->n_shared, 256);
+  if (b->n_shared > 0) {
+    s->Sh.hi = a.take<__half>((size_t)s->n_shared_pad * h->seg[0].kpad);
+    s->Sh.lo = a.take<__half>((size_t)s->n_shared_pad * h->seg[0].kpad);
+    s->sh_bias = a.take<float>((size_t)s->n_shared_pad);
+    s->Y0 = a.take<float>(mp * s->n_shared_pad);
+    b->ldy0 = s->n_shared_pad;
+    b->y0 = s->Y0;
+  } else {
+    b->y0 = nullptr;
+    b->ldy0 = 0;
+  }
   if (a.dry) return 0;
+  if (b->n_shared > 0) {
+    const int64_t K = h->seg[0].kpad;
+    s->Sh.rows = s->n_shared_pad;
+    s->Sh.K = K;
+    s->Sh.scale = h->tc->seg[0].scale;
+    JLM_TRY(make_map(&s->Sh.map_hi, s->Sh.hi, K, s->n_shared_pad, K, 256));
+    JLM_TRY(make_map(&s->Sh.map_lo, s->Sh.lo, K, s->n_shared_pad, K, 256));
+    JLM_TRY(make_map(&s->Sh.pair_hi, s->Sh.hi, K, s->n_shared_pad, K, 128));
+    JLM_TRY(make_map(&s->Sh.pair_lo, s->Sh.lo, K, s->n_shared_pad, K, 128));
+    JLM_TRY(make_map(&s->Sh.q_hi, s->Sh.hi, K, s->n_shared_pad, K, 64));
+    JLM_TRY(make_map(&s->Sh.q_lo, s->Sh.lo, K, s->n_shared_pad, K, 64));
+  }
   JLM_TRY(make_map(&s->mAg_hi, s->Ag_hi, h->Kg, s->Mpad, h->Kg, BM));
   JLM_TRY(make_map(&s->mAg_lo, s->Ag_lo, h->Kg, s->Mpad, h->Kg, BM));
   const int64_t hs_rows = (int64_t)ns + BM;
@@ -1145,27 +1534,51 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
   const int M = sp.rows_step;
   if (M == 0) return 0;
   if (b->use_lse && b->mode == JLM_DECODE_FULL) {
-    int tile0 = 0;
+    LseCols cols{};
+    cols.nseg = h->n_seg;
     if (b->timers) cudaEventRecord(b->kev[4 * t + 2], st);
     for (int i = 0; i < h->n_seg; ++i) {
       const SegDev& sg = h->seg[i];
-      GemmArgs g{};
-      g.M = M;
-      g.N = sg.end - sg.start;
-      g.K = sg.kpad;
-      g.inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, sg.kpad) / (w->sT * w->seg[i].scale);
-      g.bias = h->b2 + sg.start;
-      g.part = s->part;
-      g.part_ld = w->lse_tiles;
-      g.part_tile0 = tile0;
-      g.a_row0 = h->untied ? (int)sp.row0 : 0;      // untied: A is the per-slot h split itself
-      JLM_TRY((launch_gemm<256, EPI_LSE>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], g)));
-      tile0 += ceil_div(g.N, 256);
+      const int N = sg.end - sg.start;
+      const int a_row0 = h->untied ? (int)sp.row0 : 0;      // untied: A is the per-slot h split itself
+      const int k16 = (int)round_up64(sg.width, 16);
+      cols.col0[i] = w->lse_col0[i];
+      int rs_slots = 0;
+      // short K (D-softmax* tail segments): row-stationary kernel, A resident, only the weight tiles stream
+      if (sg.kpad <= 2 * BK && M >= 2 * BM && tc_pair_enabled() && tc_rs_enabled()) {
+        RsArgs r{};
+        r.M = M;
+        r.N = N;
+        r.K16 = k16;
+        r.a_row0 = a_row0;
+        r.inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, k16) / (w->sT * w->seg[i].scale);
+        r.bias = h->b2 + sg.start;
+        r.part = s->part;
+        r.part_ld = w->lse_tiles;
+        r.part_col0 = w->lse_col0[i];
+        if (sg.kpad == BK) JLM_TRY((launch_lse_rs<1>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], r, w->lse_cnt[i], &rs_slots)));
+        else JLM_TRY((launch_lse_rs<2>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], r, w->lse_cnt[i], &rs_slots)));
+      }
+      if (rs_slots > 0) {
+        cols.cnt[i] = rs_slots;
+      } else {
+        GemmArgs g{};
+        g.M = M;
+        g.N = N;
+        g.K = sg.kpad;
+        g.inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, sg.kpad) / (w->sT * w->seg[i].scale);
+        g.bias = h->b2 + sg.start;
+        g.part = s->part;
+        g.part_ld = w->lse_tiles;
+        g.part_tile0 = w->lse_col0[i];
+        g.a_row0 = a_row0;
+        JLM_TRY((launch_gemm<256, EPI_LSE>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], g)));
+        cols.cnt[i] = ceil_div(N, 256);
+      }
       b->launches += 1;
     }
     if (b->timers) cudaEventRecord(b->kev[4 * t + 3], st);
-    k_tc_lse_merge<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(s->part, w->lse_tiles, w->lse_tiles, M,
-                                                                  b->d.slot_lse + sp.row0);
+    k_tc_lse_merge<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(s->part, w->lse_tiles, cols, M, b->d.slot_lse + sp.row0);
     JLM_CUDA(cudaGetLastError());
     b->launches += 1;
   }
@@ -1214,13 +1627,33 @@ int32_t tc_vocab_logits(jlm_batch* b, int t, double* out) {
     JLM_CUDA(cudaFuncSetAttribute(k_tc_vocab_logits, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
     configured = true;
   }
-  const int gx = ceil_div(sp.max_vocab_cols, VT_M);
   const float inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, h->seg[0].kpad) / (w->sT * w->seg[0].scale);
-  for (int j0 = 0; j0 < sp.nstep; j0 += 65535) {
+  const int ns = b->n_shared;
+  if (ns > 0) {
+    if (t == 0) {      // the shared word rows of this batch (the first ns ids of any sentence's list)
+      k_tc_gather_shared<<<std::min(ceil_div((int64_t)s->n_shared_pad * (h->seg[0].kpad / 8), 256), h->sm_count * 8), 256, 0,
+                           h->stream>>>(w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, h->b2, b->d.vocab_cols, ns,
+                                        s->n_shared_pad, s->Sh.hi, s->Sh.lo, s->sh_bias);
+      JLM_CUDA(cudaGetLastError());
+      b->launches += 1;
+    }
+    GemmArgs g{};
+    g.M = sp.rows_step;
+    g.N = s->n_shared_pad;
+    g.K = h->seg[0].kpad;
+    g.inv_scale = inv_scale;
+    g.bias = s->sh_bias;
+    g.C32 = s->Y0;
+    g.ldc = s->n_shared_pad;
+    JLM_TRY((launch_gemm<256, EPI_STORE>(h, s->mTs_hi[0], s->mTs_lo[0], s->Sh, g)));
+    b->launches += 1;
+  }
+  const int gx = ceil_div(std::max(sp.max_vocab_cols - ns, 0), VT_M);
+  for (int j0 = 0; j0 < sp.nstep && gx > 0; j0 += 65535) {
     const int nj = std::min(sp.nstep - j0, 65535);
     k_tc_vocab_logits<<<dim3(gx, nj), 128, VT_SMEM, h->stream>>>(
         w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, s->Ts_hi + h->seg[0].koff, s->Ts_lo + h->seg[0].koff, h->Kt,
-        h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, b->d.vocab_cols, h->b2, inv_scale, out);
+        h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, b->d.vocab_cols, h->b2, inv_scale, out, ns);
   }
   JLM_CUDA(cudaGetLastError());
   return 0;

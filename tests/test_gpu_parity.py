@@ -209,24 +209,31 @@ def test_decode_tc_full_size(name, tmp_path_factory):
     check_decode(name, TC, tmp_path_factory)
 
 
-def test_tc_matches_exact_on_a_lockstep_batch(tmp_path_factory):
-    """configs[1] shape, 512 sentences decoded in lock-step: tensor-core beams == float64 beams."""
+@pytest.mark.parametrize('name,n', [('cfg2_tied', 512), ('cfg3_dsoftmax_star', 384), ('cfg5_dsoftmax_star', 40)])
+def test_tc_matches_exact_on_a_lockstep_batch(name, n, tmp_path_factory):
+    """configs[1] / [2] / [4] shapes, n sentences decoded in lock-step (enough rows for the CTA-pair GEMMs and, for the
+    D-softmax* configs, the row-stationary short-K kernel): tensor-core n-best == float64 n-best."""
     from jlm_b200 import synth
-    dec, case, _ = get_decoder('cfg2_tied', tmp_path_factory)
-    _, _, _, lexicon, _, _ = build_case('cfg2_tied')
-    sents = synth.make_sentences(lexicon, 512, min_len=20, seed=77, vocab_size=case['vocab_size'])
+    dec, case, _ = get_decoder(name, tmp_path_factory)
+    _, _, _, lexicon, _, _ = build_case(name)
+    kw = dict(case['decode_kwargs'])
+    sents = synth.make_sentences(lexicon, n, min_len=20, seed=77, vocab_size=case['vocab_size'])
     dec._want_trace = False
+    dec.model.set_guard(-1.0)                    # default scope: what decode() returns is certified
     try:
-        a = dec.decode_batch(sents, topN=10, beam_width=10, backend=EXACT)
-        b = dec.decode_batch(sents, topN=10, beam_width=10, backend=TC)
+        a = dec.decode_batch(sents, backend=EXACT, **kw)
+        b = dec.decode_batch(sents, backend=TC, **kw)
+        info = dec.last_info
     finally:
+        dec.model.set_guard(-1.0, scope='all')
         dec._want_trace = True
     same = sum([w for _, w in x] == [w for _, w in y] for x, y in zip(a, b))
     top1 = sum(x[0][1] == y[0][1] for x, y in zip(a, b))
     worst = max(abs(p[0] - q[0]) for x, y in zip(a, b) for p, q in zip(x, y))
-    print('lock-step 512: identical n-best %d/512, identical top-1 %d/512, worst score diff %.3e' % (same, top1, worst))
-    assert top1 == 512
-    assert same == 512
+    print('%s lock-step %d: identical n-best %d, identical top-1 %d, worst score diff %.3e; guard: %d flagged, %d pairs, %d re-decoded'
+          % (name, n, same, top1, worst, info.n_guard_flagged, info.n_guard_pairs, info.n_guard_rerun))
+    assert top1 == n
+    assert same == n
     assert worst < 1e-3
 
 
@@ -543,9 +550,26 @@ def test_near_tie_guard_reruns_flagged_sentences_in_float64(tmp_path_factory):
         kw = dict(dcase['decode_kwargs'])
         dd._want_trace = False
         wantd = dd.decode_batch(sents[:64], backend=EXACT, **kw)
-        dd.model.set_guard(1e9, scope='all')                               # vocabulary-selection modes: tier 2 only
+        dd.model.set_guard(1e9, verify=False, scope='all')
         assert dd.decode_batch(sents[:64], backend=TC, **kw) == wantd
         assert dd.last_info.n_guard_flagged == 64 and dd.last_info.n_guard_rerun == 64
+        # tier 1 for the vocabulary-selection modes: log-sum-exp over lattice_vocab[t] per (state, sentence, frame)
+        dd.model.set_guard(5e-3, verify=True, scope='all')
+        gotd = dd.decode_batch(sents[:64], backend=TC, **kw)
+        assert dd.last_info.n_guard_pairs > 0
+        assert [[w for _, w in r] for r in gotd] == [[w for _, w in r] for r in wantd]
+        print('dynamic, bound 5e-3: %d flagged, %d pairs re-scored, %d re-decoded'
+              % (dd.last_info.n_guard_flagged, dd.last_info.n_guard_pairs, dd.last_info.n_guard_rerun))
+        vs, vcase, _ = get_decoder('small_tied_vs_top', tmp_path_factory)
+        vkw = dict(vcase['decode_kwargs'])
+        vs._want_trace = False
+        wantv = vs.decode_batch(sents[:64], backend=EXACT, **vkw)
+        vs.model.set_guard(5e-3, verify=True, scope='all')
+        gotv = vs.decode_batch(sents[:64], backend=TC, **vkw)
+        assert vs.last_info.n_guard_pairs > 0
+        assert [[w for _, w in r] for r in gotv] == [[w for _, w in r] for r in wantv]
+        vs.model.set_guard(-1.0, scope='all')
+        vs._want_trace = True
         dd.model.set_guard(-1.0, scope='all')
         dd._want_trace = True
     finally:

@@ -432,7 +432,7 @@ constexpr int PB_CAP = 160;    // survivors per warp segment
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
 k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_eps, int guard_all, int topN) {
-  __shared__ double mins[128];
+  __shared__ double mins[128 * L];
   __shared__ double sv[4][PB_CAP];
   __shared__ int sc[4][PB_CAP];
   __shared__ int cnt_w[4];
@@ -460,7 +460,13 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_ep
   const int q = ((nc + 127) / 128) * 32;
   const int w_lo = warp * q, w_hi = min(nc, w_lo + q);
   constexpr int UN = 8;
-  double tmin = INFINITY;
+  // Every thread keeps its L smallest candidates: 128 L distinct candidates, of which the one ranked W-1 bounds the
+  // frame's W-th best score.  One value per thread is not enough for wide beams: when the best W candidates are the
+  // W parents of ONE well-scored node they sit in at most 32 lanes of one warp, the bound then comes from some
+  // mediocre candidate of another thread and the survivor buffers overflow (measured at beam 50: 45 % of sentences).
+  double tm[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) tm[i] = INFINITY;
   for (int base = w_lo; base < w_hi; base += 32 * UN) {
     double v[UN];
 #pragma unroll
@@ -469,17 +475,31 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_ep
       v[u] = c < w_hi ? value(c) : INFINITY;
     }
 #pragma unroll
-    for (int u = 0; u < UN; ++u) tmin = fmin(tmin, v[u]);
+    for (int u = 0; u < UN; ++u) {
+      double x = v[u];
+#pragma unroll
+      for (int i = 0; i < L; ++i) {      // sorted insertion, tm[0] <= tm[1] <= ...
+        const double lo_ = fmin(tm[i], x);
+        x = fmax(tm[i], x);
+        tm[i] = lo_;
+      }
+    }
   }
-  mins[tid] = tmin;
+#pragma unroll
+  for (int i = 0; i < L; ++i) mins[tid * L + i] = tm[i];
   __syncthreads();
   {
-    int rk = 0;
-    for (int j = 0; j < 128; ++j) {
+    int rk[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) rk[i] = 0;
+    for (int j = 0; j < 128 * L; ++j) {
       const double o = mins[j];
-      rk += (o < tmin || (o == tmin && j < tid)) ? 1 : 0;
+#pragma unroll
+      for (int i = 0; i < L; ++i) rk[i] += (o < tm[i] || (o == tm[i] && j < tid * L + i)) ? 1 : 0;
     }
-    if (rk == W - 1) tau_s = tmin;      // ranks are a permutation of 0..127 and W <= 128: exactly one writer
+#pragma unroll
+    for (int i = 0; i < L; ++i)
+      if (rk[i] == W - 1) tau_s = tm[i];      // ranks are a permutation of 0..128L-1 and W <= 128: exactly one writer
   }
   __syncthreads();
   const double tau = tau_s;
@@ -1490,7 +1510,8 @@ static int32_t guard_stream_create(jlm_handle* h) {
 // nodes at the end.  A decision is confirmed when the float64 scores order the pair the way the tensor-core scores
 // did (equal scores: by enumeration ordinal, the stable sort's rule); a contradicted decision sends its sentence to
 // tier 2, the float64 re-decode.  Runs on its own stream, beside whatever the main stream holds.
-static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, const int32_t* paths, std::vector<char>& need_full) {
+static int32_t guard_verify_pairs(jlm_batch* b, int rec_lo, int rec_hi, const int4* rec, const int32_t* paths, std::vector<char>& need_full) {
+  const int n_rec = rec_hi - rec_lo;      // this call's slice of the record queue
   jlm_handle* h = b->h;
   const GuardLattice& G = *b->guard_lat;
   const int L = b->max_len + 1;
@@ -1519,9 +1540,9 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
   std::unordered_map<uint64_t, int> rindex;
   auto req_key = [&](int node, int p, int t) { return ((uint64_t)(uint32_t)node << 40) ^ ((uint64_t)(uint32_t)p << 12) ^ (uint64_t)(uint32_t)t; };
   struct PathRef { std::vector<int> q; std::vector<int> lse; };
-  std::vector<PathRef> refs((size_t)2 * n_rec);
+  std::vector<PathRef> refs((size_t)2 * n_rec);      // indexed by record - rec_lo
   std::vector<char> need_lse;                       // per trie node
-  for (int r = 0; r < n_rec; ++r) {
+  for (int r = rec_lo; r < rec_hi; ++r) {
     if (need_full[rec[r].x]) continue;
     const int32_t* pa = paths + ((int64_t)2 * r) * L;
     const int32_t* pb = pa + L;
@@ -1538,7 +1559,7 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
       const int32_t* pth = which ? pb : pa;
       const int len = pth[0];
       int node = -1;
-      PathRef& pr = refs[(size_t)2 * r + which];
+      PathRef& pr = refs[(size_t)2 * (r - rec_lo) + which];
       for (int j = 0; j < len; ++j) {
         const int w = G.node_word[pth[1 + j]];
         if (j >= common && j > 0) {                 // transition into word j from the state of words 0..j-1
@@ -1574,13 +1595,13 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
   if (queries.empty()) {
     // every pair is a pair of identical word sequences (duplicate lattice nodes): equal float64 scores, and the
     // record's order (rank i before rank i+1 of a stable sort) already is the enumeration order
-    for (int r = 0; r < n_rec; ++r)
+    for (int r = rec_lo; r < rec_hi; ++r)
       if (!need_full[rec[r].x]) b->n_pairs += 1;
     return 0;
   }
   constexpr int64_t POOL_CAP = 16384;
   if ((int64_t)trie.size() > POOL_CAP) {            // pathological batch: let tier 2 handle every flagged sentence
-    for (int r = 0; r < n_rec; ++r) need_full[rec[r].x] = 1;
+    for (int r = rec_lo; r < rec_hi; ++r) need_full[rec[r].x] = 1;
     return 0;
   }
   JLM_TRY(guard_stream_create(h));
@@ -1611,7 +1632,7 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
     for (size_t i = 0; i < trie.size(); ++i)
       if (need_lse[i]) lse_slots.push_back((int32_t)trie[i].slot);
     if (!rc && !lse_slots.empty()) rc = pool_lse_slots(h->guard_pool, lse_slots.data(), (int32_t)lse_slots.size());
-    b->n_lse_rows = (int)lse_slots.size();
+    b->n_lse_rows += (int)lse_slots.size();
   } else if (!reqs.empty()) {
     std::vector<int32_t> rslots(reqs.size()), rcols;
     std::vector<int64_t> rptr(reqs.size() + 1, 0);
@@ -1627,7 +1648,7 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
       rptr[i + 1] = (int64_t)rcols.size();
     }
     if (!rc) rc = pool_lse_subsets(h->guard_pool, (int32_t)reqs.size(), rslots.data(), rptr.data(), rcols.data(), req_lse.data());
-    b->n_lse_rows = (int)reqs.size();
+    b->n_lse_rows += (int)reqs.size();
   }
   std::vector<int32_t> qs(queries.size()), qw(queries.size());
   std::vector<double> nll(queries.size());
@@ -1638,12 +1659,12 @@ static int32_t guard_verify_pairs(jlm_batch* b, int n_rec, const int4* rec, cons
   if (!rc) rc = jlm_pool_nll(h->guard_pool, (int32_t)queries.size(), qs.data(), qw.data(), nll.data());
   h->stream = main_stream;
   if (rc) return rc;
-  for (int r = 0; r < n_rec; ++r) {
+  for (int r = rec_lo; r < rec_hi; ++r) {
     if (need_full[rec[r].x]) continue;
     double sc[2];
     for (int which = 0; which < 2; ++which) {
       double v = 0.0;                               // Path.__init__: neg_log_prob = 0, then += per node (decoder.py:34,49)
-      const PathRef& pr = refs[(size_t)2 * r + which];
+      const PathRef& pr = refs[(size_t)2 * (r - rec_lo) + which];
       for (size_t k = 0; k < pr.q.size(); ++k) v += nll[pr.q[k]] + (pr.lse[k] >= 0 ? req_lse[pr.lse[k]] : 0.0);
       sc[which] = v;
     }
@@ -1681,7 +1702,9 @@ static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
   static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
   const auto t_0 = std::chrono::steady_clock::now();
   if (b->h->guard_verify) {
-    JLM_TRY(guard_verify_pairs(b, n_rec, rec, paths, need_full));
+    // in slices of 256 records: a slice's trie of word prefixes (<= 2 x 256 paths) always fits the state pool
+    b->n_lse_rows = 0;
+    for (int r0 = 0; r0 < n_rec; r0 += 256) JLM_TRY(guard_verify_pairs(b, r0, std::min(n_rec, r0 + 256), rec, paths, need_full));
     if (dbg)
       fprintf(stderr, "[jlm] guard: %d sentences flagged, %d records, %d pairs re-scored, %d lse rows, %.3f ms\n", b->n_flagged,
               n_rec, b->n_pairs, b->n_lse_rows,

@@ -180,17 +180,27 @@ class Decoder(object):
 
     def words_from_arrays(self, texts, arrays, topN=None):
         """n-best word lists [(neg_log_prob, [word, ...])] from the array form (decoder.py:237-241)."""
-        ew = self._native().entry_words
+        nlex = self._native()
+        if getattr(nlex, '_entry_words_obj', None) is None:
+            nlex._entry_words_obj = np.array(list(nlex.entry_words) + [None, None], dtype=object)   # [-2], [-1] -> None
+        ew = nlex._entry_words_obj
         scores, n_paths, path_len = arrays['scores'], arrays['n_paths'], arrays['path_len']
         path_entry, path_start = arrays['path_entry'], arrays['path_start']
+        words = ew[path_entry]                      # one vectorised gather for the whole block (negative ids -> None)
+        has_unk = (path_entry == -2).any(axis=2)
+        sc_list, np_list, len_list = scores.tolist(), n_paths.tolist(), path_len.tolist()
         out = []
         for s, text in enumerate(texts):
             res = []
-            for k in range(int(n_paths[s])):
-                n = int(path_len[s, k])
-                ents, starts = path_entry[s, k, :n].tolist(), path_start[s, k, :n].tolist()
-                # '<eos>' (-1) is dropped (decoder.py:237); '<unk>' (-2) carries the raw kana (decoder.py:130)
-                res.append((float(scores[s, k]), [ew[e] if e >= 0 else text[st] for e, st in zip(ents, starts) if e != -1]))
+            for k in range(np_list[s]):
+                n = len_list[s][k]
+                ws = words[s, k, :n].tolist()
+                if has_unk[s, k]:
+                    # '<unk>' (-2) carries the raw kana of its frame (decoder.py:130)
+                    ents, starts = path_entry[s, k, :n].tolist(), path_start[s, k, :n].tolist()
+                    ws = [text[st] if e == -2 else w for w, e, st in zip(ws, ents, starts)]
+                # '<eos>' (-1) is dropped (decoder.py:237): it is the first node of every path and maps to None
+                res.append((sc_list[s][k], [w for w in ws if w is not None]))
             out.append(res[:topN] if topN is not None else res)
         return out
 

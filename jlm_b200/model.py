@@ -167,7 +167,13 @@ class LSTM_Model(object):
     def _load_model(self, experiment_id=0, comp=0):
         # decoder/model.py:73-104 (comp>0 loads the already-decoded k-means pickle, quirk 11)
         name = 'lstm_weights_comp_{}.pkl'.format(comp) if comp else 'lstm_weights.pkl'
-        with open(os.path.join(config.experiment_path, str(experiment_id), 'weights', name), 'rb') as f:
+        wdir = os.path.join(config.experiment_path, str(experiment_id), 'weights')
+        path = os.path.join(wdir, name)
+        if not comp and not os.path.exists(path) and os.path.exists(os.path.join(wdir, 'b2.txt')):
+            # only the per-parameter text dumps of `weights.py --verbose` survive (train/weights.py:77-87)
+            from . import weights_io
+            return weights_io.load_text_weights(wdir, self.config)
+        with open(path, 'rb') as f:
             return pickle.load(f)
 
     # ------------------------------------------------------------------------------------------

@@ -67,20 +67,24 @@ def unpack_arrays(f, i, n, top, max_len):
             'path_start': i[:n, 1 + top + top * max_len:].reshape(n, top, max_len)}
 
 
-def decode_sharded(decoder, texts, rank=None, world_size=None, gather=True, **decode_kwargs):
+def decode_sharded(decoder, texts, rank=None, world_size=None, gather=True, as_arrays=False, **decode_kwargs):
     """``decoder.decode_batch`` over this rank's shard of ``texts``.
 
     With ``gather=True`` and an initialised process group every rank returns the full list in input order.
     Decoders that offer ``decode_batch_arrays`` (the GPU decoders) exchange packed arrays with
     ``all_gather_into_tensor``; others fall back to ``all_gather_object``.  With ``gather=False`` a list with
-    ``None`` for sentences owned by other ranks is returned."""
+    ``None`` for sentences owned by other ranks is returned.  ``as_arrays=True`` (GPU decoders) returns the n-best
+    block of the whole input, in input order, in its array form (``decode_batch_arrays``) instead of Python word
+    lists - ``decoder.words_from_arrays(texts, arrays)`` turns any part of it into words later."""
     if rank is None or world_size is None:
         rank, world_size = env_rank_world()
     texts = list(texts)
     shards = partition([len(t) for t in texts], world_size)
     mine = shards[rank]
     out = [None] * len(texts)
-    packed = hasattr(decoder, 'decode_batch_arrays') and gather and world_size > 1
+    packed = hasattr(decoder, 'decode_batch_arrays') and gather and (world_size > 1 or as_arrays)
+    if as_arrays and not packed:
+        raise ValueError('as_arrays=True needs gather=True and a decoder with decode_batch_arrays')
     if not packed:
         local = decoder.decode_batch([texts[i] for i in mine], **decode_kwargs) if mine else []
         for i, res in zip(mine, local):
@@ -96,10 +100,6 @@ def decode_sharded(decoder, texts, rank=None, world_size=None, gather=True, **de
                     out[i] = res
         return out
 
-    import torch
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        raise RuntimeError('decode_sharded(gather=True) needs an initialised process group')
     topN = int(decode_kwargs.get('topN', 10))
     beam = decode_kwargs.get('beam_width', 10)
     top = max(1, topN if beam is None else min(topN, int(beam)))
@@ -107,15 +107,31 @@ def decode_sharded(decoder, texts, rank=None, world_size=None, gather=True, **de
     n_rows = max(len(s) for s in shards)
     arrays = decoder.decode_batch_arrays([texts[i] for i in mine], **decode_kwargs) if mine else None
     f, i32 = pack_arrays(arrays, n_rows, top, max_len)
-    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
-    tf, ti = torch.from_numpy(f).to(dev), torch.from_numpy(i32).to(dev)
-    # output = the ranks' blocks concatenated along dim 0 (the layout both NCCL and gloo accept)
-    gf = torch.empty((world_size * tf.shape[0], tf.shape[1]), dtype=tf.dtype, device=dev)
-    gi = torch.empty((world_size * ti.shape[0], ti.shape[1]), dtype=ti.dtype, device=dev)
-    dist.all_gather_into_tensor(gf, tf)
-    dist.all_gather_into_tensor(gi, ti)
-    gf = gf.cpu().numpy().reshape(world_size, n_rows, -1)
-    gi = gi.cpu().numpy().reshape(world_size, n_rows, -1)
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError('decode_sharded(gather=True) needs an initialised process group')
+        dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+        tf, ti = torch.from_numpy(f).to(dev), torch.from_numpy(i32).to(dev)
+        # output = the ranks' blocks concatenated along dim 0 (the layout both NCCL and gloo accept)
+        gf = torch.empty((world_size * tf.shape[0], tf.shape[1]), dtype=tf.dtype, device=dev)
+        gi = torch.empty((world_size * ti.shape[0], ti.shape[1]), dtype=ti.dtype, device=dev)
+        dist.all_gather_into_tensor(gf, tf)
+        dist.all_gather_into_tensor(gi, ti)
+        gf = gf.cpu().numpy().reshape(world_size, n_rows, -1)
+        gi = gi.cpu().numpy().reshape(world_size, n_rows, -1)
+    else:
+        gf, gi = f[None], i32[None]
+    if as_arrays:
+        # scatter the ranks' rows back to input order
+        full_f = np.empty((len(texts), gf.shape[2]), dtype=gf.dtype)
+        full_i = np.empty((len(texts), gi.shape[2]), dtype=gi.dtype)
+        for r, idx in enumerate(shards):
+            if idx:
+                full_f[idx] = gf[r, :len(idx)]
+                full_i[idx] = gi[r, :len(idx)]
+        return unpack_arrays(full_f, full_i, len(texts), top, max_len)
     for r, idx in enumerate(shards):
         if not idx:
             continue

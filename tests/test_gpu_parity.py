@@ -575,3 +575,25 @@ def test_near_tie_guard_reruns_flagged_sentences_in_float64(tmp_path_factory):
     finally:
         m.set_guard(-1.0, scope='all')
         dec._want_trace = True
+
+
+def test_model_loads_from_text_weight_dumps(tmp_path_factory):
+    """An experiment that kept only the `weights.py --verbose` text dumps (train/weights.py:77-87) decodes exactly
+    like the pickle it was dumped from."""
+    import os
+    import jlm_b200
+    from jlm_b200 import config, weights_io
+    root = str(tmp_path_factory.mktemp('exp_textdump'))
+    case, sentences = write_case(root, 'small_dsoftmax')
+    _, _, weights, _, _, _ = build_case('small_dsoftmax')
+    wdir = os.path.join(root, 'train', 'experiments', '1', 'weights')
+    weights_io.dump_text_weights(weights, wdir, with_npy=False)
+    os.remove(os.path.join(wdir, 'lstm_weights.pkl'))
+    config.set_root(root)
+    dec = jlm_b200.Decoder(1)
+    meta, _ = load_golden('small_dsoftmax')
+    for si, sent in enumerate(sentences):
+        res = dec.decode(sent, backend=EXACT, **case['decode_kwargs'])
+        g = meta['decode'][si]
+        assert [ws for _, ws in res] == [ws for _, ws in g['nbest']]
+        np.testing.assert_allclose([s for s, _ in res], [s for s, _ in g['nbest']], rtol=0, atol=2e-5)

@@ -261,3 +261,30 @@ def test_public_header_is_plain_c(tmp_path):
         subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-I', inc, str(src)], check=True)
     if shutil.which('g++'):
         subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-x', 'c++', '-I', inc, str(src)], check=True)
+
+
+@pytest.mark.parametrize('mode', ['tied', 'untied', 'dsoftmax', 'dsoftmax_star'])
+def test_text_weight_dumps_round_trip(mode, tmp_path):
+    """train/weights.py:69-87 (--verbose): np.savetxt dumps per parameter -> the dict lstm_weights.pkl holds, bit for
+    bit, for every projection mode (D-softmax keeps LM as a list of blocks dumped as LM0.txt, LM1.txt, ...)."""
+    import numpy as np
+    from jlm_b200 import synth, weights_io
+    cfg = synth.make_config(300, 32, 16, mode)
+    weights = synth.make_weights(cfg, seed=5)
+    d = str(tmp_path / 'weights')
+    weights_io.dump_text_weights(weights, d, with_npy=False)
+    if mode == 'tied':
+        assert open(os.path.join(d, 'embedding.txt')).readline().startswith('0 ')
+    got = weights_io.load_text_weights(d, cfg)
+    assert sorted(got) == sorted(weights)
+    for k, v in weights.items():
+        if isinstance(v, list):
+            assert len(got[k]) == len(v)
+            for a, b in zip(got[k], v):
+                assert a.dtype == np.float32 and np.array_equal(a, b)
+        else:
+            assert got[k].dtype == np.float32 and got[k].shape == v.shape and np.array_equal(got[k], v), k
+    w2 = weights_io.import_text_dump(d, cfg)
+    import pickle
+    back = pickle.load(open(os.path.join(d, 'lstm_weights.pkl'), 'rb'))
+    assert sorted(back) == sorted(w2)

@@ -160,3 +160,14 @@ def test_pack_unpack_roundtrip_and_thread_budget():
     assert f0.shape == (2, 3) and not i0.any()
     assert shard.host_threads_per_rank(1) == (os.cpu_count() or 1)
     assert shard.host_threads_per_rank(10 ** 6) == 1
+
+
+def test_decode_sharded_as_arrays_single_rank():
+    """as_arrays=True returns the whole n-best block in input order; world_size 1 needs no process group."""
+    d = _OraclePackedDecoder()
+    want = d.decode_batch(d.sentences, topN=3, beam_width=4)
+    arr = shard.decode_sharded(d, d.sentences, rank=0, world_size=1, gather=True, as_arrays=True, topN=3, beam_width=4)
+    assert arr['scores'].shape == (len(d.sentences), 3)
+    assert d.words_from_arrays(d.sentences, arr, 3) == want
+    with pytest.raises(ValueError):
+        shard.decode_sharded(_OracleBatchDecoder(), d.sentences, rank=0, world_size=1, as_arrays=True, topN=3, beam_width=4)

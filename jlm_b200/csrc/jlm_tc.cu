@@ -74,7 +74,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // instead of 96 KB and the per-MMA shared-memory traffic (operand reads + TMA writes), which is what
 // caps the single-CTA kernel at ~88 % tensor-pipe, drops from 20 KB to 13.3 KB per 128 cycles.
 // KS > 1: the K range is cut into KS chunks, each accumulated into its OWN TMEM accumulator, and the epilogue adds
-// the partials in float64.  tcgen05 accumulates in fp32 with truncation (measured, scripts/tc_bias_probe.py: the
+// the partials (fp32, round to nearest).  tcgen05 accumulates in fp32 with truncation (measured, scripts/tc_bias_probe.py: the
 // error of C = A.B^T grows linearly with K, -3e-9 K relative, biased toward zero), so a short chain per
 // accumulator is what buys accuracy; used for the stage-1 projection h.PM whose error every logit inherits.
 template <int BN, int CG = 1, int KS = 1>
@@ -92,6 +92,7 @@ struct TileCfg {
 
 struct GemmArgs {
   int M, N, K;
+  int K16;              // MMA k-steps are issued up to this column (0: all of K); the rest of K is zero padding
   int num_m_blocks, num_n_blocks;
   int a_row0;           // first row of the A operand inside its tensor map (per-slot arrays: the step's first slot)
   float inv_scale;      // 1 / (scale_A * scale_B)
@@ -245,6 +246,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const int kchunk = ceil_div_dev(num_kb, KS);      // k-blocks per partial accumulator
+        const int k_lim = g.K16 > 0 ? g.K16 : g.K;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
@@ -254,6 +256,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
           const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS + part * BN;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (kb * BK + k * 16 >= k_lim) continue;      // zero padding: nothing to multiply
             const uint64_t ah = ptx::umma_desc_sw128(sa + k * 32);
             const uint64_t al = ptx::umma_desc_sw128(sa + A_TILE + k * 32);
             const uint64_t bh = ptx::umma_desc_sw128(sa + 2 * A_TILE + k * 32);
@@ -391,15 +394,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
           uint32_t r[32];
           ptx::tmem_ld_x32(taddr + c0, r);
           ptx::tmem_ld_wait();
-          double sum[KS > 1 ? 32 : 1];
+          // partial accumulators: added in fp32 with round-to-nearest (3 additions: ~1e-7 relative, a quarter of what
+          // one accumulation chain carries; float64 here would put 128 F2F conversions per row on the quarter-rate pipe)
+          float sum[KS > 1 ? 32 : 1];
           if (KS > 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = (double)__uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(r[j]);
             for (int pp = 1; pp < n_part; ++pp) {
               ptx::tmem_ld_x32(taddr + pp * BN + c0, r);
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sum[j] += (double)__uint_as_float(r[j]);
+              for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(r[j]);
             }
           }
           const int n0 = n_blk * BN + c0;
@@ -407,8 +412,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              v[j] = (KS > 1) ? (float)fma(sum[j], (double)g.inv_scale, (double)bs[c0 + j])
-                              : fmaf(__uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
+              v[j] = fmaf((KS > 1) ? sum[j] : __uint_as_float(r[j]), g.inv_scale, bs[c0 + j]);
             if (n0 + 32 <= g.N && (g.ldc & 3) == 0) {
               if (g.C32) {
                 float4* dst = reinterpret_cast<float4*>(g.C32 + (int64_t)row * g.ldc + n0);
@@ -544,9 +548,12 @@ struct RsCfg {
   static constexpr int BIAS_BYTES = 2 * BN * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + BIAS_BYTES + BAR_BYTES + 1024;
-  // Eight epilogue warps, two per TMEM lane quarter (each takes half of the tile's columns): with one exp per logit
-  // the epilogue paces the short-K tiles, and a lone warp per scheduler leaves every TMEM-load and MUFU latency exposed.
-  static constexpr int EPI_WARPS = 8;
+  // Sixteen epilogue warps, four per TMEM lane quarter (each takes a quarter of the tile's columns): with one exp per
+  // logit the epilogue paces the short-K tiles, and it is latency-bound, not pipe-bound - ncu on the 8-warp version
+  // (profiles/r02/ncu_rs_cfg5_v2.csv): XU pipe 61 %, issue slots 45 %, tensor pipe 42 %, the stalls are fixed-latency
+  // waits and MUFU / TMEM-load scoreboards of the two warps a scheduler had.
+  static constexpr int EPI_WARPS = 16;
+  static constexpr int COL_PARTS = EPI_WARPS / 4;            // column slices of a tile, one partial each
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
@@ -702,23 +709,23 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
   } else {
     // ===================== epilogue warps: online (max, sum exp) per row, carried across the run =====================
     constexpr int ET = 32 * C::EPI_WARPS;
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / C::COL_PARTS;    // columns per warp
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;          // which half of the tile's columns
+    const int half = (warp - 2) >> 2;          // which slice of the tile's columns
     const int te = threadIdx.x - 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     float bnext = -INFINITY;
     auto fetch_bias = [&](int tl) {
       const int n = (tl % NT) * BN + te;
-      bnext = (n < g.N) ? (g.bias ? g.bias[n] : 0.f) : -INFINITY;
+      bnext = (te < BN && n < g.N) ? (g.bias ? g.bias[n] : 0.f) : -INFINITY;
     };
     if (t_lo < t_hi) fetch_bias(t_lo);
     float m_run = -INFINITY, c_run = -INFINITY, s_run = 0.f;
     for (int tile = t_lo; tile < t_hi; ++tile) {
       const int m_unit = tile / NT;
       float* bs = bias_s + acc * BN;
-      bs[te] = bnext;
+      if (te < BN) bs[te] = bnext;
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       if (tile + 1 < t_hi) fetch_bias(tile + 1);
       const uint32_t taddr = tmem_base + acc * BN + half * HALF + (static_cast<uint32_t>(q * 32) << 16);
@@ -735,21 +742,33 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
         uint32_t(&rc)[32] = r[ch & 1];
         float v[32];
         float cm = -INFINITY;
+        // The exponentials are taken against the row's RUNNING maximum (from the chunks before), so the MUFUs can be
+        // issued as soon as a logit is formed instead of after the chunk's own maximum is known; the sum is rescaled
+        // afterwards in the (rare, after the first chunks) case that this chunk raised the maximum.  ex2.approx.ftz:
+        // 2^-inf = 0, arguments below -126 flush to 0.  A first chunk, or a jump of more than 60 (fp32 range), takes
+        // the two-pass form.
+        float part[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           v[j] = fmaf(__uint_as_float(rc[j]), g.inv_scale, bh[ch * 32 + j]);
           cm = fmaxf(cm, v[j]);
+          part[j & 3] += ex2_approx(fmaf(v[j], LOG2E, -c_run));
         }
-        if (cm > -INFINITY) {
-          const float m_new = fmaxf(m_run, cm);
-          const float c_new = m_new * LOG2E;
-          s_run *= ex2_approx(c_run - c_new);      // ex2.approx.ftz: 2^-inf = 0, arguments below -126 flush to 0
-          float part = 0.f;
+        if (cm > m_run) {
+          const float c_new = cm * LOG2E;
+          if (m_run > -INFINITY && cm - m_run < 60.f) {
+            s_run = (s_run + (part[0] + part[1]) + (part[2] + part[3])) * ex2_approx(c_run - c_new);
+          } else {
+            s_run *= ex2_approx(c_run - c_new);
+            float p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) part += ex2_approx(fmaf(v[j], LOG2E, -c_new));
-          s_run += part;
-          m_run = m_new;
+            for (int j = 0; j < 32; ++j) p2[j & 3] += ex2_approx(fmaf(v[j], LOG2E, -c_new));
+            s_run += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+          }
+          m_run = cm;
           c_run = c_new;
+        } else if (m_run > -INFINITY) {      // (no maximum yet and nothing but masked columns: part holds NaNs, skip)
+          s_run += (part[0] + part[1]) + (part[2] + part[3]);
         }
         if (ch + 1 < HALF / 32) ptx::tmem_ld_wait();
       }
@@ -767,9 +786,9 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
         const int slot = unit - u_first;
         if (row < g.M) {
           float2* p = g.part + (int64_t)row * g.part_ld + g.part_col0;
-          if (slot < g.n_slots) p[2 * slot + half] = make_float2(c_run, s_run);
+          if (slot < g.n_slots) p[C::COL_PARTS * slot + half] = make_float2(c_run, s_run);
           if (tile + 1 == (m_unit + 1) * NT)
-            for (int k = slot + 1; k < g.n_slots; ++k) p[2 * k + half] = make_float2(-INFINITY, 0.f);
+            for (int k = slot + 1; k < g.n_slots; ++k) p[C::COL_PARTS * k + half] = make_float2(-INFINITY, 0.f);
         }
         m_run = -INFINITY;
         c_run = -INFINITY;
@@ -1209,11 +1228,11 @@ int32_t launch_lse_rs(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& A
   const int U = (int)std::min<int64_t>(T, std::min(h->sm_count / 2, max_pairs));
   const int64_t L = T / U;                                   // tiles per pair (some get one more)
   const int slots = (int)std::min<int64_t>(std::min<int64_t>(g.num_n_blocks, U), (g.num_n_blocks + L - 1) / L + 1);
-  if (2 * slots > max_slots) return 0;      // two partials per (row, run): one per column half
+  if (C::COL_PARTS * slots > max_slots) return 0;      // one partial per (row, run, column slice)
   g.n_slots = slots;
   cfg.gridDim = dim3(2 * U);
   JLM_CUDA(cudaLaunchKernelEx(&cfg, k_tc_lse_rs<KB>, Ah, Al, B.pair_hi, B.pair_lo, g));
-  *n_slots = 2 * slots;
+  *n_slots = C::COL_PARTS * slots;
   return 0;
 }
 
@@ -1566,7 +1585,8 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
         g.M = M;
         g.N = N;
         g.K = sg.kpad;
-        g.inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, sg.kpad) / (w->sT * w->seg[i].scale);
+        g.K16 = k16;
+        g.inv_scale = rz_comp(RZ_OUT, RZ_DRIFT, k16) / (w->sT * w->seg[i].scale);
         g.bias = h->b2 + sg.start;
         g.part = s->part;
         g.part_ld = w->lse_tiles;

@@ -796,9 +796,16 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
   const int n_all = vfp[inf.vfp_off + inf.T + 1];
   if (n_all <= DYN_CAP && n_all > 0) {
     double* csum = csum_all[threadIdx.x >> 5];
+    __shared__ double offs_all[4][32];
+    double* offs = offs_all[threadIdx.x >> 5];
     const bool dup = (k == 0);
     double gmax = -INFINITY;
-    for (int j = lane; j < n_all; j += 32) gmax = fmax(gmax, p[j]);
+    // pass 1 (coalesced): the row goes into shared memory once; everything after reads it from there
+    for (int j = lane; j < n_all; j += 32) {
+      const double x = p[j];
+      csum[j] = x;
+      gmax = fmax(gmax, x);
+    }
     if (dup)
       for (int j = inf.nv + lane; j < inf.nv + inf.nd; j += 32) gmax = fmax(gmax, p[j]);
 #pragma unroll
@@ -812,23 +819,29 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) sdup += __shfl_xor_sync(0xffffffffu, sdup, o);
     }
-    double carry = 0.0;
-    for (int base = 0; base < n_all; base += 32) {
-      const int j = base + lane;
-      double e = j < n_all ? ex(p[j] - gmax) : 0.0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, e, o);
-        if (lane >= o) e += up;
-      }
-      e += carry;
-      if (j < n_all) csum[j] = e;
-      carry = __shfl_sync(0xffffffffu, e, 31);
+    // pass 2: ONE scan per row.  Lane l owns the contiguous segment [l*seg, (l+1)*seg): it turns its logits into
+    // running sums of exp(y - max) in place, the 32 segment totals go through a single warp scan, and a boundary's
+    // denominator is the in-segment prefix plus the offset of its segment (a scan per 32 columns cost ten shuffles
+    // of a double per chunk).  seg is odd so that the lanes' strided 8-byte accesses spread over the banks.
+    __syncwarp();
+    const int seg = ((n_all + 31) / 32) | 1;
+    const int j0 = lane * seg, j1 = min(n_all, j0 + seg);
+    double run = 0.0;
+    for (int j = j0; j < j1; ++j) {
+      run += ex(csum[j] - gmax);
+      csum[j] = run;
     }
+    double tot = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, tot, o);
+      if (lane >= o) tot += up;
+    }
+    offs[lane] = tot - run;            // sum of the segments before this lane's
     __syncwarp();
     for (int i = k + 1 + lane; i <= inf.T; i += 32) {
       const int end = vfp[inf.vfp_off + i + 1];
-      const double lse = gmax + log((end > 0 ? csum[end - 1] : 0.0) + sdup);
+      const double lse = gmax + log((end > 0 ? csum[end - 1] + offs[(end - 1) / seg] : 0.0) + sdup);
       dyn_lse[slot * tstride + i] = lse;
       dyn_chain[slot * tstride + i] = (par >= 0 ? dyn_chain[(int64_t)par * tstride + i] : 0.0) + lse;
     }

@@ -708,36 +708,44 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
     }
   } else {
     // ===================== epilogue warps: online (max, sum exp) per row, carried across the run =====================
-    constexpr int ET = 32 * C::EPI_WARPS;
     constexpr int HALF = BN / C::COL_PARTS;    // columns per warp
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;          // which slice of the tile's columns
-    const int te = threadIdx.x - 64;
     int acc = 0;
     uint32_t acc_phase = 0;
-    float bnext = -INFINITY;
-    auto fetch_bias = [&](int tl) {
-      const int n = (tl % NT) * BN + te;
-      bnext = (te < BN && n < g.N) ? (g.bias ? g.bias[n] : 0.f) : -INFINITY;
-    };
-    if (t_lo < t_hi) fetch_bias(t_lo);
+    // The bias slice of a chunk is read straight from global memory (every lane the same address: one broadcast
+    // sector per load, L1-resident after the first warp) - no shared-memory staging and, above all, no per-tile
+    // barrier keeping the sixteen warps in lock-step: their FMA/max phases and MUFU phases now overlap.
+    const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     float m_run = -INFINITY, c_run = -INFINITY, s_run = 0.f;
+    int m_unit = t_lo / NT, n_blk = t_lo - m_unit * NT;      // kept incrementally: no division per tile
     for (int tile = t_lo; tile < t_hi; ++tile) {
-      const int m_unit = tile / NT;
-      float* bs = bias_s + acc * BN;
-      if (te < BN) bs[te] = bnext;
-      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-      if (tile + 1 < t_hi) fetch_bias(tile + 1);
       const uint32_t taddr = tmem_base + acc * BN + half * HALF + (static_cast<uint32_t>(q * 32) << 16);
-      const float* bh = bs + half * HALF;
+      const int col0 = n_blk * BN + half * HALF;             // first column of this warp's slice
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       // TMEM loads are issued one 32-column chunk ahead of the math
       uint32_t r[2][32];
       ptx::tmem_ld_x32(taddr, r[0]);
-      ptx::tmem_ld_wait();
 #pragma unroll
       for (int ch = 0; ch < HALF / 32; ++ch) {
+        float bias_r[32];
+        const int cb = col0 + ch * 32;
+        if (bias_vec && cb + 32 <= g.N) {
+          const float4* bp = reinterpret_cast<const float4*>(g.bias + cb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t4 = __ldg(bp + i);
+            bias_r[4 * i] = t4.x;
+            bias_r[4 * i + 1] = t4.y;
+            bias_r[4 * i + 2] = t4.z;
+            bias_r[4 * i + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bias_r[j] = (cb + j < g.N) ? (g.bias ? __ldg(g.bias + cb + j) : 0.f) : -INFINITY;
+        }
+        ptx::tmem_ld_wait();
         if (ch + 1 < HALF / 32) ptx::tmem_ld_x32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
         uint32_t(&rc)[32] = r[ch & 1];
         float v[32];
@@ -750,7 +758,7 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
         float part[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = fmaf(__uint_as_float(rc[j]), g.inv_scale, bh[ch * 32 + j]);
+          v[j] = fmaf(__uint_as_float(rc[j]), g.inv_scale, bias_r[j]);
           cm = fmaxf(cm, v[j]);
           part[j & 3] += ex2_approx(fmaf(v[j], LOG2E, -c_run));
         }
@@ -770,14 +778,14 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
         } else if (m_run > -INFINITY) {      // (no maximum yet and nothing but masked columns: part holds NaNs, skip)
           s_run += (part[0] + part[1]) + (part[2] + part[3]);
         }
-        if (ch + 1 < HALF / 32) ptx::tmem_ld_wait();
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      if (tile + 1 == t_hi || (tile + 1) / NT != m_unit) {
+      const bool block_done = n_blk + 1 == NT;             // this tile closes the row block
+      if (tile + 1 == t_hi || block_done) {
         // end of this pair's run over the row block: one partial per (row, column half).  Slot = how many pairs before
         // this one also work on the block; the pair that finishes the block neutralises the slots nobody writes.
         const int row = (m_unit * 2 + (int)rank) * BM + q * 32 + lane;
@@ -787,12 +795,18 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
         if (row < g.M) {
           float2* p = g.part + (int64_t)row * g.part_ld + g.part_col0;
           if (slot < g.n_slots) p[C::COL_PARTS * slot + half] = make_float2(c_run, s_run);
-          if (tile + 1 == (m_unit + 1) * NT)
+          if (block_done)
             for (int k = slot + 1; k < g.n_slots; ++k) p[C::COL_PARTS * k + half] = make_float2(-INFINITY, 0.f);
         }
         m_run = -INFINITY;
         c_run = -INFINITY;
         s_run = 0.f;
+      }
+      if (block_done) {
+        n_blk = 0;
+        ++m_unit;
+      } else {
+        ++n_blk;
       }
     }
   }

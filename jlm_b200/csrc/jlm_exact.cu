@@ -613,7 +613,8 @@ bool stream_ok(int M, int N, int K) {
   }();
   // Up to 16 rows k_skinny_f64 is still the faster of the two (measured, single sentence at cfg 2: 43.5 vs 52.7 us per
   // launch, profiles/r02/launch_summary_single_*.txt); beyond that this kernel runs 16 rows at a time.
-  return on && M > 16 && M <= 512 && K <= 256 && K % 64 == 0 && N >= 1024;      // K / 8 slices of whole 16-byte pieces
+  // JLM_STREAM_GEMM=2 also routes <= 16 rows here (A/B runs)
+  return on && (M > 16 || on == 2) && M <= 512 && K <= 256 && K % 64 == 0 && N >= 1024;      // K / 8 slices of whole 16-byte pieces
 }
 
 int32_t launch_stream(cudaStream_t st, const double* A, int lda, const float* B, int ldb, const float* bias, double* C,

@@ -64,6 +64,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, degree-6 polynomial
+// for 2^f on [-0.5, 0.5] (Cephes exp2f coefficients, ~1e-7 relative), 2^n by adding n to the exponent field.  Twelve
+// issue slots instead of one MUFU: used for a fraction of the logits where the MUFU queue is what paces an epilogue.
+// x is clamped at -125 (result 2^-125 instead of 0: negligible against a sum that is >= 1).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = 1.535336188319500e-4f;
+  p = fmaf(p, f, 1.339887440266574e-3f);
+  p = fmaf(p, f, 9.618437357674640e-3f);
+  p = fmaf(p, f, 5.550332471162809e-2f);
+  p = fmaf(p, f, 2.402264791363012e-1f);
+  p = fmaf(p, f, 6.931472028550421e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(-LOG2E * x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
   return fmaf(-2.f, rcp_approx(ex2_approx((2.f * LOG2E) * x) + 1.f), 1.f);   // 1 - 2/(e^{2x}+1)
@@ -538,6 +555,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
 // running (max, sum exp) of a row also stays in registers across the column blocks of the run and one partial
 // per (row, run) is written instead of one per (row, tile): 392 -> 2..3 partials per row at V = 100k.
 // K is issued in 16-wide steps up to round_up(width, 16): the zero padding up to 64 is never multiplied.
+// Measured and rejected (profiles/r02/README.md): with one exponential in four on the FMA pipe the cfg-5 tail kernel runs
+// 0.631 ms per launch against 0.604 ms with all of them on the MUFU (cfg 3: 0.081 vs 0.076) - twelve issue slots per
+// polynomial cost more than the MUFU queue gives back.  Build with -DJLM_RS_POLY=n to try other ratios.
+#ifndef JLM_RS_POLY
+#define JLM_RS_POLY 0
+#endif
+constexpr int RS_POLY = JLM_RS_POLY;      // 0: every exponential on the MUFU; n: one in n on the FMA pipe
+
 template <int KB>
 struct RsCfg {
   static constexpr int BN = 256;
@@ -760,7 +785,10 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
         for (int j = 0; j < 32; ++j) {
           v[j] = fmaf(__uint_as_float(rc[j]), g.inv_scale, bias_r[j]);
           cm = fmaxf(cm, v[j]);
-          part[j & 3] += ex2_approx(fmaf(v[j], LOG2E, -c_run));
+          const float arg = fmaf(v[j], LOG2E, -c_run);
+          // every RS_POLY-th exponential goes to the FMA pipe: the MUFU queue paces this loop (ncu: stall_mio on
+          // every MUFU.EX2, issue slots 45 % busy)
+          part[j & 3] += (RS_POLY > 0 && (j % (RS_POLY > 0 ? RS_POLY : 1)) == RS_POLY - 1) ? ex2_poly(arg) : ex2_approx(arg);
         }
         if (cm > m_run) {
           const float c_new = cm * LOG2E;

@@ -462,7 +462,7 @@ def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
     env.windows.append((t_load0, t_load1))
 
     # ---------------- latency mode: one sentence per call (few rows in flight, exact float64 back end) ----------------
-    lat_ms = None
+    lat_ms = lat_roof = None
     if rank == 0 and headline:
         one = lattice.NativeLattices(nlex, sents[:1], MODE, extra[:1] if extra is not None else None)
         v1 = one.c_struct()
@@ -472,6 +472,37 @@ def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
         for _ in range(20):
             _lib.check(lib.jlm_decode_batch(hdl, C.byref(v1), BEAM, TOPN, MODE, _lib.BACKEND_AUTO, C.byref(nb)))
         lat_ms = (time.perf_counter() - t0) / 20 * 1e3
+        # roofline of the latency path's dominant kernel: the float64 weight stream over the output block(s)
+        # (k_skinny_f64; HBM/L2-bound, algorithmic bytes = V * K * 4 per stepped frame), from the CUDA-event
+        # "softmax" bucket of one timed call (that bucket also holds the LSE merge and the needed-word dots)
+        b1 = C.c_void_p()
+        _lib.check(lib.jlm_batch_upload(hdl, C.byref(v1), BEAM, TOPN, MODE, _lib.BACKEND_AUTO, C.byref(b1)))
+        _lib.check(lib.jlm_batch_enable_timers(b1, 1))
+        _lib.check(lib.jlm_batch_run(b1))
+        nb1 = _lib.NBest()
+        s1 = (np.empty((1, TOPN)), np.empty(1, dtype=np.int32), np.empty((1, TOPN), dtype=np.int32),
+              np.zeros((1, TOPN, max_len), dtype=np.int32))
+        nb1.top_n, nb1.max_len = TOPN, max_len
+        nb1.scores, nb1.n_paths = _lib.ptr(s1[0], C.c_double), _lib.ptr(s1[1], C.c_int32)
+        nb1.path_len, nb1.path_nodes = _lib.ptr(s1[2], C.c_int32), _lib.ptr(s1[3], C.c_int32)
+        _lib.check(lib.jlm_batch_fetch(b1, C.byref(nb1)))
+        i1 = _lib.BatchInfo()
+        _lib.check(lib.jlm_batch_get_info(b1, C.byref(i1)))
+        _lib.check(lib.jlm_batch_destroy(b1))
+        if wl['mode'] == 'dsoftmax_star':
+            out_bytes = sum(4.0 * sz * ((wl['V'] if e is None else e) - st) for sz, st, e in wl['segments'])
+        else:
+            out_bytes = 4.0 * wl['E'] * wl['V']
+        n_frames = len(sents[0]) + (0 if wl['dynamic'] else 1)
+        lat_roof = None
+        if not wl['dynamic'] and i1.ms_softmax > 0:
+            gbs = out_bytes * n_frames / (i1.ms_softmax * 1e-3) / 1e9
+            lat_roof = {'bound': 'hbm', 'kernel': 'k_skinny_f64 (float64 weight stream over the output block, <= 16 rows)',
+                        'achieved': gbs, 'peak': peaks()[2], 'unit': 'GB/s', 'frac': gbs / peaks()[2],
+                        'bytes_per_frame': out_bytes, 'frames': n_frames, 'ms_softmax_bucket': float(i1.ms_softmax),
+                        'ms_lstm_bucket': float(i1.ms_lstm), 'ms_beam_bucket': float(i1.ms_beam),
+                        'note': 'the block is L2-resident between frames (51 MB < 126 MB): this is an L2 stream; bucket = '
+                                'weight stream + LSE merge + needed-word dots of every frame'}
         _lib.check(lib.jlm_decode_batch(hdl, C.byref(lb), BEAM, TOPN, MODE, args.backend, C.byref(nb)))   # restore nb
 
     if rank != 0:
@@ -539,6 +570,7 @@ def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
                    'lm_rows_per_step': rows_stepped, 'backend': 'tcgen05' if args.backend == 2 else 'exact-f64',
                    'l2': 'explicit 256 MiB flush between timed steps', 'host_lattice_build_s': t_lat,
                    'single_sentence_latency_ms': lat_ms, 'single_sentence_chars': len(sents[0]),
+                   'single_sentence_roofline': lat_roof,
                    'wall_s_timed_region': wall,
                    'timed_region': 'jlm_batch_run + jlm_batch_fetch per step (frames, n-best D2H, near-tie guard)'},
         'e2e': {'value': e2e, 'unit': 'chars/s', 'h2d_bytes_per_step': int(i2.h2d_bytes),

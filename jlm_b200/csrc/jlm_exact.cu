@@ -359,6 +359,54 @@ k_stream_f64(const double* __restrict__ A, int lda, const float* __restrict__ B,
   }
 }
 
+// Small-N float64 GEMM for few rows (the gate pre-activations, N = 4H, and the stage-1 projection, N = E): ONE WARP PER
+// OUTPUT COLUMN.  k_skinny_f64's column-per-lane layout gives N / 32 CTAs - 64 for the gate GEMM, 8 for stage-1 - on a
+// 148-SM part, and both were pure latency (15 and 13 us per launch for 6 MB and 1 MB of weights).  Here the lanes of a
+// warp split K with 16-byte loads (a warp reads 512 contiguous bytes of its weight row), every lane keeps one
+// float64 accumulator per row against its own K slice of A (read through L1: the same few KB for every warp of the
+// SM), and the rows are reduced across the warp at the end.
+template <typename TB, int MT>
+__global__ void __launch_bounds__(256)
+k_warpcol_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb, const float* __restrict__ bias,
+              double* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  constexpr int VEC = 16 / (int)sizeof(TB);
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const TB* brow = B + (int64_t)n * ldb;
+  double acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+#pragma unroll 4      // the iterations are independent: their weight and A loads overlap instead of paying one L2 round trip each
+  for (int k = lane * VEC; k < K; k += 32 * VEC) {
+    double w[VEC];
+    SkLoad<TB>::load(brow + k, nullptr, w);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        const double* ap = A + (int64_t)m * lda + k;
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) {
+          const double2 a2 = __ldg(reinterpret_cast<const double2*>(ap + i));
+          acc[m] = fma(a2.x, w[i], acc[m]);
+          acc[m] = fma(a2.y, w[i + 1], acc[m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+    const double bv = bias ? (double)bias[n] : 0.0;
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+      if (m < M) C[(int64_t)m * ldc + n] = acc[m] + bv;
+  }
+}
+
 __global__ void k_lse_merge(const double2* __restrict__ part, int part_ld, int n_tiles, int M,
                             double* __restrict__ lse, int self_norm) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -548,6 +596,14 @@ int grid_1d(int64_t total, int block, int cap) {
   return (int)g;
 }
 
+static bool warpcol_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_WARPCOL");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 template <typename TB, int MT>
 int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, int ldb, const float* codebook,
                       const float* bias, double* C, int64_t ldc, int M, int N, int K, double2* part, int part_ld,
@@ -556,6 +612,10 @@ int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, in
   if (!configured) {
     JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 32, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // three 72 KB CTAs per SM need the whole shared-memory carve-out (ncu showed two resident: the kernel is
+    // latency-bound at 3.5 warps per scheduler)
+    JLM_CUDA(cudaFuncSetAttribute(k_skinny_f64<TB, MT, 64, 2, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   constexpr int VEC = 16 / (int)sizeof(TB);
@@ -563,6 +623,8 @@ int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, in
     const size_t smem = ((size_t)M * K + (size_t)8 * MT * 64 + 256) * sizeof(double);
     k_skinny_f64<TB, MT, 64, 2, 8><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, B, ldb, codebook, bias, C, ldc, M, N, K,
                                                                       part, part_ld, part_tile0);
+  } else if (warpcol_enabled() && C && K % (32 * VEC) == 0) {
+    k_warpcol_f64<TB, MT><<<ceil_div(N, 8), 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
   } else {
     const size_t smem = ((size_t)M * K + (size_t)16 * MT * 32 + 256) * sizeof(double);
     k_skinny_f64<TB, MT, 32, 1, 16><<<ceil_div(N, 32), 512, smem, st>>>(A, lda, B, ldb, codebook, bias, C, ldc, M, N, K,

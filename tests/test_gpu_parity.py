@@ -597,3 +597,31 @@ def test_model_loads_from_text_weight_dumps(tmp_path_factory):
         g = meta['decode'][si]
         assert [ws for _, ws in res] == [ws for _, ws in g['nbest']]
         np.testing.assert_allclose([s for s, _ in res], [s for s, _ in g['nbest']], rtol=0, atol=2e-5)
+
+
+def test_decode_batch_arrays_and_sharded_single_rank(tmp_path_factory):
+    """decode_batch_arrays (the array form a sharded caller exchanges) rebuilds into exactly what decode_batch returns,
+    for the static and the dynamic decoder; decode_sharded with world_size 1 returns the same block in input order."""
+    from jlm_b200 import shard, synth
+    dec, case, _ = get_decoder('small_tied', tmp_path_factory)
+    _, _, _, lexicon, _, _ = build_case('small_tied')
+    sents = synth.make_sentences(lexicon, 70, min_len=5, seed=12, vocab_size=case['vocab_size']) + ['ヰヱ', '']
+    dec._want_trace = False
+    try:
+        want = dec.decode_batch(sents, topN=4, beam_width=6, backend=EXACT)
+        arr = dec.decode_batch_arrays(sents, topN=4, beam_width=6, backend=EXACT)
+        assert arr['scores'].shape == (len(sents), 4) and arr['path_entry'].dtype == np.int32
+        assert dec.words_from_arrays(sents, arr, 4) == want
+        full = shard.decode_sharded(dec, sents, rank=0, world_size=1, gather=True, as_arrays=True, topN=4, beam_width=6,
+                                    backend=EXACT)
+        assert dec.words_from_arrays(sents, full, 4) == want
+        assert shard.decode_sharded(dec, sents, rank=0, world_size=1, topN=4, beam_width=6, backend=EXACT) == want
+        dd, dcase, _ = get_decoder('small_tied_dyn_top', tmp_path_factory)
+        dd._want_trace = False
+        kw = dict(dcase['decode_kwargs'])
+        wantd = dd.decode_batch(sents[:40], backend=EXACT, **kw)
+        arrd = dd.decode_batch_arrays(sents[:40], backend=EXACT, **kw)
+        assert dd.words_from_arrays(sents[:40], arrd, kw['topN']) == wantd
+        dd._want_trace = True
+    finally:
+        dec._want_trace = True

@@ -1686,6 +1686,10 @@ static int32_t guard_verify_pairs(jlm_batch* b, int rec_lo, int rec_hi, const in
     // the scores are equal and z comes first in enumeration order
     const bool ok = sc[0] < sc[1] || (sc[0] == sc[1] && rec[r].z < rec[r].w);
     if (!ok) need_full[rec[r].x] = 1;
+    static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
+    if (dbg && !ok)
+      fprintf(stderr, "[jlm] guard: contradicted decision: sentence %d (T=%d) frame %d, float64 suffix scores %.9g vs %.9g\n",
+              b->order[rec[r].x], b->sent_T[rec[r].x], rec[r].y, sc[0], sc[1]);
   }
   return 0;
 }

@@ -577,7 +577,7 @@ struct RsCfg {
   // logit the epilogue paces the short-K tiles, and it is latency-bound, not pipe-bound - ncu on the 8-warp version
   // (profiles/r02/ncu_rs_cfg5_v2.csv): XU pipe 61 %, issue slots 45 %, tensor pipe 42 %, the stalls are fixed-latency
   // waits and MUFU / TMEM-load scoreboards of the two warps a scheduler had.
-  static constexpr int EPI_WARPS = 16;
+  static constexpr int EPI_WARPS = 16;      // also for K = 128 (measured with eight: 101 vs 94 us per launch at cfg 3)
   static constexpr int COL_PARTS = EPI_WARPS / 4;            // column slices of a tile, one partial each
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };

@@ -12,13 +12,14 @@ from jlm_b200 import config, synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 root = tempfile.mkdtemp(prefix='jlm_par_')
 cfg, weights, lexicon, reading = synth.make_experiment(root, 1, 50000, 512, 256, 'tied', seed=0)
-sents = synth.make_sentences(lexicon, n, min_len=20, seed=321, vocab_size=50000)
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 321
+sents = synth.make_sentences(lexicon, n, min_len=20, seed=seed, vocab_size=50000)
 config.set_root(root)
 dec = jlm_b200.Decoder(1)
 a = dec.decode_batch(sents, topN=10, beam_width=10, backend=1)
 gaps = sorted(min(abs(x[i + 1][0] - x[i][0]) for i in range(len(x) - 1)) for x in a if len(x) > 1)
 print('sentences %d, smallest adjacent n-best gap %.3e (median %.3e)' % (n, gaps[0], gaps[len(gaps) // 2]))
-for eps in (0.0, 0.0, -1.0, 3e-5, 1e-4, 3e-4, 1e-3):
+for eps in ((0.0, 0.0, -1.0, 3e-5, 1e-4, 3e-4, 1e-3) if len(sys.argv) <= 2 else (0.0, 1e-4)):
     dec.model.set_guard(eps)
     import time
     t0 = time.perf_counter()

@@ -311,11 +311,17 @@ def test_quantized_blocks_match_decoded_floats(mode, tmp_path_factory, monkeypat
     df = jlm_b200.Decoder(2)
     assert dq.model.quantized_blocks == {'tied': ['LM'], 'untied': ['UM'], 'dsoftmax_star': ['LM0', 'LM1', 'LM2']}[mode]
     assert df.model.quantized_blocks == []
+    # the arbiter is the CPU oracle on the decoded floats (what the reference itself loads, decoder/model.py:74-76)
+    from oracle import jlm_oracle as O
+    ora = O.OracleDecoder(cfg, decoded, lexicon, reading_dict)
     for s in sents:
         a = dq.decode(s, topN=5, beam_width=5, backend=EXACT)
         b = df.decode(s, topN=5, beam_width=5, backend=EXACT)
         assert [w for _, w in a] == [w for _, w in b]
         np.testing.assert_allclose([x for x, _ in a], [x for x, _ in b], rtol=0, atol=1e-11)
+        want = ora.decode(s, topN=5, beam_width=5)
+        assert [w for _, w in a] == [w for _, w in want]
+        np.testing.assert_allclose([x for x, _ in a], [x for x, _ in want], rtol=0, atol=2e-5)
     (pa, ya, _, _), ha, ca = dq.model.predict_with_context([1, 5, 17], np.zeros((3, 128)), np.zeros((3, 128)))
     (pb, yb, _, _), hb, cb = df.model.predict_with_context([1, 5, 17], np.zeros((3, 128)), np.zeros((3, 128)))
     np.testing.assert_allclose(ya, yb, rtol=0, atol=1e-11)

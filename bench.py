@@ -399,13 +399,21 @@ def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
         env.barrier()
         t0 = time.perf_counter()
         inflight = []
+        t_sub = t_col = 0.0
         for _ in range(n_steps):
+            t1 = time.perf_counter()
             inflight.append(e2e_submit())
+            t2 = time.perf_counter()
             if len(inflight) >= depth:
                 e2e_collect(inflight.pop(0))
+            t_sub += t2 - t1
+            t_col += time.perf_counter() - t2
         while inflight:
             e2e_collect(inflight.pop(0))
         env.barrier()
+        if os.environ.get('JLM_BENCH_E2E_DEBUG'):
+            sys.stderr.write('[bench] e2e depth %d: %.2f ms per batch in submit, %.2f ms in collect (host thread)\n'
+                             % (depth, 1e3 * t_sub / n_steps, 1e3 * t_col / n_steps))
         return env.reduce(time.perf_counter() - t0, 'MAX')
 
     for _ in range(2):

@@ -184,6 +184,11 @@ extern "C" int32_t jlm_destroy(jlm_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& cs : h->copy_stream)
+    if (cs) {
+      cudaStreamSynchronize(cs);
+      cudaStreamDestroy(cs);
+    }
   tc_free_weights(h);
   beam_free_plan_scratch(h);
   beam_free_guard(h);

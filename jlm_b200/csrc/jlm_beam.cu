@@ -22,6 +22,7 @@ namespace {
 // device kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_init_frame0(BeamDev d, int S) {
+  pdl_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
   const int fid = (int)d.fbase[p];
@@ -39,6 +40,7 @@ __global__ void k_init_frame0(BeamDev d, int S) {
 }
 
 __global__ void k_build_items(BeamDev d) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.n_items) return;
   const int n = d.start_items[i];
@@ -77,6 +79,7 @@ template <typename TT, bool DYN>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
               int64_t item0, int n_items, int64_t row0, int use_lse, int defer) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
   if (item >= n_items) return;
@@ -176,6 +179,7 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
 
 // Second half of a deferred k_score_nodes: cand_val holds -y; add the parent path's score and LSE.
 __global__ void k_add_base(BeamDev d, int64_t item0, int n_items, int W) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int item = (int)(i / W), r = (int)(i % W);
   if (item >= n_items) return;
@@ -260,6 +264,7 @@ constexpr int PRUNE_CAP = 96;   // survivors of the threshold filter a warp can 
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
 k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= nact) return;
@@ -432,6 +437,7 @@ constexpr int PB_CAP = 160;    // survivors per warp segment
 template <int L, bool DYN>
 __global__ void __launch_bounds__(128)
 k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_eps, int guard_all, int topN) {
+  pdl_enter();
   __shared__ double mins[128 * L];
   __shared__ double sv[4][PB_CAP];
   __shared__ int sc[4][PB_CAP];
@@ -662,6 +668,7 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_ep
 // Near-tie guard: the node sequences of the two candidates of every queued record, so the host can re-score both
 // paths in float64 (guard_resolve).  A candidate is (node, parent rank); its parent's slots hold the rest of the path.
 __global__ void k_guard_paths(BeamDev d, int max_len) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(*d.guard_n, d.guard_cap);
   if (i >= 2 * n) return;
@@ -694,6 +701,7 @@ __global__ void k_guard_paths(BeamDev d, int max_len) {
 template <bool DYN>
 __global__ void __launch_bounds__(128)
 k_keep_all(BeamDev d, int t, int tstride, int use_lse) {
+  pdl_enter();
   const int p = blockIdx.x;
   const int fid = (int)d.fbase[p] + t;
   const int nc = d.frame_ncand[fid];
@@ -719,6 +727,7 @@ k_keep_all(BeamDev d, int t, int tstride, int use_lse) {
 
 // decoder.py:237: walk the back-pointers of the best paths of the last frame.
 __global__ void k_backtrace(BeamDev d, int S, int topN, int max_len) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * topN) return;
   const int p = i / topN, k = i % topN;
@@ -752,6 +761,7 @@ struct RowLogits {
 __global__ void __launch_bounds__(128)
 k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv, double* __restrict__ lse_out,
                const float* __restrict__ y0, int ldy0, int n_shared) {
+  pdl_enter();
   const SubsetJob job = jobs[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -779,6 +789,7 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
                  const int32_t* __restrict__ vfp, const double* __restrict__ yv, double* __restrict__ dyn_lse,
                  double* dyn_chain, const int32_t* __restrict__ slot_parent, int64_t slot_base, int k, int tstride,
                  const float* __restrict__ y0, int ldy0, int n_shared, int fast_exp) {
+  pdl_enter();
   const SubsetJob job = jobs[blockIdx.y];
   const DynJobInfo inf = info[blockIdx.y];
   const int lane = threadIdx.x & 31;
@@ -1278,11 +1289,9 @@ int32_t launch_score(jlm_batch* b, int t, const TT* T, int ldt, cudaStream_t st,
   const int grid = ceil_div(sp.n_items, SC_WARPS);
   const int ul = b->use_lse ? 1 : 0;
   if (b->dynamic)
-    k_score_nodes<TT, true><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items,
-                                                           sp.row0, ul, 0);
+    JLM_CUDA(jlm_launch(k_score_nodes<TT, true>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0));
   else
-    k_score_nodes<TT, false><<<grid, SC_WARPS * 32, 0, st>>>(make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items,
-                                                            sp.row0, ul, defer);
+    JLM_CUDA(jlm_launch(k_score_nodes<TT, false>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer));
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   return 0;
@@ -1307,11 +1316,9 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
     dim3 grid(ceil_div(b->W, 4), sp.nstep);
     const int ns = (on_tc == 0) ? b->n_shared : 0;      // the shared block exists only when the tensor-core kernel ran
     if (b->dynamic)
-      k_dyn_prefix_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse,
-                                             d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1, b->y0, b->ldy0, ns,
-                                             on_tc == 0 ? 1 : 0);
+      JLM_CUDA(jlm_launch(k_dyn_prefix_lse, dim3(grid), dim3(128), 0, st, d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse, d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1, b->y0, b->ldy0, ns, on_tc == 0 ? 1 : 0));
     else
-      k_job_rows_lse<<<grid, 128, 0, st>>>(d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0, b->y0, b->ldy0, ns);
+      JLM_CUDA(jlm_launch(k_job_rows_lse, dim3(grid), dim3(128), 0, st, d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0, b->y0, b->ldy0, ns));
     JLM_CUDA(cudaGetLastError());
     b->launches += 2;
   }
@@ -1382,7 +1389,7 @@ int32_t launch_prune(jlm_batch* b, int t) {
   const int ul = b->use_lse ? 1 : 0;
   cudaStream_t st = b->h->stream;
   if (b->unlimited) {
-    k_keep_all<DYN><<<dim3(sp.nact, ceil_div(b->W, 128)), 128, 0, st>>>(b->d, t, b->Tmax + 1, ul);
+    JLM_CUDA(jlm_launch(k_keep_all<DYN>, dim3(dim3(sp.nact, ceil_div(b->W, 128))), dim3(128), 0, st, b->d, t, b->Tmax + 1, ul));
     JLM_CUDA(cudaGetLastError());
     b->launches += 1;
     return 0;
@@ -1393,17 +1400,17 @@ int32_t launch_prune(jlm_batch* b, int t) {
   }();
   if (block_mode || b->guard_eps > 0.0) {      // one CTA per sentence (the near-tie guard lives in this kernel)
     if (L <= 1)
-      k_prune_block<1, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN);
+      JLM_CUDA(jlm_launch(k_prune_block<1, DYN>, dim3(sp.nact), dim3(128), 0, st, b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN));
     else if (L <= 2)
-      k_prune_block<2, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN);
+      JLM_CUDA(jlm_launch(k_prune_block<2, DYN>, dim3(sp.nact), dim3(128), 0, st, b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN));
     else
-      k_prune_block<4, DYN><<<sp.nact, 128, 0, st>>>(b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN);
+      JLM_CUDA(jlm_launch(k_prune_block<4, DYN>, dim3(sp.nact), dim3(128), 0, st, b->d, t, b->W, b->Tmax + 1, ul, b->guard_eps, b->guard_all ? 1 : 0, b->topN));
   } else if (L <= 1)
-    k_prune<1, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+    JLM_CUDA(jlm_launch(k_prune<1, DYN>, dim3(grid), dim3(128), 0, st, b->d, t, sp.nact, b->W, b->Tmax + 1, ul));
   else if (L <= 2)
-    k_prune<2, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+    JLM_CUDA(jlm_launch(k_prune<2, DYN>, dim3(grid), dim3(128), 0, st, b->d, t, sp.nact, b->W, b->Tmax + 1, ul));
   else
-    k_prune<4, DYN><<<grid, 128, 0, st>>>(b->d, t, sp.nact, b->W, b->Tmax + 1, ul);
+    JLM_CUDA(jlm_launch(k_prune<4, DYN>, dim3(grid), dim3(128), 0, st, b->d, t, sp.nact, b->W, b->Tmax + 1, ul));
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   return 0;
@@ -1735,6 +1742,7 @@ static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
     if (need_full[p]) which.push_back(b->order[p]);
   b->n_rerun = (int)which.size();
   if (which.empty()) return 0;
+  b->h->tier2_recent = 16;
   std::sort(which.begin(), which.end());
   GuardLattice& G = *b->guard_lat;
   const jlm_lattice_batch sub = G.subset(which, b->mode);
@@ -1759,6 +1767,9 @@ static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
   }
   h->stream = main_stream;
   if (rc) return rc;
+  if (dbg)
+    fprintf(stderr, "[jlm] guard: tier 2 re-decoded %d sentences in float64, %.3f ms since the fetch\n", (int)which.size(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_0).count());
   for (size_t k = 0; k < which.size(); ++k) b->rerun_index[which[k]] = (int)k;
   return 0;
 }
@@ -1768,6 +1779,26 @@ void beam_free_guard(jlm_handle* h) {
   h->guard_pool = nullptr;
   if (h->guard_stream) cudaStreamDestroy(h->guard_stream);
   h->guard_stream = nullptr;
+}
+
+// Optional copy streams of the handle (JLM_COPY_STREAM=1): plan upload and n-best download beside the neighbouring
+// batches' kernels instead of between them (two streams - on one, the upload of batch k+1 would queue behind the
+// download of batch k, which waits for batch k's kernels).  OFF by default: the ~0.35 ms the in-stream copies leave
+// the SMs idle per batch is where the near-tie guard's float64 kernels of the previous batch run; measured with three
+// batches in flight (cfg 2): 1.30 M chars/s with the copies in-stream, 1.17 M with the copy streams.
+static cudaStream_t copy_stream_of(jlm_handle* h, int which) {
+  static const int on = [] {
+    const char* e = getenv("JLM_COPY_STREAM");
+    return e ? atoi(e) : 0;
+  }();
+  if (!on) return h->stream;
+  cudaStream_t& cs = h->copy_stream[which];
+  if (!cs && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    cs = nullptr;
+    return h->stream;
+  }
+  return cs;
 }
 
 void beam_free_plan_scratch(jlm_handle* h) {
@@ -1891,8 +1922,13 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
       stage(host, base, b->d.dyn_info, P.dyn_info);
       stage(host, base, b->d.vocab_cols, P.vocab_cols);
       stage(host, base, b->d.vfp, P.vfp);
-      if (cudaMemcpyAsync(base, host, plan_bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
-          cudaEventRecord(h->stage_ev[slot], h->stream) != cudaSuccess) {
+      // The copy goes through the handle's copy stream and the compute stream waits for its event: enqueued on the
+      // compute stream itself it would sit between the previous batch's last kernel and this batch's first one with
+      // the SMs idle (~0.25 ms per 1024-sentence plan); the arena is idle (jlm_batch_destroy waited for its last user).
+      cudaStream_t cs = copy_stream_of(h, 0);
+      if (cudaMemcpyAsync(base, host, plan_bytes, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+          cudaEventRecord(h->stage_ev[slot], cs) != cudaSuccess ||
+          (cs != h->stream && cudaStreamWaitEvent(h->stream, h->stage_ev[slot], 0) != cudaSuccess)) {
         jlm_set_error("jlm_batch_upload: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = 1;
       } else {
@@ -1917,6 +1953,21 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   cudaStream_t st = h->stream;
   b->launches = 0;
   guard_drop_rerun(b);
+  // Launch chaining (pdl_enter, jlm_common.cuh) removes the points where the device drains between kernels - and those
+  // are where the near-tie guard's float64 kernels (own stream, highest priority) get their SMs.  Measured with three
+  // batches in flight and a float64 re-decode in every batch (bench.py e2e arm, cfg 2 / cfg 5): 1.41 -> 1.30 and
+  // 0.235 -> 0.213 M chars/s with chaining, while batches without re-decodes gain (cfg 3 e2e 1.98 -> 2.15 M, blocking
+  // cfg 2 16.4 -> 15.9 ms).  So a batch is chained unless another batch is still in flight AND one of the last
+  // sixteen batches needed a re-decode.
+  const bool main_tc = b->backend == JLM_BACKEND_TC && st != h->guard_stream;
+  const PdlOff plain(main_tc && h->batches_unfetched > 0 && h->tier2_recent > 0);
+  if (main_tc) {
+    if (h->tier2_recent > 0) --h->tier2_recent;
+    if (!b->counted) {
+      b->counted = true;
+      ++h->batches_unfetched;
+    }
+  }
   if (b->backend == JLM_BACKEND_TC && score_overlap_enabled()) {
     if (!h->side_stream) JLM_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     if (!b->ev_fork) JLM_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -1931,9 +1982,9 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   for (int t = 0; t < b->n_steps; ++t) {
     if (b->timers) cudaEventRecord(b->events[3 * t], st);
     if (t == 0) {
-      k_init_frame0<<<ceil_div(b->S, 128), 128, 0, st>>>(b->d, b->S);
+      JLM_CUDA(jlm_launch(k_init_frame0, dim3(ceil_div(b->S, 128)), dim3(128), 0, st, b->d, b->S));
       JLM_CUDA(cudaGetLastError());
-      k_build_items<<<ceil_div(b->d.n_items, 256), 256, 0, st>>>(b->d);
+      JLM_CUDA(jlm_launch(k_build_items, dim3(ceil_div(b->d.n_items, 256)), dim3(256), 0, st, b->d));
       JLM_CUDA(cudaGetLastError());
       b->launches += 2;
     } else if (b->dynamic) {
@@ -1962,7 +2013,7 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
       if (overlap) {
         const StepPlan& sp = b->steps[t];
         JLM_CUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
-        k_add_base<<<ceil_div((int64_t)sp.n_items * b->W, 256), 256, 0, st>>>(b->d, sp.item0, sp.n_items, b->W);
+        JLM_CUDA(jlm_launch(k_add_base, dim3(ceil_div((int64_t)sp.n_items * b->W, 256)), dim3(256), 0, st, b->d, sp.item0, sp.n_items, b->W));
         JLM_CUDA(cudaGetLastError());
         b->launches += 1;
       } else if (T32) {
@@ -1972,11 +2023,11 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   }
   if (b->timers) cudaEventRecord(b->events[3 * (size_t)b->n_steps], st);
   if (b->guard_eps > 0.0) {
-    k_guard_paths<<<ceil_div(2 * (int64_t)b->d.guard_cap, 128), 128, 0, st>>>(b->d, b->max_len);
+    JLM_CUDA(jlm_launch(k_guard_paths, dim3(ceil_div(2 * (int64_t)b->d.guard_cap, 128)), dim3(128), 0, st, b->d, b->max_len));
     JLM_CUDA(cudaGetLastError());
     b->launches += 1;
   }
-  k_backtrace<<<ceil_div((int64_t)b->S * b->topN, 128), 128, 0, st>>>(b->d, b->S, b->topN, b->max_len);
+  JLM_CUDA(jlm_launch(k_backtrace, dim3(ceil_div((int64_t)b->S * b->topN, 128)), dim3(128), 0, st, b->d, b->S, b->topN, b->max_len));
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   b->ran = true;
@@ -2009,8 +2060,12 @@ extern "C" int32_t jlm_batch_fetch_async(jlm_batch* b) {
     h->out_pool.erase(h->out_pool.begin() + pick);
   }
   JLM_TRY(b->out_host.reserve(total));
-  JLM_CUDA(cudaMemcpyAsync(b->out_host.p, src, total, cudaMemcpyDeviceToHost, h->stream));
-  JLM_CUDA(cudaEventRecord(b->done, h->stream));
+  // behind this batch's kernels (b->done, recorded by jlm_batch_run) but on the copy stream: the next batch's
+  // kernels, already enqueued on the compute stream, do not wait for the transfer
+  cudaStream_t cs = copy_stream_of(h, 1);
+  if (cs != h->stream) JLM_CUDA(cudaStreamWaitEvent(cs, b->done, 0));
+  JLM_CUDA(cudaMemcpyAsync(b->out_host.p, src, total, cudaMemcpyDeviceToHost, cs));
+  JLM_CUDA(cudaEventRecord(b->done, cs));
   b->d2h_bytes = (int64_t)total;
   b->d2h_queued = true;
   return 0;
@@ -2026,6 +2081,10 @@ extern "C" int32_t jlm_batch_fetch(jlm_batch* b, jlm_nbest* out) {
   JLM_CUDA(cudaSetDevice(h->device));
   JLM_TRY(jlm_batch_fetch_async(b));
   JLM_CUDA(cudaEventSynchronize(b->done));   // this batch only: later batches keep running
+  if (b->counted) {
+    b->counted = false;
+    --h->batches_unfetched;
+  }
   const char* src = reinterpret_cast<const char*>(b->d.guard_gap);
   const char* host = b->out_host.as<char>();
   const double* sc = reinterpret_cast<const double*>(host + (reinterpret_cast<const char*>(b->d.out_score) - src));
@@ -2117,6 +2176,8 @@ extern "C" int32_t jlm_batch_destroy(jlm_batch* b) {
   } else {
     cudaStreamSynchronize(b->h->stream);
   }
+  if (b->counted) --b->h->batches_unfetched;
+  b->counted = false;
   guard_drop_rerun(b);
   delete b->guard_lat;
   b->guard_lat = nullptr;

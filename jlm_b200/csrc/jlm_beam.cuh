@@ -88,6 +88,7 @@ struct jlm_batch {
   bool use_lse = true;
   bool dynamic = false;
   bool unlimited = false;        // beam_width=None: no sort, no prune (W = widest frame of the plan)
+  bool counted = false;          // this batch is in jlm_handle::batches_unfetched
   // Near-tie guard.  The tensor-core back end carries fp32 state and fp32-accumulated logits, so two candidates
   // whose float64 scores differ by less than its error can come out in the other order.  With guard_eps > 0 the
   // prune kernel flags every sentence in which a rank decision (adjacent kept paths, or the last kept path against

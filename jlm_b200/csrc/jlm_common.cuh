@@ -38,6 +38,77 @@ void jlm_set_error(const char* fmt, ...);
 static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library starts with pdl_enter(): it lets the NEXT kernel of the stream be scheduled as soon as all
+// CTAs of this one are running (griddepcontrol.launch_dependents) and then waits until everything the PREVIOUS kernels
+// wrote is visible (griddepcontrol.wait) before it touches global memory.  With jlm_launch() (below) the launch
+// latency, the CTA ramp and - for the GEMM kernels, which call it after their barrier / TMEM set-up - the prologue of
+// kernel k+1 hide under the tail of kernel k; a lock-step frame is 7-9 dependent launches.  Both instructions are
+// no-ops for a kernel launched without the attribute.  A kernel that allocates TMEM calls pdl_enter() AFTER the
+// allocation: a dependent CTA that became co-resident and took the columns first would wait forever on a
+// predecessor that cannot get them.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Every CTA of a kernel must pass a wait before it exits (also one that has nothing to do): a grid that finished
+// without waiting would let ITS dependent start reading what the grid before it is still writing.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+#endif
+
+// Launches made while a PdlOff object lives on this thread are plain (see jlm_batch_run for when).
+inline thread_local int jlm_pdl_off_depth = 0;
+struct PdlOff {
+  bool on;
+  explicit PdlOff(bool off) : on(off) { if (on) ++jlm_pdl_off_depth; }
+  ~PdlOff() { if (on) --jlm_pdl_off_depth; }
+  PdlOff(const PdlOff&) = delete;
+  PdlOff& operator=(const PdlOff&) = delete;
+};
+
+static inline bool jlm_pdl_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0 && jlm_pdl_off_depth == 0;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with programmatic stream serialization (JLM_PDL=0: a plain launch)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t jlm_launch_opt(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && jlm_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t jlm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = jlm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int JLM_KALIGN = 64;  // every GEMM K extent on the device is padded to this (zero filled)
 
 // Grow-only device / pinned-host buffers, reused across calls so the steady state allocates nothing.
@@ -123,6 +194,7 @@ struct jlm_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t side_stream = nullptr;   // needed-word dot products run here while the output GEMM holds `stream`
+  cudaStream_t copy_stream[2] = {};     // [0] plan H2D, [1] n-best D2H of a batch: beside the previous / next batch's kernels
   int sm_count = 148;
   jlm_config cfg{};
   int V = 0, H = 0, E = 0;
@@ -147,6 +219,8 @@ struct jlm_handle {
   bool guard_verify = true;                   // tier 1 (re-score the near-tied pairs) before tier 2 (re-decode the sentence)
   jlm_pool* guard_pool = nullptr;             // float64 state pool the guard re-scores near-tied paths with
   cudaStream_t guard_stream = nullptr;        // ... on its own stream, beside the next batch's kernels
+  int batches_unfetched = 0;                  // tensor-core batches run but not yet fetched (a streaming caller keeps several)
+  int tier2_recent = 0;                       // > 0: one of the last batches needed a float64 re-decode (launch chaining policy)
   void* plan_scratch = nullptr;   // host vectors of the last batch plan, reused by the next upload (jlm_beam.cu)
   TcWeights* tc = nullptr;
   // scratch for the model-level API and the batch engine

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256)
 k_gemm_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
            const float* __restrict__ bias, double* __restrict__ C, int64_t ldc, int M, int N, int K,
            double2* __restrict__ part, int part_ld, int part_tile0) {
+  pdl_enter();
   constexpr int BM = 16 * TM;
   __shared__ double As[BM][BK + 2];
   __shared__ TB Bs[BK][BN + 1];
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(COLS / CPT * KG)
 k_skinny_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
              const float* __restrict__ codebook, const float* __restrict__ bias, double* __restrict__ C,
              int64_t ldc, int M, int N, int K, double2* __restrict__ part, int part_ld, int part_tile0) {
+  pdl_enter();
   extern __shared__ __align__(16) double smem_sk[];
   constexpr int SK_THREADS = COLS / CPT * KG;
   constexpr int VEC = SkLoad<TB>::VEC;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(32 * ST_KG)
 k_stream_f64(const double* __restrict__ A, int lda, const float* __restrict__ B, int ldb, const float* __restrict__ bias,
              double* __restrict__ C, int64_t ldc, int M, int N, int K, double2* __restrict__ part, int part_ld,
              int part_tile0) {
+  pdl_enter();
   constexpr int ST_THREADS = 32 * ST_KG;
   extern __shared__ __align__(128) unsigned char smem_st[];
   const int tile_bytes = ST_COLS * K * 4;
@@ -369,6 +372,7 @@ template <typename TB, int MT>
 __global__ void __launch_bounds__(256)
 k_warpcol_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb, const float* __restrict__ bias,
               double* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  pdl_enter();
   constexpr int VEC = 16 / (int)sizeof(TB);
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -409,6 +413,7 @@ k_warpcol_f64(const double* __restrict__ A, int lda, const TB* __restrict__ B, i
 
 __global__ void k_lse_merge(const double2* __restrict__ part, int part_ld, int n_tiles, int M,
                             double* __restrict__ lse, int self_norm) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -429,6 +434,7 @@ __global__ void k_lse_merge(const double2* __restrict__ part, int part_ld, int n
 }
 
 __global__ void k_rows_lse(const double* __restrict__ y, int64_t ld, int M, int N, double* __restrict__ lse) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -446,6 +452,7 @@ __global__ void k_rows_lse(const double* __restrict__ y, int64_t ld, int M, int 
 
 __global__ void k_softmax_rows(const double* __restrict__ y, int64_t ld, int M, int N,
                                const double* __restrict__ lse, double* __restrict__ pred) {
+  pdl_enter();
   const int64_t total = (int64_t)M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / N);
@@ -458,6 +465,7 @@ __global__ void k_softmax_rows(const double* __restrict__ y, int64_t ld, int M, 
 __global__ void k_gather_gate_input(const double* __restrict__ h_src, const int32_t* __restrict__ parent,
                                     const int32_t* __restrict__ word, const float* __restrict__ LM_in, int Hp,
                                     int Ep, int M, double* __restrict__ A) {
+  pdl_enter();
   const int Kg = Hp + Ep;
   const int64_t total = (int64_t)M * Kg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -478,6 +486,7 @@ __global__ void k_gather_gate_input(const double* __restrict__ h_src, const int3
 __global__ void k_lstm_pointwise(const double* __restrict__ gates, const double* __restrict__ c_src,
                                  const int32_t* __restrict__ parent, int H, int Hp, int M,
                                  double* __restrict__ h_out, double* __restrict__ c_out) {
+  pdl_enter();
   const int64_t total = (int64_t)M * Hp;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(idx / Hp);
@@ -515,6 +524,7 @@ __global__ void __launch_bounds__(VL_COLS)
 k_vocab_logits(SegTable seg, const TT* __restrict__ T, int64_t ldt, const SubsetJob* __restrict__ jobs,
                const int32_t* __restrict__ cols, const int32_t* __restrict__ bias_idx,
                const float* __restrict__ b2, double* __restrict__ out) {
+  pdl_enter();
   __shared__ __align__(16) double Ts[VL_RC][VL_KC];
   __shared__ __align__(16) float Ws[VL_COLS][VL_KC + 2];
   __shared__ int32_t Wid[VL_COLS];
@@ -621,14 +631,12 @@ int32_t launch_skinny(cudaStream_t st, const double* A, int lda, const TB* B, in
   constexpr int VEC = 16 / (int)sizeof(TB);
   if (part || N > 8192 || sizeof(TB) == 1 || K % (16 * VEC) != 0) {
     const size_t smem = ((size_t)M * K + (size_t)8 * MT * 64 + 256) * sizeof(double);
-    k_skinny_f64<TB, MT, 64, 2, 8><<<ceil_div(N, 64), 256, smem, st>>>(A, lda, B, ldb, codebook, bias, C, ldc, M, N, K,
-                                                                      part, part_ld, part_tile0);
+    JLM_CUDA(jlm_launch(k_skinny_f64<TB, MT, 64, 2, 8>, dim3(ceil_div(N, 64)), dim3(256), smem, st, A, lda, B, ldb, codebook, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   } else if (warpcol_enabled() && C && K % (32 * VEC) == 0) {
-    k_warpcol_f64<TB, MT><<<ceil_div(N, 8), 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+    JLM_CUDA(jlm_launch(k_warpcol_f64<TB, MT>, dim3(ceil_div(N, 8)), dim3(256), 0, st, A, lda, B, ldb, bias, C, ldc, M, N, K));
   } else {
     const size_t smem = ((size_t)M * K + (size_t)16 * MT * 32 + 256) * sizeof(double);
-    k_skinny_f64<TB, MT, 32, 1, 16><<<ceil_div(N, 32), 512, smem, st>>>(A, lda, B, ldb, codebook, bias, C, ldc, M, N, K,
-                                                                       nullptr, 0, 0);
+    JLM_CUDA(jlm_launch(k_skinny_f64<TB, MT, 32, 1, 16>, dim3(ceil_div(N, 32)), dim3(512), smem, st, A, lda, B, ldb, codebook, bias, C, ldc, M, N, K, nullptr, 0, 0));
   }
   JLM_CUDA(cudaGetLastError());
   return 0;
@@ -663,7 +671,7 @@ int32_t launch_stream_mt(cudaStream_t st, const double* A, int lda, const float*
   }
   const size_t smem = (size_t)2 * ST_COLS * K * 4 + ((size_t)M * K + (size_t)KG * MT * ST_COLS) * sizeof(double);
   const int grid = std::min(ceil_div(N, ST_COLS), sm_count);
-  k_stream_f64<MT, KG><<<grid, 32 * KG, smem, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+  JLM_CUDA(jlm_launch(k_stream_f64<MT, KG>, dim3(grid), dim3(32 * KG), smem, st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -715,13 +723,13 @@ int32_t launch_gemm(cudaStream_t st, const double* A, int lda, const TB* B, int 
     JLM_TRY(skinny_dispatch<TB>(st, A, lda, B, ldb, nullptr, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   } else if (M <= 16) {
     dim3 grid(ceil_div(N, BN), ceil_div(M, 16));
-    k_gemm_f64<TB, 1><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+    JLM_CUDA(jlm_launch(k_gemm_f64<TB, 1>, dim3(grid), dim3(256), 0, st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   } else if (M <= 32) {
     dim3 grid(ceil_div(N, BN), ceil_div(M, 32));
-    k_gemm_f64<TB, 2><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+    JLM_CUDA(jlm_launch(k_gemm_f64<TB, 2>, dim3(grid), dim3(256), 0, st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   } else {
     dim3 grid(ceil_div(N, BN), ceil_div(M, 64));
-    k_gemm_f64<TB, 4><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0);
+    JLM_CUDA(jlm_launch(k_gemm_f64<TB, 4>, dim3(grid), dim3(256), 0, st, A, lda, B, ldb, bias, C, ldc, M, N, K, part, part_ld, part_tile0));
   }
   JLM_CUDA(cudaGetLastError());
   return 0;
@@ -759,14 +767,14 @@ int32_t exact_gemm_f64w(cudaStream_t st, const double* A, int lda, const double*
 int32_t exact_lse_merge(cudaStream_t st, const double2* part, int part_ld, int n_tiles, int M, double* lse,
                         int self_norm) {
   if (M <= 0) return 0;
-  k_lse_merge<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(part, part_ld, n_tiles, M, lse, self_norm);
+  JLM_CUDA(jlm_launch(k_lse_merge, dim3(ceil_div((int64_t)M * 32, 256)), dim3(256), 0, st, part, part_ld, n_tiles, M, lse, self_norm));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
 
 int32_t exact_rows_lse(cudaStream_t st, const double* y, int64_t ld, int M, int N, double* lse) {
   if (M <= 0) return 0;
-  k_rows_lse<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(y, ld, M, N, lse);
+  JLM_CUDA(jlm_launch(k_rows_lse, dim3(ceil_div((int64_t)M * 32, 256)), dim3(256), 0, st, y, ld, M, N, lse));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -774,7 +782,7 @@ int32_t exact_rows_lse(cudaStream_t st, const double* y, int64_t ld, int M, int 
 int32_t exact_softmax_rows(cudaStream_t st, const double* y, int64_t ld, int M, int N, const double* lse,
                            double* pred) {
   if (M <= 0 || N <= 0) return 0;
-  k_softmax_rows<<<grid_1d((int64_t)M * N, 256, 148 * 16), 256, 0, st>>>(y, ld, M, N, lse, pred);
+  JLM_CUDA(jlm_launch(k_softmax_rows, dim3(grid_1d((int64_t)M * N, 256, 148 * 16)), dim3(256), 0, st, y, ld, M, N, lse, pred));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -782,8 +790,7 @@ int32_t exact_softmax_rows(cudaStream_t st, const double* y, int64_t ld, int M, 
 int32_t exact_gather_gate_input(cudaStream_t st, const jlm_handle* h, const double* h_src, const int32_t* parent,
                                 const int32_t* word, int M, double* A) {
   if (M <= 0) return 0;
-  k_gather_gate_input<<<grid_1d((int64_t)M * h->Kg, 256, 148 * 16), 256, 0, st>>>(h_src, parent, word, h->LM_in,
-                                                                                 h->Hp, h->Ep, M, A);
+  JLM_CUDA(jlm_launch(k_gather_gate_input, dim3(grid_1d((int64_t)M * h->Kg, 256, 148 * 16)), dim3(256), 0, st, h_src, parent, word, h->LM_in, h->Hp, h->Ep, M, A));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -791,8 +798,7 @@ int32_t exact_gather_gate_input(cudaStream_t st, const jlm_handle* h, const doub
 int32_t exact_lstm_pointwise(cudaStream_t st, const jlm_handle* h, const double* gates, const double* c_src,
                              const int32_t* parent, int M, double* h_out, double* c_out) {
   if (M <= 0) return 0;
-  k_lstm_pointwise<<<grid_1d((int64_t)M * h->Hp, 256, 148 * 16), 256, 0, st>>>(gates, c_src, parent, h->H, h->Hp, M,
-                                                                              h_out, c_out);
+  JLM_CUDA(jlm_launch(k_lstm_pointwise, dim3(grid_1d((int64_t)M * h->Hp, 256, 148 * 16)), dim3(256), 0, st, gates, c_src, parent, h->H, h->Hp, M, h_out, c_out));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -805,7 +811,7 @@ int32_t subset_logits(cudaStream_t st, const jlm_handle* h, const TT* T, int64_t
   for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
     const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
     dim3 grid(gx, nj);
-    k_vocab_logits<TT><<<grid, VL_COLS, 0, st>>>(make_seg_table(h), T, ldt, jobs + j0, cols, bias_idx, h->b2, out);
+    JLM_CUDA(jlm_launch(k_vocab_logits<TT>, dim3(grid), dim3(VL_COLS), 0, st, make_seg_table(h), T, ldt, jobs + j0, cols, bias_idx, h->b2, out));
   }
   JLM_CUDA(cudaGetLastError());
   return 0;

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256)
 k_pool_nll(SegTable seg, const double* __restrict__ T, int64_t ldt, const double* __restrict__ lse,
            const float* __restrict__ b2, const int32_t* __restrict__ slot, const int32_t* __restrict__ col, int n,
            int use_lse, double* __restrict__ out) {
+  pdl_enter();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
@@ -51,6 +52,7 @@ k_pool_nll(SegTable seg, const double* __restrict__ T, int64_t ldt, const double
 
 __global__ void k_pool_gather_T(const double* __restrict__ T, int64_t ldt, const int32_t* __restrict__ slots, int n,
                                 double* __restrict__ out) {
+  pdl_enter();
   const int64_t total = (int64_t)n * ldt;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = T[(int64_t)slots[i / ldt] * ldt + i % ldt];
@@ -58,6 +60,7 @@ __global__ void k_pool_gather_T(const double* __restrict__ T, int64_t ldt, const
 
 __global__ void k_pool_scatter_lse(const double* __restrict__ tmp, const int32_t* __restrict__ slots, int n,
                                    double* __restrict__ lse) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) lse[slots[i]] = tmp[i];
 }
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(128)
 k_pool_lse_subset(SegTable seg, const double* __restrict__ T, int64_t ldt, const float* __restrict__ b2,
                   const int32_t* __restrict__ slots, const int64_t* __restrict__ col_ptr, const int32_t* __restrict__ cols,
                   double* __restrict__ out) {
+  pdl_enter();
   __shared__ double wm[4], ws[4];
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t c0 = col_ptr[r], c1 = col_ptr[r + 1];
@@ -190,7 +194,7 @@ int32_t pool_lse_slots(jlm_pool* p, const int32_t* slots, int32_t n) {
   double* Tg = p->G.as<double>();
   double* lse_tmp = Tg + (size_t)n * p->ldt;
   JLM_CUDA(cudaMemcpyAsync(d_slots, slots, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-  k_pool_gather_T<<<ceil_div((int64_t)n * p->ldt, 256), 256, 0, st>>>(p->T, p->ldt, d_slots, n, Tg);
+  JLM_CUDA(jlm_launch(k_pool_gather_T, dim3(ceil_div((int64_t)n * p->ldt, 256)), dim3(256), 0, st, p->T, p->ldt, d_slots, n, Tg));
   JLM_CUDA(cudaGetLastError());
   double2* part = p->part.as<double2>();
   int tile0 = 0;
@@ -202,7 +206,7 @@ int32_t pool_lse_slots(jlm_pool* p, const int32_t* slots, int32_t n) {
     tile0 += exact_tiles_n(Vi);
   }
   JLM_TRY(exact_lse_merge(st, part, p->tiles, p->tiles, n, lse_tmp, 0));
-  k_pool_scatter_lse<<<ceil_div(n, 256), 256, 0, st>>>(lse_tmp, d_slots, n, p->lse);
+  JLM_CUDA(jlm_launch(k_pool_scatter_lse, dim3(ceil_div(n, 256)), dim3(256), 0, st, lse_tmp, d_slots, n, p->lse));
   JLM_CUDA(cudaGetLastError());
   return 0;      // asynchronous: later users of p->idx / p->G enqueue behind these kernels on the same stream
 }
@@ -222,7 +226,7 @@ int32_t pool_lse_subsets(jlm_pool* p, int32_t n, const int32_t* slots, const int
   JLM_CUDA(cudaMemcpyAsync(d_ptr, col_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
   JLM_CUDA(cudaMemcpyAsync(d_slots, slots, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
   JLM_CUDA(cudaMemcpyAsync(d_cols, cols, sizeof(int32_t) * (size_t)nc, cudaMemcpyHostToDevice, st));
-  k_pool_lse_subset<<<n, 128, 0, st>>>(make_seg_table(h), p->T, p->ldt, h->b2, d_slots, d_ptr, d_cols, d_out);
+  JLM_CUDA(jlm_launch(k_pool_lse_subset, dim3(n), dim3(128), 0, st, make_seg_table(h), p->T, p->ldt, h->b2, d_slots, d_ptr, d_cols, d_out));
   JLM_CUDA(cudaGetLastError());
   JLM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
   JLM_CUDA(cudaStreamSynchronize(st));
@@ -291,8 +295,7 @@ extern "C" int32_t jlm_pool_nll(jlm_pool* p, int32_t n, const int32_t* slot, con
   int32_t* d_col = d_slot + n;
   JLM_CUDA(cudaMemcpyAsync(d_slot, slot, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
   JLM_CUDA(cudaMemcpyAsync(d_col, col, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-  k_pool_nll<<<ceil_div((int64_t)n * 32, 256), 256, 0, st>>>(make_seg_table(h), p->T, p->ldt, p->lse, h->b2, d_slot, d_col,
-                                                            n, h->cfg.self_norm ? 0 : 1, p->out.as<double>());
+  JLM_CUDA(jlm_launch(k_pool_nll, dim3(ceil_div((int64_t)n * 32, 256)), dim3(256), 0, st, make_seg_table(h), p->T, p->ldt, p->lse, h->b2, d_slot, d_col, n, h->cfg.self_norm ? 0 : 1, p->out.as<double>()));
   JLM_CUDA(cudaGetLastError());
   JLM_CUDA(cudaMemcpyAsync(p->out_host.p, p->out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   JLM_CUDA(cudaStreamSynchronize(st));

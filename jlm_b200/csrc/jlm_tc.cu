@@ -213,6 +213,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // Barriers, TMEM and tensor maps are set up: from here on global memory is read and written.  The trigger comes late
+  // (producer thread, when it starts this CTA's LAST tile): a persistent GEMM lives for hundreds of microseconds, and
+  // dependents that became resident at its start would sit on the SMs' thread slots all that time - measured: the
+  // near-tie guard's short float64 kernels (other stream, highest priority) then wait a whole GEMM each for a slot
+  // and the streaming end-to-end rate drops 6 %.
+  pdl_wait();
 
   // tiles: CG == 1 -> 128-row blocks; CG == 2 -> 256-row blocks, rows [rank*128, +128) of each belong to this CTA
   const int num_m_units = (CG == 2) ? (g.num_m_blocks + 1) / 2 : g.num_m_blocks;
@@ -226,6 +232,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUten
       uint32_t phase = 0;
       for (int tile = unit; tile < num_tiles; tile += n_units) {
         const int m_blk = (tile % num_m_units) * CG + (int)rank, n_blk = tile / num_m_units;
+        if (tile + n_units >= num_tiles) pdl_trigger();
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE;
@@ -568,11 +575,13 @@ struct RsCfg {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = KB * 2 * A_TILE;                 // hi + lo, 128 rows x 64 per k-block
   static constexpr int B_HALF = (BN / 2) * BK * 2;                // one k-block of this CTA's half of the N tile
-  static constexpr int B_STAGE = KB * 2 * B_HALF;
-  static constexpr int STAGES = (KB == 1) ? 4 : 2;
-  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  // the weight ring holds single k-blocks (hi + lo, 32 KB): four of them beside a one- or two-block A operand; with
+  // K = 256 (A = 128 KB) three still fit, 3/4 of a tile ahead of the MMAs - the depth k_tc_gemm's pair ring has
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int STAGES = (KB <= 2) ? 4 : 3;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + BAR_BYTES + 1024;
+  static_assert(SMEM <= 227 * 1024, "row-stationary kernel: A operand + weight ring exceed the shared memory of an SM");
   // Sixteen epilogue warps, four per TMEM lane quarter (each takes a quarter of the tile's columns): with one exp per
   // logit the epilogue paces the short-K tiles, and it is latency-bound, not pipe-bound - ncu on the 8-warp version
   // (profiles/r02/ncu_rs_cfg5_v2.csv): XU pipe 61 %, issue slots 45 %, tensor pipe 42 %, the stalls are fixed-latency
@@ -606,8 +615,7 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t a_base = base;
   const uint32_t b_base = base + C::A_BYTES;
-  float* bias_s = reinterpret_cast<float*>(gen + C::A_BYTES + C::STAGES * C::B_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + C::A_BYTES + C::STAGES * C::B_STAGE + C::BIAS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + C::A_BYTES + C::STAGES * C::B_STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 6);
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -646,6 +654,7 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();      // trigger: producer thread at the pair's last tile (see k_tc_gemm)
 
   // this pair's contiguous tile range, tile id = m_unit * NT + n_blk
   const int NT = g.num_n_blocks;
@@ -659,6 +668,7 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
       uint32_t phase = 0, a_phase = 0;
       for (int tile = t_lo; tile < t_hi; ++tile) {
         const int m_unit = tile / NT, n_blk = tile - m_unit * NT;
+        if (tile + 1 == t_hi) pdl_trigger();
         if (m_unit != cur_m) {      // new row block: wait until the MMAs of the previous one have read A
           ptx::mbar_wait(aempty_bar, a_phase ^ 1u);
           a_phase ^= 1u;
@@ -671,18 +681,19 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
           }
           cur_m = m_unit;
         }
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::B_STAGE);
-        const uint32_t sb = b_base + stage * C::B_STAGE;
         const int b_row = n_blk * BN + (int)rank * (BN / 2);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          ptx::tma_load_2d_pair(sb + kb * 2 * C::B_HALF, &mBh, full_bar(stage), kb * BK, b_row);
-          ptx::tma_load_2d_pair(sb + kb * 2 * C::B_HALF + C::B_HALF, &mBl, full_bar(stage), kb * BK, b_row);
-        }
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1u;
+          if (kb * BK >= g.K16) break;                      // a k-block of nothing but zero padding is not fetched
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::B_STAGE);
+          const uint32_t sb = b_base + stage * C::B_STAGE;
+          ptx::tma_load_2d_pair(sb, &mBh, full_bar(stage), kb * BK, b_row);
+          ptx::tma_load_2d_pair(sb + C::B_HALF, &mBl, full_bar(stage), kb * BK, b_row);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -700,33 +711,34 @@ k_tc_lse_rs(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUt
           cur_m = m_unit;
         }
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        ptx::mbar_wait(full_bar(stage), phase);
-        ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const uint32_t sb = b_base + stage * C::B_STAGE;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
+          if (kb * BK >= g.K16) break;
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sb = b_base + stage * C::B_STAGE;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (kb * BK + k * 16 < g.K16) {
               const uint64_t ah = ptx::umma_desc_sw128(a_base + kb * 2 * A_TILE + k * 32);
               const uint64_t al = ptx::umma_desc_sw128(a_base + kb * 2 * A_TILE + A_TILE + k * 32);
-              const uint64_t bh = ptx::umma_desc_sw128(sb + kb * 2 * C::B_HALF + k * 32);
-              const uint64_t bl = ptx::umma_desc_sw128(sb + kb * 2 * C::B_HALF + C::B_HALF + k * 32);
+              const uint64_t bh = ptx::umma_desc_sw128(sb + k * 32);
+              const uint64_t bl = ptx::umma_desc_sw128(sb + C::B_HALF + k * 32);
               ptx::mma_f16_ss_pair(d_tmem, ah, bl, idesc, (kb | k) != 0 ? 1u : 0u);
               ptx::mma_f16_ss_pair(d_tmem, al, bh, idesc, 1u);
               ptx::mma_f16_ss_pair(d_tmem, ah, bh, idesc, 1u);
             }
           }
+          ptx::tc_commit_pair(empty_bar(stage), 3);      // this k-block's weight stage is free once its MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        ptx::tc_commit_pair(empty_bar(stage), 3);
         // last tile of this row block in our range: once its MMAs are done the A operand may be overwritten
         if (tile + 1 == t_hi || (tile + 1) / NT != m_unit) ptx::tc_commit_pair(aempty_bar, 3);
         ptx::tc_commit_pair(tfull_bar(acc), 3);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -850,6 +862,7 @@ __global__ void k_tc_gather_rows(const __half* __restrict__ H_hi, const __half* 
                                  const int32_t* __restrict__ parent, const int32_t* __restrict__ word,
                                  const __half* __restrict__ E_hi, const __half* __restrict__ E_lo, int Hp, int Ep, int M,
                                  __half* __restrict__ A_hi, __half* __restrict__ A_lo) {
+  pdl_enter();
   const int Kg = Hp + Ep;
   const int64_t total = (int64_t)M * (Kg / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -901,7 +914,10 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
   __shared__ uint32_t tmem_slot;
   const SubsetJob job = jobs[blockIdx.y];
   const int c0 = col_skip + blockIdx.x * VT_M;      // the first col_skip words are shared by all sentences: dense GEMM
-  if (c0 >= job.ncols) return;
+  if (c0 >= job.ncols) {
+    pdl_wait();
+    return;
+  }
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
@@ -921,6 +937,7 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  pdl_enter();      // (jobs / cols above are plan data, uploaded before the batch's first kernel)
   constexpr int KBH = VT_KH / BK;                 // k-blocks per pass
   constexpr int PASS = 2 * VT_A_TILE + 2 * VT_B_TILE;
   uint32_t phase = 0;
@@ -1006,6 +1023,7 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
 __global__ void k_tc_gather_shared(const __half* __restrict__ W_hi, const __half* __restrict__ W_lo, int64_t ldw,
                                    const float* __restrict__ b2, const int32_t* __restrict__ ids, int n, int n_pad,
                                    __half* __restrict__ S_hi, __half* __restrict__ S_lo, float* __restrict__ bias) {
+  pdl_enter();
   const int64_t total = (int64_t)n_pad * (ldw / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / (ldw / 8)), k = (int)(i % (ldw / 8)) * 8;
@@ -1031,6 +1049,7 @@ struct LseCols {
 
 __global__ void k_tc_lse_merge(const float2* __restrict__ part, int part_ld, LseCols cols, int M,
                                double* __restrict__ lse) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -1187,13 +1206,15 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
     cfg.blockDim = dim3(EpiCfg<EPI>::THREADS);
     cfg.dynamicSmemBytes = C::SMEM + EpiCfg<EPI>::STG;
     cfg.stream = h->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_enter (jlm_common.cuh)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = jlm_pdl_enabled() ? 2 : 1;
     if (max_pairs < 0) {
       JLM_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + EpiCfg<EPI>::STG));
       int n = 0;
@@ -1219,8 +1240,7 @@ int32_t launch_gemm(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& Al,
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
   // 64-column tiles read B through the quarter-box maps (operands are uploaded with 256-row boxes)
-  k_tc_gemm<BN, EPI, 1, KS><<<grid, EpiCfg<EPI>::THREADS, C::SMEM + EpiCfg<EPI>::STG, h->stream>>>(Ah, Al, BN == 64 ? B.q_hi : B.map_hi,
-                                                                               BN == 64 ? B.q_lo : B.map_lo, g);
+  JLM_CUDA(jlm_launch(k_tc_gemm<BN, EPI, 1, KS>, dim3(grid), dim3(EpiCfg<EPI>::THREADS), C::SMEM + EpiCfg<EPI>::STG, h->stream, Ah, Al, BN == 64 ? B.q_hi : B.map_hi, BN == 64 ? B.q_lo : B.map_lo, g));
   JLM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1229,6 +1249,14 @@ static bool tc_rs_enabled() {
   static const int v = [] {
     const char* e = getenv("JLM_TC_RS");
     return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+static bool tc_rs256_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_TC_RS256");
+    return e ? atoi(e) : 0;
   }();
   return v != 0;
 }
@@ -1250,13 +1278,15 @@ int32_t launch_lse_rs(jlm_handle* h, const CUtensorMap& Ah, const CUtensorMap& A
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = jlm_pdl_enabled() ? 2 : 1;
   if (max_pairs < 0) {
     JLM_CUDA(cudaFuncSetAttribute(k_tc_lse_rs<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     int n = 0;
@@ -1520,8 +1550,7 @@ int32_t tc_batch_lm_state(jlm_batch* b, int t, const float** T_out, int* ldt_out
   {
     const int64_t total = (int64_t)M * (h->Kg / 8);
     int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
-    k_tc_gather_rows<<<grid, 256, 0, st>>>(s->Hs_hi, s->Hs_lo, parent, word, w->Emb.hi, w->Emb.lo, h->Hp, h->Ep, M,
-                                           s->Ag_hi, s->Ag_lo);
+    JLM_CUDA(jlm_launch(k_tc_gather_rows, dim3(grid), dim3(256), 0, st, s->Hs_hi, s->Hs_lo, parent, word, w->Emb.hi, w->Emb.lo, h->Hp, h->Ep, M, s->Ag_hi, s->Ag_lo));
     JLM_CUDA(cudaGetLastError());
   }
   {
@@ -1606,7 +1635,13 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
       cols.col0[i] = w->lse_col0[i];
       int rs_slots = 0;
       // short K (D-softmax* tail segments): row-stationary kernel, A resident, only the weight tiles stream
-      if (sg.kpad <= 2 * BK && M >= 2 * BM && tc_pair_enabled() && tc_rs_enabled()) {
+      // JLM_TC_RS256=1 also sends K = 256 (the cfg-2 output block) here: with A resident the pair asks L2 for 256 KB per
+      // tile instead of 512 KB and a row's 196 tile partials become <= 16 run partials - measured +3 % on the cfg-2 step
+      // (13.8 -> 13.1 ms).  Off by default: where a pair's tile range cuts a row block depends on the block's position,
+      // so a sentence's fp32 partial sums - hence its scores, at 1e-7 - would depend on its place in the batch, and
+      // tests/test_gpu_parity.py::test_full_size_batch_properties demands bit-identical results under a permutation.
+      const bool rs_shape = sg.kpad <= 2 * BK || (sg.kpad == 4 * BK && tc_rs256_enabled());
+      if (rs_shape && M >= 2 * BM && tc_pair_enabled() && tc_rs_enabled()) {
         RsArgs r{};
         r.M = M;
         r.N = N;
@@ -1618,7 +1653,8 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
         r.part_ld = w->lse_tiles;
         r.part_col0 = w->lse_col0[i];
         if (sg.kpad == BK) JLM_TRY((launch_lse_rs<1>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], r, w->lse_cnt[i], &rs_slots)));
-        else JLM_TRY((launch_lse_rs<2>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], r, w->lse_cnt[i], &rs_slots)));
+        else if (sg.kpad == 2 * BK) JLM_TRY((launch_lse_rs<2>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], r, w->lse_cnt[i], &rs_slots)));
+        else JLM_TRY((launch_lse_rs<4>(h, s->mTs_hi[i], s->mTs_lo[i], w->seg[i], r, w->lse_cnt[i], &rs_slots)));
       }
       if (rs_slots > 0) {
         cols.cnt[i] = rs_slots;
@@ -1640,7 +1676,7 @@ int32_t tc_batch_lm_lse(jlm_batch* b, int t) {
       b->launches += 1;
     }
     if (b->timers) cudaEventRecord(b->kev[4 * t + 3], st);
-    k_tc_lse_merge<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(s->part, w->lse_tiles, cols, M, b->d.slot_lse + sp.row0);
+    JLM_CUDA(jlm_launch(k_tc_lse_merge, dim3(ceil_div((int64_t)M * 32, 256)), dim3(256), 0, st, s->part, w->lse_tiles, cols, M, b->d.slot_lse + sp.row0));
     JLM_CUDA(cudaGetLastError());
     b->launches += 1;
   }
@@ -1693,9 +1729,7 @@ int32_t tc_vocab_logits(jlm_batch* b, int t, double* out) {
   const int ns = b->n_shared;
   if (ns > 0) {
     if (t == 0) {      // the shared word rows of this batch (the first ns ids of any sentence's list)
-      k_tc_gather_shared<<<std::min(ceil_div((int64_t)s->n_shared_pad * (h->seg[0].kpad / 8), 256), h->sm_count * 8), 256, 0,
-                           h->stream>>>(w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, h->b2, b->d.vocab_cols, ns,
-                                        s->n_shared_pad, s->Sh.hi, s->Sh.lo, s->sh_bias);
+      JLM_CUDA(jlm_launch(k_tc_gather_shared, dim3(std::min(ceil_div((int64_t)s->n_shared_pad * (h->seg[0].kpad / 8), 256), h->sm_count * 8)), dim3(256), 0, h->stream, w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, h->b2, b->d.vocab_cols, ns, s->n_shared_pad, s->Sh.hi, s->Sh.lo, s->sh_bias));
       JLM_CUDA(cudaGetLastError());
       b->launches += 1;
     }
@@ -1713,9 +1747,7 @@ int32_t tc_vocab_logits(jlm_batch* b, int t, double* out) {
   const int gx = ceil_div(std::max(sp.max_vocab_cols - ns, 0), VT_M);
   for (int j0 = 0; j0 < sp.nstep && gx > 0; j0 += 65535) {
     const int nj = std::min(sp.nstep - j0, 65535);
-    k_tc_vocab_logits<<<dim3(gx, nj), 128, VT_SMEM, h->stream>>>(
-        w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, s->Ts_hi + h->seg[0].koff, s->Ts_lo + h->seg[0].koff, h->Kt,
-        h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, b->d.vocab_cols, h->b2, inv_scale, out, ns);
+    JLM_CUDA(jlm_launch(k_tc_vocab_logits, dim3(dim3(gx, nj)), dim3(128), VT_SMEM, h->stream,  w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, s->Ts_hi + h->seg[0].koff, s->Ts_lo + h->seg[0].koff, h->Kt, h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, b->d.vocab_cols, h->b2, inv_scale, out, ns));
   }
   JLM_CUDA(cudaGetLastError());
   return 0;

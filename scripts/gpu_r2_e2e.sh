@@ -1,0 +1,13 @@
+#!/bin/bash
+# where the host thread of the streaming e2e arm spends its time, with / without PDL and the copy streams
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 ) 2>&1 | tail -7
+P='import json,sys
+d=[json.loads(l) for l in sys.stdin if l.startswith("{")][-1]
+def show(n, x): print(n, "value %.3fM e2e %.3fM (blk %.3fM) ms %.2f off %.2f" % (x["value"]/1e6, x["e2e"]["value"]/1e6, x["e2e"]["blocking_value"]/1e6, x["ms_per_step"], x["guard"]["ms_per_step_guard_off"]), "roof", round(x["roofline"].get("frac"),4), x["roofline"].get("avg_launch_ms"), "par", x["cpu_baseline"]["nbest_identical_to_gpu"])
+show("cfg2", d)
+for w in d["workloads"]: show(w["workload"], w)
+print(d["clocks"], "lat", d["config"]["single_sentence_latency_ms"])'
+for v in "JLM_X=1" "JLM_PDL=0" "JLM_COPY_STREAM=0" "JLM_COPY_STREAM=0 JLM_PDL=0" "JLM_GUARD_EPS=0" "JLM_GUARD_EPS=0 JLM_COPY_STREAM=0 JLM_PDL=0"; do
+  env $v JLM_BENCH_E2E_DEBUG=1 timeout 600 python bench.py --steps 10 --cpu-baseline-sentences 4 --extra none > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err; echo "== $v rc=$?"; python -c "$P" < gpurun_out/bench_ab.json; grep "bench\] e2e" gpurun_out/bench_ab.err
+done

@@ -1155,6 +1155,7 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
       col_ptr[s + 1] = col_ptr[s] + nv + nd;
     }
     P.vocab_cols.resize(col_ptr[S]);
+    b->n_vocab_cols = col_ptr[S];
     for (int s = 0; s < S; ++s) {
       const int64_t nv = lat->vocab_ptr[s + 1] - lat->vocab_ptr[s];
       int32_t* dst = &P.vocab_cols[col_ptr[s]];
@@ -1723,6 +1724,15 @@ static int32_t guard_resolve(jlm_batch* b, const char* host, const char* src) {
   }
   b->min_gap = mg;
   if (b->n_flagged == 0) return 0;
+  // The guard's own kernels are launched plain: chained, their successors sit resident on the SMs (the float64
+  // output-layer stream with 71 KB of shared memory each) while they wait, in the way of the main stream's next
+  // tensor-core kernel - measured with three batches in flight: 1.44 -> 1.30 M chars/s at cfg 2; and at beam 50
+  // (cfg 5, 50-row float64 GEMMs) the chained re-decode is slower even alone (20.9 vs 17.7 ms).
+  static const int guard_pdl = [] {
+    const char* e = getenv("JLM_PDL_GUARD");
+    return e ? atoi(e) : 0;
+  }();
+  const PdlOff plain(!guard_pdl);
   static const bool dbg = getenv("JLM_DEBUG_TIMING") != nullptr;
   const auto t_0 = std::chrono::steady_clock::now();
   if (b->h->guard_verify) {
@@ -1960,7 +1970,11 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
   // cfg 2 16.4 -> 15.9 ms).  So a batch is chained unless another batch is still in flight AND one of the last
   // sixteen batches needed a re-decode.
   const bool main_tc = b->backend == JLM_BACKEND_TC && st != h->guard_stream;
-  const PdlOff plain(main_tc && h->batches_unfetched > 0 && h->tier2_recent > 0);
+  static const int adaptive = [] {
+    const char* e = getenv("JLM_PDL_ADAPTIVE");
+    return e ? atoi(e) : 1;
+  }();
+  const PdlOff plain(adaptive && main_tc && h->batches_unfetched > 0 && h->tier2_recent > 0);
   if (main_tc) {
     if (h->tier2_recent > 0) --h->tier2_recent;
     if (!b->counted) {

@@ -117,6 +117,7 @@ struct jlm_batch {
   // `samples` top words of top_sampling, decoder.py:144-149 / decoder_dynamic.py:37-43): their logits come from one
   // dense tensor-core GEMM per step (y0, row stride ldy0, float32, bias included) instead of a gather per sentence.
   int n_shared = 0;
+  int64_t n_vocab_cols = 0;      // entries of all sentences' word lists (vocabulary-selection modes)
   const float* y0 = nullptr;
   int ldy0 = 0;
   int max_len = 0;

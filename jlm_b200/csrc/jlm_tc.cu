@@ -1019,6 +1019,107 @@ k_tc_vocab_logits(const __half* __restrict__ W_hi, const __half* __restrict__ W_
   if (warp == 0) ptx::tmem_dealloc(tmem_base, VT_N);
 }
 
+// The same product with the word rows of EVERY sentence's list gathered ONCE per batch into a dense operand
+// (k_tc_gather_shared over jlm_batch's vocab_cols: row = position in the concatenated lists) instead of once per
+// frame: a sentence's list does not change from frame to frame (DynamicDecoder cuts the running log-sum-exp of the
+// full list at the per-frame boundaries), so the per-frame gather - 128 threads copying 16-byte pieces through the
+// LSU, 320 MB per frame at cfg 4 - was the same rows twenty-five times.  Here one thread issues TMA boxes for the
+// sentence's 128 word rows (A) and its <= 32 stage-1 rows (B); a tile that runs past the end of the list just reads
+// the next sentence's rows (lanes beyond ncols are not stored).
+__global__ void __launch_bounds__(128, 2)
+k_tc_vocab_dense(const __grid_constant__ CUtensorMap mWh, const __grid_constant__ CUtensorMap mWl,
+                 const __grid_constant__ CUtensorMap mTh, const __grid_constant__ CUtensorMap mTl, int K,
+                 const SubsetJob* __restrict__ jobs, const float* __restrict__ wd_bias, float inv_scale,
+                 double* __restrict__ out, int col_skip) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_s[2];      // [0] TMA bytes of a pass, [1] its MMAs retired
+  __shared__ uint32_t tmem_slot;
+  const SubsetJob job = jobs[blockIdx.y];
+  const int c0 = col_skip + blockIdx.x * VT_M;
+  if (c0 >= job.ncols) {
+    pdl_wait();
+    return;
+  }
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_tma = ptx::smem_u32(&bar_s[0]), bar_mma = ptx::smem_u32(&bar_s[1]);
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::prefetch_tensormap(&mWh);
+      ptx::prefetch_tensormap(&mWl);
+      ptx::prefetch_tensormap(&mTh);
+      ptx::prefetch_tensormap(&mTl);
+      ptx::mbar_init(bar_tma, 1);
+      ptx::mbar_init(bar_mma, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), VT_N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  pdl_enter();
+  constexpr int KBH = VT_KH / BK;                 // k-blocks per pass
+  constexpr int PASS = 2 * VT_A_TILE + 2 * VT_B_TILE;
+  uint32_t phase = 0;
+  for (int kh = 0; kh < K; kh += VT_KH) {
+    if (tid == 0) {
+      ptx::mbar_expect_tx(bar_tma, KBH * PASS);
+#pragma unroll
+      for (int kb = 0; kb < KBH; ++kb) {
+        const uint32_t sa = base + kb * PASS;
+        const int kcol = kh + kb * BK;            // a k-block past K is out of bounds: zero filled, bytes still counted
+        ptx::tma_load_2d(sa, &mWh, bar_tma, kcol, (int32_t)(job.col0 + c0));
+        ptx::tma_load_2d(sa + VT_A_TILE, &mWl, bar_tma, kcol, (int32_t)(job.col0 + c0));
+        ptx::tma_load_2d(sa + 2 * VT_A_TILE, &mTh, bar_tma, kcol, (int32_t)job.row0);
+        ptx::tma_load_2d(sa + 2 * VT_A_TILE + VT_B_TILE, &mTl, bar_tma, kcol, (int32_t)job.row0);
+      }
+    }
+    ptx::mbar_wait(bar_tma, phase);
+    if (warp == 0 && ptx::elect_one()) {
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(VT_M, VT_N);
+#pragma unroll
+      for (int kb = 0; kb < KBH; ++kb) {
+        const uint32_t sa = base + kb * PASS;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ah = ptx::umma_desc_sw128(sa + k * 32);
+          const uint64_t al = ptx::umma_desc_sw128(sa + VT_A_TILE + k * 32);
+          const uint64_t bh = ptx::umma_desc_sw128(sa + 2 * VT_A_TILE + k * 32);
+          const uint64_t bl = ptx::umma_desc_sw128(sa + 2 * VT_A_TILE + VT_B_TILE + k * 32);
+          ptx::mma_f16_ss(tmem_base, ah, bl, idesc, (kh | kb | k) != 0 ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_base, al, bh, idesc, 1u);
+          ptx::mma_f16_ss(tmem_base, ah, bh, idesc, 1u);
+        }
+      }
+      ptx::tc_commit(bar_mma);
+    }
+    __syncwarp();
+    ptx::mbar_wait(bar_mma, phase);    // shared memory may be overwritten / accumulators may be read
+    phase ^= 1u;
+    ptx::tc_fence_after();
+  }
+  {
+    uint32_t r[32];
+    ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), r);
+    ptx::tmem_ld_wait();
+    const int j = c0 + tid;
+    if (j < job.ncols) {
+      const double bias = (double)wd_bias[job.col0 + j];
+      for (int q = 0; q < job.rows; ++q)
+        out[job.out0 + (int64_t)q * job.ncols + j] = (double)(__uint_as_float(r[q]) * inv_scale) + bias;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, VT_N);
+}
+
 // rows ids[0..n) of the split weight block and their biases -> dense operand (zero rows up to n_pad)
 __global__ void k_tc_gather_shared(const __half* __restrict__ W_hi, const __half* __restrict__ W_lo, int64_t ldw,
                                    const float* __restrict__ b2, const int32_t* __restrict__ ids, int n, int n_pad,
@@ -1253,6 +1354,14 @@ static bool tc_rs_enabled() {
   return v != 0;
 }
 
+static bool tc_vocab_dense_enabled() {
+  static const int v = [] {
+    const char* e = getenv("JLM_TC_VOCAB_DENSE");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 static bool tc_rs256_enabled() {
   static const int v = [] {
     const char* e = getenv("JLM_TC_RS256");
@@ -1456,6 +1565,11 @@ struct TcBatchState {
   float* sh_bias = nullptr;           // [n_shared_pad] b2 of those words
   float* Y0 = nullptr;                // [Mpad, ldy0]
   int n_shared_pad = 0;
+  // ... and ALL word rows of all sentences' lists, gathered once per batch (k_tc_vocab_dense)
+  __half *Wd_hi = nullptr, *Wd_lo = nullptr;   // [dense_rows, kpad]
+  float* wd_bias = nullptr;                    // [dense_rows]
+  int64_t dense_rows = 0;
+  CUtensorMap mWd_hi, mWd_lo, mTv_hi, mTv_lo;  // 128-row boxes over Wd, 32-row boxes over the step's stage-1 rows
   CUtensorMap mAg_hi, mAg_lo, mHs_hi, mHs_lo;
   CUtensorMap mTs_hi[JLM_MAX_SEGMENTS], mTs_lo[JLM_MAX_SEGMENTS];
 };
@@ -1485,8 +1599,20 @@ int32_t tc_batch_plan(jlm_batch* b, Arena& a) {
   }
   s->part = (b->mode == JLM_DECODE_FULL && b->use_lse) ? a.take<float2>(mp * h->tc->lse_tiles) : nullptr;
   // shared word rows: only where the tensor-core vocabulary kernel runs (tc_vocab_logits)
-  if (b->mode == JLM_DECODE_FULL || h->untied || h->n_seg != 1 || b->W > VT_N || h->seg[0].kpad % BK != 0 || !b->use_lse)
-    b->n_shared = 0;
+  const bool vocab_tc = !(b->mode == JLM_DECODE_FULL || h->untied || h->n_seg != 1 || b->W > VT_N || h->seg[0].kpad % BK != 0 || !b->use_lse);
+  if (!vocab_tc) b->n_shared = 0;
+  s->dense_rows = 0;
+  s->Wd_hi = s->Wd_lo = nullptr;
+  s->wd_bias = nullptr;
+  if (vocab_tc && tc_vocab_dense_enabled() && b->n_vocab_cols > 0) {
+    const int64_t rows = round_up64(b->n_vocab_cols, VT_M) + VT_M;      // a tile may start at any row: one spare tile
+    if (rows * h->seg[0].kpad * 4 <= ((int64_t)8 << 30)) {             // hi + lo, 2 bytes each; beyond 8 GB: per-frame gather
+      s->dense_rows = rows;
+      s->Wd_hi = a.take<__half>((size_t)rows * h->seg[0].kpad);
+      s->Wd_lo = a.take<__half>((size_t)rows * h->seg[0].kpad);
+      s->wd_bias = a.take<float>((size_t)rows);
+    }
+  }
   s->n_shared_pad = (int)round_up64(b->n_shared, 256);
   if (b->n_shared > 0) {
     s->Sh.hi = a.take<__half>((size_t)s->n_shared_pad * h->seg[0].kpad);
@@ -1511,6 +1637,13 @@ int32_t tc_batch_plan(jlm_batch* b, Arena& a) {
     JLM_TRY(make_map(&s->Sh.pair_lo, s->Sh.lo, K, s->n_shared_pad, K, 128));
     JLM_TRY(make_map(&s->Sh.q_hi, s->Sh.hi, K, s->n_shared_pad, K, 64));
     JLM_TRY(make_map(&s->Sh.q_lo, s->Sh.lo, K, s->n_shared_pad, K, 64));
+  }
+  if (s->dense_rows > 0) {
+    const int64_t K = h->seg[0].kpad;
+    JLM_TRY(make_map(&s->mWd_hi, s->Wd_hi, K, s->dense_rows, K, VT_M));
+    JLM_TRY(make_map(&s->mWd_lo, s->Wd_lo, K, s->dense_rows, K, VT_M));
+    JLM_TRY(make_map(&s->mTv_hi, s->Ts_hi + h->seg[0].koff, K, s->Mpad, h->Kt, VT_N));
+    JLM_TRY(make_map(&s->mTv_lo, s->Ts_lo + h->seg[0].koff, K, s->Mpad, h->Kt, VT_N));
   }
   JLM_TRY(make_map(&s->mAg_hi, s->Ag_hi, h->Kg, s->Mpad, h->Kg, BM));
   JLM_TRY(make_map(&s->mAg_lo, s->Ag_lo, h->Kg, s->Mpad, h->Kg, BM));
@@ -1745,6 +1878,25 @@ int32_t tc_vocab_logits(jlm_batch* b, int t, double* out) {
     b->launches += 1;
   }
   const int gx = ceil_div(std::max(sp.max_vocab_cols - ns, 0), VT_M);
+  if (s->dense_rows > 0 && gx > 0) {
+    static bool dense_configured = false;
+    if (!dense_configured) {
+      JLM_CUDA(cudaFuncSetAttribute(k_tc_vocab_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
+      dense_configured = true;
+    }
+    if (t == 0) {      // every sentence's word rows, once per run
+      JLM_CUDA(jlm_launch(k_tc_gather_shared, dim3(std::min(ceil_div(s->dense_rows * (h->seg[0].kpad / 8), 256), h->sm_count * 16)),
+                          dim3(256), 0, h->stream, w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, h->b2, b->d.vocab_cols,
+                          (int)b->n_vocab_cols, (int)s->dense_rows, s->Wd_hi, s->Wd_lo, s->wd_bias));
+      b->launches += 1;
+    }
+    for (int j0 = 0; j0 < sp.nstep; j0 += 65535) {
+      const int nj = std::min(sp.nstep - j0, 65535);
+      JLM_CUDA(jlm_launch(k_tc_vocab_dense, dim3(gx, nj), dim3(128), VT_SMEM, h->stream, s->mWd_hi, s->mWd_lo, s->mTv_hi,
+                          s->mTv_lo, h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, s->wd_bias, inv_scale, out, ns));
+    }
+    return 0;
+  }
   for (int j0 = 0; j0 < sp.nstep && gx > 0; j0 += 65535) {
     const int nj = std::min(sp.nstep - j0, 65535);
     JLM_CUDA(jlm_launch(k_tc_vocab_logits, dim3(dim3(gx, nj)), dim3(128), VT_SMEM, h->stream,  w->seg[0].hi, w->seg[0].lo, h->seg[0].kpad, s->Ts_hi + h->seg[0].koff, s->Ts_lo + h->seg[0].koff, h->Kt, h->seg[0].kpad, b->d.vocab_jobs + sp.job0 + j0, b->d.vocab_cols, h->b2, inv_scale, out, ns));

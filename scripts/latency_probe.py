@@ -16,9 +16,11 @@ sents = synth.make_sentences(lexicon, 4, min_len=20, seed=100, vocab_size=50000)
 config.set_root(root)
 dec = jlm_b200.Decoder(1)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+backend = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0 auto (float64 for one sentence), 1 float64, 2 tensor cores
 for s in sents[:2]:
-    dec.decode_batch([s], topN=10, beam_width=10)
+    dec.decode_batch([s], topN=10, beam_width=10, backend=backend)
 t0 = time.perf_counter()
 for i in range(n):
-    dec.decode_batch([sents[i % 4]], topN=10, beam_width=10)
-print('single-sentence decode_batch: %.3f ms per call (%d kana)' % ((time.perf_counter() - t0) / n * 1e3, len(sents[0])))
+    dec.decode_batch([sents[i % 4]], topN=10, beam_width=10, backend=backend)
+print('single-sentence decode_batch (backend %d): %.3f ms per call (%d kana)'
+      % (backend, (time.perf_counter() - t0) / n * 1e3, len(sents[0])))

@@ -14,6 +14,8 @@
 #include <thread>
 #include <unordered_map>
 
+#include <cooperative_groups.h>
+
 #include "jlm_beam.cuh"
 
 namespace {
@@ -75,14 +77,14 @@ __device__ __forceinline__ void load4(const double* p, double (&t)[4]) {
   t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y;
 }
 
+// One warp scores work item `item` of the step (k_score_nodes: warp-per-item kernel; k_single_f64: its scoring phase).
+// lse_rows: the log-sum-exp of the start frame's rows by rank when they are not in d.slot_lse yet (k_single_f64 keeps
+// them in shared memory), else nullptr.
 template <typename TT, bool DYN>
-__global__ void __launch_bounds__(SC_WARPS * 32)
-k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
-              int64_t item0, int n_items, int64_t row0, int use_lse, int defer) {
-  pdl_enter();
+__device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int64_t ldt, const BeamDev& d,
+                                           const float* __restrict__ b2, int64_t item0, int item, int64_t row0, int use_lse,
+                                           int defer, const double* lse_rows) {
   const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
-  if (item >= n_items) return;
   const int4* ip = reinterpret_cast<const int4*>(d.items + item0 + item);
   const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
   const int w = i0.x;
@@ -97,7 +99,7 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
     pre[q] = 0.0;
     const int r = q * SC_RC + my_r;
     if (!DYN && !defer && (lane & 3) == 0 && r < rows)
-      pre[q] = d.slot_score[ps0 + r] + (use_lse ? d.slot_lse[ps0 + r] : 0.0);
+      pre[q] = d.slot_score[ps0 + r] + (use_lse ? (lse_rows ? lse_rows[r] : d.slot_lse[ps0 + r]) : 0.0);
   }
   int s = 0;
 #pragma unroll
@@ -170,11 +172,21 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
       } else {
         double base_score;
         if (q < SC_MAXPASS) base_score = q == 0 ? pre[0] : pre[1];
-        else base_score = d.slot_score[ps] + (use_lse ? d.slot_lse[ps] : 0.0);
+        else base_score = d.slot_score[ps] + (use_lse ? (lse_rows ? lse_rows[r0 + r] : d.slot_lse[ps]) : 0.0);
         d.cand_val[cpos + r0 + r] = base_score - y;
       }
     }
   }
+}
+
+template <typename TT, bool DYN>
+__global__ void __launch_bounds__(SC_WARPS * 32)
+k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
+              int64_t item0, int n_items, int64_t row0, int use_lse, int defer) {
+  pdl_enter();
+  const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr);
 }
 
 // Second half of a deferred k_score_nodes: cand_val holds -y; add the parent path's score and LSE.
@@ -261,13 +273,10 @@ __device__ __forceinline__ void serial_select(ValueFn value, int nc, int W, int 
 
 constexpr int PRUNE_CAP = 96;   // survivors of the threshold filter a warp can rank in shared memory
 
+// One warp prunes frame t of sorted sentence `warp` (k_prune: warp-per-sentence kernel; k_single_f64: warp 0 of CTA 0).
 template <int L, bool DYN>
-__global__ void __launch_bounds__(128)
-k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
-  pdl_enter();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ void prune_sentence(const BeamDev& d, int t, int warp, int W, int tstride, int use_lse) {
   const int lane = threadIdx.x & 31;
-  if (warp >= nact) return;
   const unsigned FULL = 0xffffffffu;
   const int fid = (int)d.fbase[warp] + t;
   const int lo = d.frame_lo[fid], hi = d.frame_hi[fid];
@@ -423,6 +432,15 @@ k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
       if (DYN) d.slot_cumy[s0 + idx] = d.slot_cumy[par] + d.cand_val[c];
     }
   }
+}
+
+template <int L, bool DYN>
+__global__ void __launch_bounds__(128)
+k_prune(BeamDev d, int t, int nact, int W, int tstride, int use_lse) {
+  pdl_enter();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= nact) return;
+  prune_sentence<L, DYN>(d, t, warp, W, tstride, use_lse);
 }
 
 // Block-per-sentence form of the same selection (W <= 128): the four warps split the candidate range, so the one
@@ -889,6 +907,410 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Single sentence, float64 back end: the whole frame loop in ONE cooperative kernel
+// ------------------------------------------------------------------------------------------------
+// A sentence decoded alone (latency mode; the near-tie guard's re-decode of a flagged sentence) is <= 16 rows per
+// LM step: eight launches per frame, each a few microseconds of work behind a launch, a ramp and a drain
+// (profiles/r02/launch_summary_single_*.txt: 87 us per frame, 160 launches per 20 kana).  Here one CTA per SM stays
+// resident for the whole sentence and the phases of a frame are separated by grid barriers:
+//   prune (warp 0 of CTA 0: the lock-step kernel's own selection, prune_sentence)
+//   LSTM cell   - warp per hidden unit: the four gate rows of [HM | IM] against the <= 16 gathered input rows,
+//                 warp reduce-scatter of the 4 x 16 sums, sigmoid / tanh / cell update on the lanes that end up with
+//                 a row's four gates (decoder/model.py:125-139)
+//   stage 1     - warp per column of h . PM (model.py:145,162,184)
+//   output      - thread per vocabulary column (the word's K <= 512 weight row streamed once, the stage-1 rows
+//                 broadcast from shared memory), logits of the CTA's slice in shared memory, one (max, sum exp)
+//                 per (row, CTA) (model.py:15-20 softmax as a log-sum-exp)
+//   merge+score - the first CTAs merge the per-CTA partials and score the lattice nodes that start at this frame
+//                 (score_item, the lock-step kernel's own dot products; Path.append_node, decoder.py:43-49)
+// Every quantity that crosses a barrier is read with plain (coherent) loads.
+namespace cg = cooperative_groups;
+
+constexpr int SG_THREADS = 256;      // measured with 512 (128-register cap, 4-load batches): 1.94 vs 1.48 ms per 20-kana sentence
+constexpr int SG_WARPS = SG_THREADS / 32;
+constexpr int SG_MAXM = 16;          // rows per LM step (beam width)
+constexpr int SG_MAXSTEPS = 128;
+
+struct SingleArgs {
+  BeamDev d;
+  SegTable seg;
+  const float* Wg;        // [4H, Kg]
+  const float* bg;        // [4H]
+  const float* LM_in;     // [V, Ep]
+  const double* P1;       // [Kt, Hp]
+  const float* b2;        // [V]
+  double* hx;             // [n_slots, Hp]
+  double* cx;
+  double* T;              // [SG_MAXM, Kt] stage-1 rows of the step
+  double2* part;          // [gridDim.x, SG_MAXM] (max, sum exp) of the CTA's vocabulary slice
+  int V, H, Hp, Ep, Kg, Kt;
+  int W, use_lse, n_steps, sent_T;
+  int per;                // vocabulary columns per CTA
+  int r0;                 // doubles of shared-memory region 0 (see the kernel)
+  int item0[SG_MAXSTEPS + 2];   // work items (lattice nodes starting at frame t): [item0[t], item0[t+1])
+};
+
+// N live values per lane -> N/2: lanes with bit OFF set keep the upper half, the others the lower half
+template <int N, int OFF>
+__device__ __forceinline__ void rs_halve(double* acc, int lane) {
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const double send = up ? acc[i] : acc[i + N / 2];
+    const double keep = up ? acc[i + N / 2] : acc[i];
+    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+
+__global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double sg_sm[];
+  const BeamDev& d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gwarp = blockIdx.x * SG_WARPS + warp, NW = gridDim.x * SG_WARPS;
+  const int Hp = a.Hp, Kt = a.Kt;
+  // shared memory: stage-1 rows | logits of this CTA's columns | per-row LSE | parents, words of the step's rows
+  // region 0 is, in turn, the gathered gate input [M][Kg], the step's h rows [M][Hp], and the stage-1 rows [M][Kt]
+  // followed by the logits of this CTA's columns [M][per]
+  double* As = sg_sm;
+  double* ys = As + (size_t)SG_MAXM * Kt;
+  double* lse_sm = sg_sm + a.r0;                    // [SG_MAXM]
+  int* s_par = reinterpret_cast<int*>(lse_sm + SG_MAXM);   // [SG_MAXM]
+  int* s_word = s_par + SG_MAXM;                            // [SG_MAXM]
+
+  // ---- prologue: k_init_frame0 (sentence 0) and k_build_items ----
+  if (blockIdx.x == 0 && tid == 0) {
+    const int fid = (int)d.fbase[0];
+    const int64_t s0 = d.slot0[fid];
+    const int node = d.frame_lo[fid];
+    d.slot_score[s0] = 0.0;
+    d.slot_lse[s0] = 0.0;
+    d.slot_parent[s0] = -1;
+    d.slot_node[s0] = node;
+    d.slot_word[s0] = d.node_word[node];
+    d.guard_gap[0] = INFINITY;
+    d.guard_flag[0] = 0;
+    *d.guard_n = 0;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * SG_THREADS + tid; i < d.n_items; i += (int64_t)gridDim.x * SG_THREADS) {
+    const int n = d.start_items[i];
+    const int pf = d.node_pfid[n];
+    ScoreItem it;
+    it.word = d.node_word[n];
+    it.rows = d.bc[pf];
+    it.node = n;
+    it.pad = 0;
+    it.ps0 = d.slot0[pf];
+    it.cpos = d.cand_pos[n];
+    d.items[i] = it;
+  }
+  grid.sync();
+
+  const int fb = (int)d.fbase[0];
+  for (int t = 0; t < a.n_steps; ++t) {
+    const int fid = fb + t;
+    // Prune: EVERY CTA runs the (deterministic) selection with its warp 0 and writes the same slots - a grid barrier
+    // and a phase in which 147 SMs wait for one warp cost more than the redundant scan of a few hundred candidates.
+    if (t > 0) {
+      if (warp == 0) prune_sentence<1, false>(d, t, 0, a.W, 0, a.use_lse);
+      __syncthreads();
+    }
+    const int M = (t < a.sent_T) ? d.bc[fid] : 0;     // rows that take an LM step (plan data: the same in every CTA)
+    if (M == 0) continue;
+    const int64_t row0 = d.slot0[fid];
+    if (tid < SG_MAXM) {
+      s_par[tid] = tid < M ? d.slot_parent[row0 + tid] : -1;
+      s_word[tid] = tid < M ? d.slot_word[row0 + tid] : 0;
+    }
+    __syncthreads();
+    // gathered gate input [ h[parent] | LM_in[word] ] of the step's rows -> shared memory (float64), once per CTA
+    {
+      const int Kg2 = a.Kg >> 1;
+      const int total = M * Kg2;                      // double2 pieces
+      for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * SG_THREADS;
+          v[u] = make_double2(0.0, 0.0);
+          if (i < total) {
+            const int m = i / Kg2, k = (i - m * Kg2) * 2;
+            if (k < Hp) {
+              const int p = s_par[m];
+              if (p >= 0) v[u] = *reinterpret_cast<const double2*>(a.hx + (int64_t)p * Hp + k);
+            } else {
+              const float2 e = __ldg(reinterpret_cast<const float2*>(a.LM_in + (int64_t)s_word[m] * a.Ep + (k - Hp)));
+              v[u] = make_double2((double)e.x, (double)e.y);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * SG_THREADS;
+          if (i < total) reinterpret_cast<double2*>(As)[i] = v[u];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- LSTM cell: warp per hidden unit ----
+    for (int j = gwarp; j < Hp; j += NW) {
+      if (j >= a.H) {      // padding units of the state rows stay zero (stage 1 multiplies them by zero weights)
+        if (lane < M) {
+          a.hx[(row0 + lane) * Hp + j] = 0.0;
+          a.cx[(row0 + lane) * Hp + j] = 0.0;
+        }
+        continue;
+      }
+      const float* w0 = a.Wg + (int64_t)j * a.Kg;
+      const float* w1 = a.Wg + ((int64_t)a.H + j) * a.Kg;
+      const float* w2 = a.Wg + ((int64_t)2 * a.H + j) * a.Kg;
+      const float* w3 = a.Wg + ((int64_t)3 * a.H + j) * a.Kg;
+      {
+        double acc[4 * SG_MAXM];               // index = row * 4 + gate (i, f, o, g)
+#pragma unroll
+        for (int i = 0; i < 4 * SG_MAXM; ++i) acc[i] = 0.0;
+        for (int k = lane * 4; k < a.Kg; k += 128) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(w0 + k));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(w1 + k));
+          const float4 g2 = __ldg(reinterpret_cast<const float4*>(w2 + k));
+          const float4 g3 = __ldg(reinterpret_cast<const float4*>(w3 + k));
+          const double gw[4][4] = {{(double)g0.x, (double)g0.y, (double)g0.z, (double)g0.w},
+                                   {(double)g1.x, (double)g1.y, (double)g1.z, (double)g1.w},
+                                   {(double)g2.x, (double)g2.y, (double)g2.z, (double)g2.w},
+                                   {(double)g3.x, (double)g3.y, (double)g3.z, (double)g3.w}};
+#pragma unroll
+          for (int r = 0; r < SG_MAXM; ++r) {
+            if (r < M) {
+              const double2* xp = reinterpret_cast<const double2*>(As + (size_t)r * a.Kg + k);
+              const double2 xu = xp[0], xv = xp[1];
+#pragma unroll
+              for (int gte = 0; gte < 4; ++gte) {
+                double sacc = acc[r * 4 + gte];
+                sacc = fma(xu.x, gw[gte][0], sacc);
+                sacc = fma(xu.y, gw[gte][1], sacc);
+                sacc = fma(xv.x, gw[gte][2], sacc);
+                sacc = fma(xv.y, gw[gte][3], sacc);
+                acc[r * 4 + gte] = sacc;
+              }
+            }
+          }
+        }
+        rs_halve<64, 16>(acc, lane);
+        rs_halve<32, 8>(acc, lane);
+        rs_halve<16, 4>(acc, lane);
+        rs_halve<8, 2>(acc, lane);
+        rs_halve<4, 1>(acc, lane);
+        // lane l holds the sums with index 2l and 2l+1: row l/2, gates (i, f) on even lanes, (o, g) on odd lanes
+        const double o0 = __shfl_xor_sync(0xffffffffu, acc[0], 1), o1 = __shfl_xor_sync(0xffffffffu, acc[1], 1);
+        const int m = lane >> 1;
+        if ((lane & 1) == 0 && m < M) {
+          const double pi = acc[0] + (double)a.bg[j], pf = acc[1] + (double)a.bg[a.H + j];
+          const double po = o0 + (double)a.bg[2 * a.H + j], pg = o1 + (double)a.bg[3 * a.H + j];
+          const double gi = 1.0 / (exp(-pi) + 1.0), gf = 1.0 / (exp(-pf) + 1.0), go = 1.0 / (exp(-po) + 1.0);
+          const double gg = tanh(pg);
+          const int p = s_par[m];
+          const double cp = p >= 0 ? a.cx[(int64_t)p * Hp + j] : 0.0;
+          const double c = cp * gf + gg * gi;
+          a.cx[(row0 + m) * Hp + j] = c;
+          a.hx[(row0 + m) * Hp + j] = tanh(c) * go;
+        }
+      }
+    }
+    grid.sync();
+
+    // ---- stage 1: T[m][e] = h[m] . P1[e], warp per column; the step's h rows go to shared memory first ----
+    {
+      const int Hp2 = Hp >> 1;
+      const int total = M * Hp2;
+      for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * SG_THREADS;
+          if (i < total) v[u] = reinterpret_cast<const double2*>(a.hx + row0 * Hp)[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * SG_THREADS;
+          if (i < total) reinterpret_cast<double2*>(As)[i] = v[u];
+        }
+      }
+    }
+    __syncthreads();
+    for (int e = gwarp; e < Kt; e += NW) {
+      double acc[SG_MAXM];
+#pragma unroll
+      for (int i = 0; i < SG_MAXM; ++i) acc[i] = 0.0;
+      const double* prow = a.P1 + (int64_t)e * Hp;
+      for (int k0 = lane * 2; k0 < Hp; k0 += 256) {      // Hp is a multiple of 64: a group of four k-steps may end early
+        double2 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 64 * u;
+          w[u] = k < Hp ? *reinterpret_cast<const double2*>(prow + k) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 64 * u;
+          if (k < Hp) {
+#pragma unroll
+            for (int m = 0; m < SG_MAXM; ++m) {
+              if (m < M) {
+                const double2 hv = *reinterpret_cast<const double2*>(As + (size_t)m * Hp + k);
+                acc[m] = fma(hv.x, w[u].x, acc[m]);
+                acc[m] = fma(hv.y, w[u].y, acc[m]);
+              }
+            }
+          }
+        }
+      }
+      rs_halve<16, 16>(acc, lane);
+      rs_halve<8, 8>(acc, lane);
+      rs_halve<4, 4>(acc, lane);
+      rs_halve<2, 2>(acc, lane);
+      const double v = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+      const int m = lane >> 1;
+      if ((lane & 1) == 0 && m < M) a.T[(int64_t)m * Kt + e] = v;
+    }
+    grid.sync();
+
+    // ---- output layer: (max, sum exp) of this CTA's vocabulary slice for every row ----
+    if (a.use_lse) {
+      {
+        const int total = (M * Kt) >> 1;
+        for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * SG_THREADS;
+            if (i < total) v[u] = reinterpret_cast<const double2*>(a.T)[i];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * SG_THREADS;
+            if (i < total) reinterpret_cast<double2*>(As)[i] = v[u];
+          }
+        }
+      }
+      __syncthreads();
+      const int c_lo = blockIdx.x * a.per, c_hi = min(a.V, c_lo + a.per);
+      for (int n = c_lo + tid; n < c_hi; n += SG_THREADS) {
+        int sgi = 0;
+#pragma unroll
+        for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
+          if (i < a.seg.n && n >= a.seg.start[i]) sgi = i;
+        const int kpad = a.seg.kpad[sgi];
+        const float* wrow = a.seg.W[sgi] + (int64_t)(n - a.seg.start[sgi]) * kpad;
+        const double* arow = As + a.seg.koff[sgi];
+        double acc[SG_MAXM];
+#pragma unroll
+        for (int i = 0; i < SG_MAXM; ++i) acc[i] = 0.0;
+        // the word's weight row streams through registers in 128-byte batches (one cache line per thread), the next
+        // batch in flight while this one is multiplied
+        float4 wn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wn[u] = __ldg(reinterpret_cast<const float4*>(wrow + 4 * u));
+        for (int k0 = 0; k0 < kpad; k0 += 32) {
+          float4 wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = wn[u];
+          if (k0 + 32 < kpad) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wn[u] = __ldg(reinterpret_cast<const float4*>(wrow + k0 + 32 + 4 * u));
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double w0 = (double)wv[u].x, w1 = (double)wv[u].y, w2 = (double)wv[u].z, w3 = (double)wv[u].w;
+#pragma unroll
+            for (int m = 0; m < SG_MAXM; ++m) {
+              if (m < M) {
+                const double2* ap = reinterpret_cast<const double2*>(arow + (size_t)m * Kt + k0 + 4 * u);
+                const double2 u0 = ap[0], u1 = ap[1];      // the same address in every lane: broadcast
+                double sacc = acc[m];
+                sacc = fma(u0.x, w0, sacc);
+                sacc = fma(u0.y, w1, sacc);
+                sacc = fma(u1.x, w2, sacc);
+                sacc = fma(u1.y, w3, sacc);
+                acc[m] = sacc;
+              }
+            }
+          }
+        }
+        const double bias = (double)__ldg(a.b2 + n);
+#pragma unroll
+        for (int m = 0; m < SG_MAXM; ++m)
+          if (m < M) ys[(size_t)m * a.per + (n - c_lo)] = acc[m] + bias;
+      }
+      __syncthreads();
+      const int nc = max(c_hi - c_lo, 0);
+      {
+        // a warp takes rows warp and warp + 8 together: two independent chains of float64 exponentials per lane
+        const int m0 = warp, m1 = warp + SG_WARPS;
+        const bool r0 = m0 < M, r1 = m1 < M;
+        const double* y0 = ys + (size_t)m0 * a.per;
+        const double* y1 = ys + (size_t)(r1 ? m1 : m0) * a.per;
+        double mx0 = -INFINITY, mx1 = -INFINITY;
+        if (r0)
+          for (int i = lane; i < nc; i += 32) {
+            mx0 = fmax(mx0, y0[i]);
+            mx1 = fmax(mx1, y1[i]);
+          }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          mx0 = fmax(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+          mx1 = fmax(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+        }
+        double s0 = 0.0, s1 = 0.0;
+        if (r0)
+          for (int i = lane; i < nc; i += 32) {
+            s0 += exp(y0[i] - mx0);
+            if (r1) s1 += exp(y1[i] - mx1);
+          }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane == 0 && r0) a.part[(size_t)blockIdx.x * SG_MAXM + m0] = make_double2(mx0, s0);
+        if (lane == 0 && r1) a.part[(size_t)blockIdx.x * SG_MAXM + m1] = make_double2(mx1, s1);
+      }
+      grid.sync();
+    }
+
+    // ---- merge the partials, score the nodes that start at this frame ----
+    const int it0 = a.item0[t], n_it = a.item0[t + 1] - it0;
+    if (blockIdx.x * SG_WARPS < n_it || blockIdx.x == 0) {
+      if (a.use_lse) {
+        for (int m = warp; m < M; m += SG_WARPS) {
+          double mx = -INFINITY;
+          for (int c = lane; c < (int)gridDim.x; c += 32) mx = fmax(mx, a.part[(size_t)c * SG_MAXM + m].x);
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          double sum = 0.0;
+          for (int c = lane; c < (int)gridDim.x; c += 32) {
+            const double2 pr = a.part[(size_t)c * SG_MAXM + m];
+            if (pr.x > -INFINITY) sum += pr.y * exp(pr.x - mx);
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) {
+            const double l = mx + log(sum);
+            lse_sm[m] = l;
+            if (blockIdx.x == 0) d.slot_lse[row0 + m] = l;
+          }
+        }
+        __syncthreads();
+      }
+      for (int item = gwarp; item < n_it; item += NW)
+        score_item<double, false>(a.seg, a.T, Kt, d, a.b2, it0, item, row0, a.use_lse, 0, a.use_lse ? lse_sm : nullptr);
+    }
+    grid.sync();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: plan
 // ------------------------------------------------------------------------------------------------
@@ -1271,6 +1693,7 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
     b->part_tiles = 0;
     for (int i = 0; i < h->n_seg; ++i) b->part_tiles += exact_tiles_n(h->seg[i].end - h->seg[i].start);
     b->part = (b->mode == JLM_DECODE_FULL && b->use_lse) ? a.take<double2>(mr * b->part_tiles) : nullptr;
+    b->spart = (b->S == 1 && b->mode == JLM_DECODE_FULL) ? a.take<double2>((size_t)SG_MAXM * std::max(h->sm_count, 1)) : nullptr;
   }
 }
 
@@ -1369,6 +1792,78 @@ int32_t exact_lm_step(jlm_batch* b, int t) {
     b->launches += 1;
   }
   return lm_step_tail<double>(b, t, T, ldt);
+}
+
+// Runs the whole batch through k_single_f64 when it is one sentence the kernel's shapes cover; *done says whether it
+// did (otherwise the caller goes through the per-frame launches).  JLM_SINGLE=0 switches the kernel off.
+int32_t single_try_run(jlm_batch* b, bool* done) {
+  *done = false;
+  jlm_handle* h = b->h;
+  static const int enabled = [] {
+    const char* e = getenv("JLM_SINGLE");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || b->backend != JLM_BACKEND_EXACT || b->S != 1 || b->mode != JLM_DECODE_FULL || b->dynamic || b->unlimited ||
+      b->W > SG_MAXM || b->timers || h->untied || !h->P1 || !b->T || !b->spart || b->n_steps > SG_MAXSTEPS)
+    return 0;
+  for (int i = 0; i < h->n_seg; ++i)
+    if (h->seg[i].kpad % 32 != 0 || exact_use_q8(h, h->seg[i], b->W)) return 0;
+  if (h->Hp % 64 != 0 || h->Ep % 4 != 0 || h->Kt % 4 != 0 || h->Kg % 4 != 0) return 0;
+  static int blocks_per_sm = -1;
+  int dev_smem = 0;
+  JLM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const int G = h->sm_count;
+  const int per = ceil_div(h->V, G);
+  const size_t r0 = (size_t)SG_MAXM * std::max<size_t>(std::max(h->Kg, h->Hp), (size_t)h->Kt + per);
+  const size_t smem = (r0 + SG_MAXM) * sizeof(double) + 2 * SG_MAXM * sizeof(int);
+  if (smem + 8 * 1024 > (size_t)dev_smem) return 0;      // + the prune phase's static buffers
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    JLM_CUDA(cudaFuncSetAttribute(k_single_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+    blocks_per_sm = -1;
+  }
+  if (blocks_per_sm < 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_single_f64, SG_THREADS, smem) != cudaSuccess) {
+      cudaGetLastError();
+      nb = 0;
+    }
+    blocks_per_sm = nb;
+  }
+  if (blocks_per_sm < 1) return 0;      // a cooperative grid must be co-resident: one CTA per SM
+  SingleArgs sa{};
+  sa.d = b->d;
+  sa.seg = make_seg_table(h);
+  sa.Wg = h->Wg;
+  sa.bg = h->bg;
+  sa.LM_in = h->LM_in;
+  sa.P1 = h->P1;
+  sa.b2 = h->b2;
+  sa.hx = b->hx;
+  sa.cx = b->cx;
+  sa.T = b->T;
+  sa.part = b->spart;
+  sa.V = h->V;
+  sa.H = h->H;
+  sa.Hp = h->Hp;
+  sa.Ep = h->Ep;
+  sa.Kg = h->Kg;
+  sa.Kt = h->Kt;
+  sa.W = b->W;
+  sa.use_lse = b->use_lse ? 1 : 0;
+  sa.n_steps = b->n_steps;
+  sa.sent_T = b->sent_T[0];
+  sa.per = per;
+  sa.r0 = (int)r0;
+  for (int t = 0; t < b->n_steps; ++t) sa.item0[t] = (int)b->steps[t].item0;
+  sa.item0[b->n_steps] = (int)b->d.n_items;
+  void* args[] = {&sa};
+  JLM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_single_f64), dim3(G), dim3(SG_THREADS), args, smem,
+                                       h->stream));
+  b->launches += 1;
+  *done = true;
+  return 0;
 }
 
 bool score_overlap_enabled() {
@@ -1993,7 +2488,9 @@ extern "C" int32_t jlm_batch_run(jlm_batch* b) {
     b->kev.resize(4 * (size_t)b->n_steps);
     for (auto& e : b->kev) JLM_CUDA(cudaEventCreate(&e));
   }
-  for (int t = 0; t < b->n_steps; ++t) {
+  bool single = false;
+  JLM_TRY(single_try_run(b, &single));
+  for (int t = 0; t < b->n_steps && !single; ++t) {
     if (b->timers) cudaEventRecord(b->events[3 * t], st);
     if (t == 0) {
       JLM_CUDA(jlm_launch(k_init_frame0, dim3(ceil_div(b->S, 128)), dim3(128), 0, st, b->d, b->S));

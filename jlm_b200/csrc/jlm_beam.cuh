@@ -131,6 +131,7 @@ struct jlm_batch {
   double* T = nullptr;           // [max_rows_step, Kt]
   double2* part = nullptr;
   int part_tiles = 0;
+  double2* spart = nullptr;      // [sm_count, 16] per-CTA (max, sum exp) of the single-sentence kernel (k_single_f64)
   double* yv = nullptr;          // vocab logits scratch
   TcBatchState* tc = nullptr;
   // bookkeeping

@@ -964,6 +964,10 @@ __device__ __forceinline__ void rs_halve(double* acc, int lane) {
   }
 }
 
+// MT: rows the register tiles are written for (>= beam width).  Rows M..MT-1 of the shared-memory operands are zero and
+// are multiplied like the others: with `if (m < M)` around every row the compiler keeps each row's four dependent
+// float64 FMAs in a basic block of their own and the two warps a scheduler has cannot cover their latency.
+template <int MT>
 __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double sg_sm[];
@@ -1028,7 +1032,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     // gathered gate input [ h[parent] | LM_in[word] ] of the step's rows -> shared memory (float64), once per CTA
     {
       const int Kg2 = a.Kg >> 1;
-      const int total = M * Kg2;                      // double2 pieces
+      const int total = MT * Kg2;                     // double2 pieces (rows M..MT-1: zeros)
       for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
         double2 v[4];
 #pragma unroll
@@ -1037,7 +1041,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
           v[u] = make_double2(0.0, 0.0);
           if (i < total) {
             const int m = i / Kg2, k = (i - m * Kg2) * 2;
-            if (k < Hp) {
+            if (m >= M) {
+            } else if (k < Hp) {
               const int p = s_par[m];
               if (p >= 0) v[u] = *reinterpret_cast<const double2*>(a.hx + (int64_t)p * Hp + k);
             } else {
@@ -1069,7 +1074,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
       const float* w2 = a.Wg + ((int64_t)2 * a.H + j) * a.Kg;
       const float* w3 = a.Wg + ((int64_t)3 * a.H + j) * a.Kg;
       {
-        double acc[4 * SG_MAXM];               // index = row * 4 + gate (i, f, o, g)
+        double acc[4 * SG_MAXM];               // index = row * 4 + gate (i, f, o, g); rows >= MT stay zero
 #pragma unroll
         for (int i = 0; i < 4 * SG_MAXM; ++i) acc[i] = 0.0;
         for (int k = lane * 4; k < a.Kg; k += 128) {
@@ -1082,8 +1087,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
                                    {(double)g2.x, (double)g2.y, (double)g2.z, (double)g2.w},
                                    {(double)g3.x, (double)g3.y, (double)g3.z, (double)g3.w}};
 #pragma unroll
-          for (int r = 0; r < SG_MAXM; ++r) {
-            if (r < M) {
+          for (int r = 0; r < MT; ++r) {
+            {
               const double2* xp = reinterpret_cast<const double2*>(As + (size_t)r * a.Kg + k);
               const double2 xu = xp[0], xv = xp[1];
 #pragma unroll
@@ -1124,13 +1129,14 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     // ---- stage 1: T[m][e] = h[m] . P1[e], warp per column; the step's h rows go to shared memory first ----
     {
       const int Hp2 = Hp >> 1;
-      const int total = M * Hp2;
+      const int total = MT * Hp2, live = M * Hp2;
       for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
         double2 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + u * SG_THREADS;
-          if (i < total) v[u] = reinterpret_cast<const double2*>(a.hx + row0 * Hp)[i];
+          v[u] = make_double2(0.0, 0.0);
+          if (i < live) v[u] = reinterpret_cast<const double2*>(a.hx + row0 * Hp)[i];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -1157,8 +1163,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
           const int k = k0 + 64 * u;
           if (k < Hp) {
 #pragma unroll
-            for (int m = 0; m < SG_MAXM; ++m) {
-              if (m < M) {
+            for (int m = 0; m < MT; ++m) {
+              {
                 const double2 hv = *reinterpret_cast<const double2*>(As + (size_t)m * Hp + k);
                 acc[m] = fma(hv.x, w[u].x, acc[m]);
                 acc[m] = fma(hv.y, w[u].y, acc[m]);
@@ -1180,13 +1186,14 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     // ---- output layer: (max, sum exp) of this CTA's vocabulary slice for every row ----
     if (a.use_lse) {
       {
-        const int total = (M * Kt) >> 1;
+        const int total = (MT * Kt) >> 1, live = (M * Kt) >> 1;
         for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
           double2 v[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * SG_THREADS;
-            if (i < total) v[u] = reinterpret_cast<const double2*>(a.T)[i];
+            v[u] = make_double2(0.0, 0.0);
+            if (i < live) v[u] = reinterpret_cast<const double2*>(a.T)[i];
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -1225,8 +1232,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
           for (int u = 0; u < 8; ++u) {
             const double w0 = (double)wv[u].x, w1 = (double)wv[u].y, w2 = (double)wv[u].z, w3 = (double)wv[u].w;
 #pragma unroll
-            for (int m = 0; m < SG_MAXM; ++m) {
-              if (m < M) {
+            for (int m = 0; m < MT; ++m) {
+              {
                 const double2* ap = reinterpret_cast<const double2*>(arow + (size_t)m * Kt + k0 + 4 * u);
                 const double2 u0 = ap[0], u1 = ap[1];      // the same address in every lane: broadcast
                 double sacc = acc[m];
@@ -1817,15 +1824,22 @@ int32_t single_try_run(jlm_batch* b, bool* done) {
   const size_t r0 = (size_t)SG_MAXM * std::max<size_t>(std::max(h->Kg, h->Hp), (size_t)h->Kt + per);
   const size_t smem = (r0 + SG_MAXM) * sizeof(double) + 2 * SG_MAXM * sizeof(int);
   if (smem + 8 * 1024 > (size_t)dev_smem) return 0;      // + the prune phase's static buffers
+  const void* kern = b->W <= 4 ? reinterpret_cast<const void*>(k_single_f64<4>)
+                     : b->W <= 8 ? reinterpret_cast<const void*>(k_single_f64<8>)
+                     : b->W <= 12 ? reinterpret_cast<const void*>(k_single_f64<12>)
+                                  : reinterpret_cast<const void*>(k_single_f64<16>);
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    JLM_CUDA(cudaFuncSetAttribute(k_single_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JLM_CUDA(cudaFuncSetAttribute(k_single_f64<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JLM_CUDA(cudaFuncSetAttribute(k_single_f64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JLM_CUDA(cudaFuncSetAttribute(k_single_f64<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JLM_CUDA(cudaFuncSetAttribute(k_single_f64<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
     blocks_per_sm = -1;
   }
   if (blocks_per_sm < 0) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_single_f64, SG_THREADS, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_single_f64<16>, SG_THREADS, smem) != cudaSuccess) {
       cudaGetLastError();
       nb = 0;
     }
@@ -1859,7 +1873,7 @@ int32_t single_try_run(jlm_batch* b, bool* done) {
   for (int t = 0; t < b->n_steps; ++t) sa.item0[t] = (int)b->steps[t].item0;
   sa.item0[b->n_steps] = (int)b->d.n_items;
   void* args[] = {&sa};
-  JLM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_single_f64), dim3(G), dim3(SG_THREADS), args, smem,
+  JLM_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(SG_THREADS), args, smem,
                                        h->stream));
   b->launches += 1;
   *done = true;

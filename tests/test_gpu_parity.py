@@ -153,6 +153,47 @@ def test_model_api_matches_reference(name, tmp_path_factory):
                 m.project(h, probe['vocab'])
 
 
+@pytest.mark.parametrize('name', ['small_tied', 'small_dsoftmax', 'small_dsoftmax_star', 'small_tied_selfnorm',
+                                  'cfg2_tied', 'cfg3_dsoftmax_star'])
+def test_single_sentence_kernel_matches_fixtures(name, tmp_path_factory):
+    """One sentence on the float64 back end without per-bucket timers runs in ONE cooperative kernel
+    (k_single_f64: 2 launches instead of ~8 per frame).  Its n-best lists and per-frame beams must equal the
+    reference fixtures, and the per-frame launch path (timers on) bit-for-bit in the indices, 1e-12 in the scores."""
+    from jlm_b200 import lattice
+    dec, case, sentences = get_decoder(name, tmp_path_factory)
+    meta, arr = load_golden(name)
+    kw = dict(case['decode_kwargs'])
+    topN, beam = kw.get('topN', 10), kw.get('beam_width', 10)
+    if beam is None or beam > 16:
+        pytest.skip('the kernel takes beams up to 16')
+    hs = meta['h_stride']
+    for si, sent in enumerate(sentences):
+        g = meta['decode'][si]
+        frames = dec._build_lattice(sent)
+        packed, mode = dec._pack([frames], [None])
+        launch = dec._run(packed, mode, topN, beam, EXACT, timers=True)[0]
+        n_launch, trace_launch = dec.last_info.kernel_launches, dec._last_batch_trace[0]
+        single = dec._run(packed, mode, topN, beam, EXACT, timers=False)[0]
+        assert dec.last_info.kernel_launches == 2 < n_launch, (name, dec.last_info.kernel_launches)
+        trace = dec._last_batch_trace[0]
+        assert [ws for _, ws in single] == [ws for _, ws in g['nbest']] == [ws for _, ws in launch], (name, si)
+        np.testing.assert_allclose([s for s, _ in single], [s for s, _ in g['nbest']], rtol=0, atol=SCORE_TOL[EXACT])
+        np.testing.assert_allclose([s for s, _ in single], [s for s, _ in launch], rtol=0, atol=1e-12)
+        assert len(trace) == len(trace_launch)
+        for t, (fa, fb) in enumerate(zip(trace, trace_launch)):
+            assert np.array_equal(fa['node'], fb['node']) and np.array_equal(fa['parent_rank'], fb['parent_rank']), (name, si, t)
+            np.testing.assert_allclose(fa['score'], fb['score'], rtol=0, atol=1e-12)
+            if t < len(sent):
+                np.testing.assert_allclose(fa['h'], fb['h'], rtol=0, atol=1e-13)
+                np.testing.assert_allclose(fa['c'], fb['c'], rtol=0, atol=1e-13)
+                key = 's%d_f%d' % (si, t)
+                if key + '_h' in arr:
+                    np.testing.assert_allclose(fa['h'][:, ::hs], arr[key + '_h'], rtol=0, atol=TOL[EXACT])
+                if not case.get('self_norm'):
+                    np.testing.assert_allclose(fa['lse'], fb['lse'], rtol=1e-14, atol=1e-12)
+                    np.testing.assert_allclose(fa['lse'], arr[key + '_lse'], rtol=2e-7, atol=TOL[EXACT])
+
+
 def test_decode_batch_equals_single(tmp_path_factory):
     dec, case, sentences = get_decoder('small_tied', tmp_path_factory)
     single = [dec.decode(s, backend=EXACT, **case['decode_kwargs']) for s in sentences]

@@ -964,6 +964,69 @@ __device__ __forceinline__ void rs_halve(double* acc, int lane) {
   }
 }
 
+// Output-layer columns n .. n+NC-1 (one segment) of k_single_f64 for one thread: the words' weight rows stream through
+// registers in 64-byte batches (the next batch in flight while this one is multiplied), the stage-1 rows are broadcast
+// from shared memory - with NC = 2 every broadcast feeds eight FMAs instead of four (the phase is bound by FMA issue
+// and those loads).
+template <int MT, int NC>
+__device__ __forceinline__ void sg_columns(const SingleArgs& a, const double* As, double* ys, int n, int c_lo, int M) {
+  int sgi = 0;
+#pragma unroll
+  for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
+    if (i < a.seg.n && n >= a.seg.start[i]) sgi = i;
+  const int kpad = a.seg.kpad[sgi];
+  const float* wrow = a.seg.W[sgi] + (int64_t)(n - a.seg.start[sgi]) * kpad;
+  const double* arow = As + a.seg.koff[sgi];
+  double acc[NC][MT];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[c][m] = 0.0;
+  float4 wn[NC][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wn[c][u] = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)c * kpad + 4 * u));
+  for (int k0 = 0; k0 < kpad; k0 += 16) {
+    float4 wv[NC][4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[c][u] = wn[c][u];
+    if (k0 + 16 < kpad) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          wn[c][u] = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)c * kpad + k0 + 16 + 4 * u));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const double2* ap = reinterpret_cast<const double2*>(arow + (size_t)m * a.Kt + k0 + 4 * u);
+        const double2 u0 = ap[0], u1 = ap[1];      // the same address in every lane: broadcast
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          double sacc = acc[c][m];
+          sacc = fma(u0.x, (double)wv[c][u].x, sacc);
+          sacc = fma(u0.y, (double)wv[c][u].y, sacc);
+          sacc = fma(u1.x, (double)wv[c][u].z, sacc);
+          sacc = fma(u1.y, (double)wv[c][u].w, sacc);
+          acc[c][m] = sacc;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const double bias = (double)__ldg(a.b2 + n + c);
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+      if (m < M) ys[(size_t)m * a.per + (n + c - c_lo)] = acc[c][m] + bias;
+  }
+}
+
 // MT: rows the register tiles are written for (>= beam width).  Rows M..MT-1 of the shared-memory operands are zero and
 // are multiplied like the others: with `if (m < M)` around every row the compiler keeps each row's four dependent
 // float64 FMAs in a basic block of their own and the two warps a scheduler has cannot cover their latency.
@@ -1204,85 +1267,66 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
       }
       __syncthreads();
       const int c_lo = blockIdx.x * a.per, c_hi = min(a.V, c_lo + a.per);
-      for (int n = c_lo + tid; n < c_hi; n += SG_THREADS) {
-        int sgi = 0;
+      // A thread takes two adjacent columns at a time: every broadcast of a stage-1 value then feeds eight FMAs instead
+      // of four (measured per 20-kana sentence: one column per thread 1.36 ms, two 1.22 ms; three columns on the first
+      // four warps only - one per scheduler - 1.43 ms).  A pair cut by the end of the slice or by a segment boundary
+      // goes column by column.
+      for (int n = c_lo + 2 * tid; n < c_hi; n += 2 * SG_THREADS) {
+        bool pair = n + 1 < c_hi;
 #pragma unroll
         for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
-          if (i < a.seg.n && n >= a.seg.start[i]) sgi = i;
-        const int kpad = a.seg.kpad[sgi];
-        const float* wrow = a.seg.W[sgi] + (int64_t)(n - a.seg.start[sgi]) * kpad;
-        const double* arow = As + a.seg.koff[sgi];
-        double acc[SG_MAXM];
-#pragma unroll
-        for (int i = 0; i < SG_MAXM; ++i) acc[i] = 0.0;
-        // the word's weight row streams through registers in 128-byte batches (one cache line per thread), the next
-        // batch in flight while this one is multiplied
-        float4 wn[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) wn[u] = __ldg(reinterpret_cast<const float4*>(wrow + 4 * u));
-        for (int k0 = 0; k0 < kpad; k0 += 32) {
-          float4 wv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) wv[u] = wn[u];
-          if (k0 + 32 < kpad) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) wn[u] = __ldg(reinterpret_cast<const float4*>(wrow + k0 + 32 + 4 * u));
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const double w0 = (double)wv[u].x, w1 = (double)wv[u].y, w2 = (double)wv[u].z, w3 = (double)wv[u].w;
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              {
-                const double2* ap = reinterpret_cast<const double2*>(arow + (size_t)m * Kt + k0 + 4 * u);
-                const double2 u0 = ap[0], u1 = ap[1];      // the same address in every lane: broadcast
-                double sacc = acc[m];
-                sacc = fma(u0.x, w0, sacc);
-                sacc = fma(u0.y, w1, sacc);
-                sacc = fma(u1.x, w2, sacc);
-                sacc = fma(u1.y, w3, sacc);
-                acc[m] = sacc;
-              }
-            }
-          }
+          if (i < a.seg.n && a.seg.start[i] == n + 1) pair = false;
+        if (pair) {
+          sg_columns<MT, 2>(a, As, ys, n, c_lo, M);
+        } else {
+          sg_columns<MT, 1>(a, As, ys, n, c_lo, M);
+          if (n + 1 < c_hi) sg_columns<MT, 1>(a, As, ys, n + 1, c_lo, M);
         }
-        const double bias = (double)__ldg(a.b2 + n);
-#pragma unroll
-        for (int m = 0; m < SG_MAXM; ++m)
-          if (m < M) ys[(size_t)m * a.per + (n - c_lo)] = acc[m] + bias;
       }
       __syncthreads();
       const int nc = max(c_hi - c_lo, 0);
       {
-        // a warp takes rows warp and warp + 8 together: two independent chains of float64 exponentials per lane
-        const int m0 = warp, m1 = warp + SG_WARPS;
-        const bool r0 = m0 < M, r1 = m1 < M;
-        const double* y0 = ys + (size_t)m0 * a.per;
-        const double* y1 = ys + (size_t)(r1 ? m1 : m0) * a.per;
-        double mx0 = -INFINITY, mx1 = -INFINITY;
-        if (r0)
-          for (int i = lane; i < nc; i += 32) {
-            mx0 = fmax(mx0, y0[i]);
-            mx1 = fmax(mx1, y1[i]);
-          }
+        // (max, sum exp) of the slice per row.  Pass 1: row maxima.  Pass 2: the M x nc exponentials in 2M units of
+        // half a row, three units interleaved per warp (independent chains of the ~60-instruction float64 exp), so
+        // that all eight warps carry about the same number of them; a row's two halves are added in a fixed order.
+        __shared__ double mx_s[SG_MAXM];
+        __shared__ double us_s[2 * SG_MAXM];
+        for (int m = warp; m < M; m += SG_WARPS) {
+          const double* y = ys + (size_t)m * a.per;
+          double mx = -INFINITY;
+          for (int i = lane; i < nc; i += 32) mx = fmax(mx, y[i]);
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          mx0 = fmax(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
-          mx1 = fmax(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+          for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0) mx_s[m] = mx;
         }
-        double s0 = 0.0, s1 = 0.0;
-        if (r0)
-          for (int i = lane; i < nc; i += 32) {
-            s0 += exp(y0[i] - mx0);
-            if (r1) s1 += exp(y1[i] - mx1);
-          }
+        __syncthreads();
+        const int h0 = (nc + 1) >> 1;                 // columns [0, h0) and [h0, nc)
+        const double* yu[3];
+        double mu[3], su[3] = {0.0, 0.0, 0.0};
+        int nu[3];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        for (int q = 0; q < 3; ++q) {
+          const int u = warp + q * SG_WARPS;
+          const bool ok = u < 2 * M;
+          const int m = ok ? (u >> 1) : 0;
+          yu[q] = ys + (size_t)m * a.per + ((u & 1) ? h0 : 0);
+          nu[q] = ok ? ((u & 1) ? nc - h0 : h0) : 0;
+          mu[q] = mx_s[m];
         }
-        if (lane == 0 && r0) a.part[(size_t)blockIdx.x * SG_MAXM + m0] = make_double2(mx0, s0);
-        if (lane == 0 && r1) a.part[(size_t)blockIdx.x * SG_MAXM + m1] = make_double2(mx1, s1);
+        for (int i = lane; i < h0; i += 32) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (i < nu[q]) su[q] += exp(yu[q][i] - mu[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) su[q] += __shfl_xor_sync(0xffffffffu, su[q], o);
+          const int u = warp + q * SG_WARPS;
+          if (lane == 0 && u < 2 * M) us_s[u] = su[q];
+        }
+        __syncthreads();
+        if (tid < M) a.part[(size_t)blockIdx.x * SG_MAXM + tid] = make_double2(mx_s[tid], us_s[2 * tid] + us_s[2 * tid + 1]);
       }
       grid.sync();
     }
@@ -1291,22 +1335,41 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     const int it0 = a.item0[t], n_it = a.item0[t + 1] - it0;
     if (blockIdx.x * SG_WARPS < n_it || blockIdx.x == 0) {
       if (a.use_lse) {
-        for (int m = warp; m < M; m += SG_WARPS) {
-          double mx = -INFINITY;
-          for (int c = lane; c < (int)gridDim.x; c += 32) mx = fmax(mx, a.part[(size_t)c * SG_MAXM + m].x);
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          double sum = 0.0;
+        {
+          // rows warp and warp + 8 together (two independent chains of loads and float64 exponentials per lane)
+          const int m0 = warp, m1 = warp + SG_WARPS;
+          const bool r0 = m0 < M, r1 = m1 < M;
+          const int ma = r0 ? m0 : 0, mb = r1 ? m1 : ma;
+          double mxa = -INFINITY, mxb = -INFINITY;
           for (int c = lane; c < (int)gridDim.x; c += 32) {
-            const double2 pr = a.part[(size_t)c * SG_MAXM + m];
-            if (pr.x > -INFINITY) sum += pr.y * exp(pr.x - mx);
+            mxa = fmax(mxa, a.part[(size_t)c * SG_MAXM + ma].x);
+            mxb = fmax(mxb, a.part[(size_t)c * SG_MAXM + mb].x);
           }
 #pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) {
-            const double l = mx + log(sum);
-            lse_sm[m] = l;
-            if (blockIdx.x == 0) d.slot_lse[row0 + m] = l;
+          for (int o = 16; o >= 1; o >>= 1) {
+            mxa = fmax(mxa, __shfl_xor_sync(0xffffffffu, mxa, o));
+            mxb = fmax(mxb, __shfl_xor_sync(0xffffffffu, mxb, o));
+          }
+          double sa = 0.0, sb = 0.0;
+          for (int c = lane; c < (int)gridDim.x; c += 32) {
+            const double2 pa = a.part[(size_t)c * SG_MAXM + ma], pb = a.part[(size_t)c * SG_MAXM + mb];
+            if (pa.x > -INFINITY) sa += pa.y * exp(pa.x - mxa);
+            if (pb.x > -INFINITY) sb += pb.y * exp(pb.x - mxb);
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+          }
+          if (lane == 0 && r0) {
+            const double l = mxa + log(sa);
+            lse_sm[m0] = l;
+            if (blockIdx.x == 0) d.slot_lse[row0 + m0] = l;
+          }
+          if (lane == 0 && r1) {
+            const double l = mxb + log(sb);
+            lse_sm[m1] = l;
+            if (blockIdx.x == 0) d.slot_lse[row0 + m1] = l;
           }
         }
         __syncthreads();
@@ -1826,12 +1889,14 @@ int32_t single_try_run(jlm_batch* b, bool* done) {
   if (smem + 8 * 1024 > (size_t)dev_smem) return 0;      // + the prune phase's static buffers
   const void* kern = b->W <= 4 ? reinterpret_cast<const void*>(k_single_f64<4>)
                      : b->W <= 8 ? reinterpret_cast<const void*>(k_single_f64<8>)
+                     : b->W <= 10 ? reinterpret_cast<const void*>(k_single_f64<10>)
                      : b->W <= 12 ? reinterpret_cast<const void*>(k_single_f64<12>)
                                   : reinterpret_cast<const void*>(k_single_f64<16>);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     JLM_CUDA(cudaFuncSetAttribute(k_single_f64<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JLM_CUDA(cudaFuncSetAttribute(k_single_f64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JLM_CUDA(cudaFuncSetAttribute(k_single_f64<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JLM_CUDA(cudaFuncSetAttribute(k_single_f64<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JLM_CUDA(cudaFuncSetAttribute(k_single_f64<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;

@@ -930,7 +930,8 @@ namespace cg = cooperative_groups;
 
 constexpr int SG_THREADS = 256;      // measured with 512 (128-register cap, 4-load batches): 1.94 vs 1.48 ms per 20-kana sentence
 constexpr int SG_WARPS = SG_THREADS / 32;
-constexpr int SG_MAXM = 16;          // rows per LM step (beam width)
+constexpr int SG_MAXM = 16;          // rows per register tile
+constexpr int SG_MAXW = 64;          // rows per LM step (beam width): taken SG_MAXM (MT) at a time
 constexpr int SG_MAXSTEPS = 128;
 
 struct SingleArgs {
@@ -944,7 +945,7 @@ struct SingleArgs {
   double* hx;             // [n_slots, Hp]
   double* cx;
   double* T;              // [SG_MAXM, Kt] stage-1 rows of the step
-  double2* part;          // [gridDim.x, SG_MAXM] (max, sum exp) of the CTA's vocabulary slice
+  double2* part;          // [gridDim.x, SG_MAXW] (max, sum exp) of the CTA's vocabulary slice
   int V, H, Hp, Ep, Kg, Kt;
   int W, use_lse, n_steps, sent_T;
   int per;                // vocabulary columns per CTA
@@ -1043,9 +1044,9 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
   // followed by the logits of this CTA's columns [M][per]
   double* As = sg_sm;
   double* ys = As + (size_t)SG_MAXM * Kt;
-  double* lse_sm = sg_sm + a.r0;                    // [SG_MAXM]
-  int* s_par = reinterpret_cast<int*>(lse_sm + SG_MAXM);   // [SG_MAXM]
-  int* s_word = s_par + SG_MAXM;                            // [SG_MAXM]
+  double* lse_sm = sg_sm + a.r0;                    // [SG_MAXW]
+  int* s_par = reinterpret_cast<int*>(lse_sm + SG_MAXW);   // [SG_MAXW]
+  int* s_word = s_par + SG_MAXW;                            // [SG_MAXW]
 
   // ---- prologue: k_init_frame0 (sentence 0) and k_build_items ----
   if (blockIdx.x == 0 && tid == 0) {
@@ -1081,18 +1082,25 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     // Prune: EVERY CTA runs the (deterministic) selection with its warp 0 and writes the same slots - a grid barrier
     // and a phase in which 147 SMs wait for one warp cost more than the redundant scan of a few hundred candidates.
     if (t > 0) {
-      if (warp == 0) prune_sentence<1, false>(d, t, 0, a.W, 0, a.use_lse);
+      if (warp == 0) {
+        if (a.W <= 32) prune_sentence<1, false>(d, t, 0, a.W, 0, a.use_lse);
+        else prune_sentence<2, false>(d, t, 0, a.W, 0, a.use_lse);
+      }
       __syncthreads();
     }
     const int M = (t < a.sent_T) ? d.bc[fid] : 0;     // rows that take an LM step (plan data: the same in every CTA)
     if (M == 0) continue;
     const int64_t row0 = d.slot0[fid];
-    if (tid < SG_MAXM) {
+    if (tid < SG_MAXW) {
       s_par[tid] = tid < M ? d.slot_parent[row0 + tid] : -1;
       s_word[tid] = tid < M ? d.slot_word[row0 + tid] : 0;
     }
     __syncthreads();
-    // gathered gate input [ h[parent] | LM_in[word] ] of the step's rows -> shared memory (float64), once per CTA
+    // The step's rows go through every phase MT at a time (beams wider than the register tile: the weights are re-read
+    // from L2 per pass).
+    for (int mp = 0; mp < M; mp += MT) {
+    const int Mp = min(MT, M - mp);
+    // gathered gate input [ h[parent] | LM_in[word] ] of the pass's rows -> shared memory (float64), once per CTA
     {
       const int Kg2 = a.Kg >> 1;
       const int total = MT * Kg2;                     // double2 pieces (rows M..MT-1: zeros)
@@ -1104,12 +1112,12 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
           v[u] = make_double2(0.0, 0.0);
           if (i < total) {
             const int m = i / Kg2, k = (i - m * Kg2) * 2;
-            if (m >= M) {
+            if (m >= Mp) {
             } else if (k < Hp) {
-              const int p = s_par[m];
+              const int p = s_par[mp + m];
               if (p >= 0) v[u] = *reinterpret_cast<const double2*>(a.hx + (int64_t)p * Hp + k);
             } else {
-              const float2 e = __ldg(reinterpret_cast<const float2*>(a.LM_in + (int64_t)s_word[m] * a.Ep + (k - Hp)));
+              const float2 e = __ldg(reinterpret_cast<const float2*>(a.LM_in + (int64_t)s_word[mp + m] * a.Ep + (k - Hp)));
               v[u] = make_double2((double)e.x, (double)e.y);
             }
           }
@@ -1126,9 +1134,9 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     // ---- LSTM cell: warp per hidden unit ----
     for (int j = gwarp; j < Hp; j += NW) {
       if (j >= a.H) {      // padding units of the state rows stay zero (stage 1 multiplies them by zero weights)
-        if (lane < M) {
-          a.hx[(row0 + lane) * Hp + j] = 0.0;
-          a.cx[(row0 + lane) * Hp + j] = 0.0;
+        if (lane < Mp) {
+          a.hx[(row0 + mp + lane) * Hp + j] = 0.0;
+          a.cx[(row0 + mp + lane) * Hp + j] = 0.0;
         }
         continue;
       }
@@ -1174,32 +1182,36 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
         // lane l holds the sums with index 2l and 2l+1: row l/2, gates (i, f) on even lanes, (o, g) on odd lanes
         const double o0 = __shfl_xor_sync(0xffffffffu, acc[0], 1), o1 = __shfl_xor_sync(0xffffffffu, acc[1], 1);
         const int m = lane >> 1;
-        if ((lane & 1) == 0 && m < M) {
+        if ((lane & 1) == 0 && m < Mp) {
           const double pi = acc[0] + (double)a.bg[j], pf = acc[1] + (double)a.bg[a.H + j];
           const double po = o0 + (double)a.bg[2 * a.H + j], pg = o1 + (double)a.bg[3 * a.H + j];
           const double gi = 1.0 / (exp(-pi) + 1.0), gf = 1.0 / (exp(-pf) + 1.0), go = 1.0 / (exp(-po) + 1.0);
           const double gg = tanh(pg);
-          const int p = s_par[m];
+          const int p = s_par[mp + m];
           const double cp = p >= 0 ? a.cx[(int64_t)p * Hp + j] : 0.0;
           const double c = cp * gf + gg * gi;
-          a.cx[(row0 + m) * Hp + j] = c;
-          a.hx[(row0 + m) * Hp + j] = tanh(c) * go;
+          a.cx[(row0 + mp + m) * Hp + j] = c;
+          a.hx[(row0 + mp + m) * Hp + j] = tanh(c) * go;
         }
       }
     }
+    __syncthreads();      // the next pass overwrites the staged rows
+    }
     grid.sync();
 
-    // ---- stage 1: T[m][e] = h[m] . P1[e], warp per column; the step's h rows go to shared memory first ----
+    // ---- stage 1: T[m][e] = h[m] . P1[e], warp per column; the pass's h rows go to shared memory first ----
+    for (int mp = 0; mp < M; mp += MT) {
+    const int Mp = min(MT, M - mp);
     {
       const int Hp2 = Hp >> 1;
-      const int total = MT * Hp2, live = M * Hp2;
+      const int total = MT * Hp2, live = Mp * Hp2;
       for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
         double2 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + u * SG_THREADS;
           v[u] = make_double2(0.0, 0.0);
-          if (i < live) v[u] = reinterpret_cast<const double2*>(a.hx + row0 * Hp)[i];
+          if (i < live) v[u] = reinterpret_cast<const double2*>(a.hx + (row0 + mp) * Hp)[i];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -1242,21 +1254,25 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
       rs_halve<2, 2>(acc, lane);
       const double v = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
       const int m = lane >> 1;
-      if ((lane & 1) == 0 && m < M) a.T[(int64_t)m * Kt + e] = v;
+      if ((lane & 1) == 0 && m < Mp) a.T[(int64_t)(mp + m) * Kt + e] = v;
+    }
+    __syncthreads();
     }
     grid.sync();
 
     // ---- output layer: (max, sum exp) of this CTA's vocabulary slice for every row ----
     if (a.use_lse) {
+      for (int mp = 0; mp < M; mp += MT) {
+      const int Mp = min(MT, M - mp);
       {
-        const int total = (MT * Kt) >> 1, live = (M * Kt) >> 1;
+        const int total = (MT * Kt) >> 1, live = (Mp * Kt) >> 1;
         for (int i0 = tid; i0 < total; i0 += 4 * SG_THREADS) {
           double2 v[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * SG_THREADS;
             v[u] = make_double2(0.0, 0.0);
-            if (i < live) v[u] = reinterpret_cast<const double2*>(a.T)[i];
+            if (i < live) v[u] = reinterpret_cast<const double2*>(a.T + (size_t)mp * Kt)[i];
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -1277,21 +1293,21 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
         for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
           if (i < a.seg.n && a.seg.start[i] == n + 1) pair = false;
         if (pair) {
-          sg_columns<MT, 2>(a, As, ys, n, c_lo, M);
+          sg_columns<MT, 2>(a, As, ys, n, c_lo, Mp);
         } else {
-          sg_columns<MT, 1>(a, As, ys, n, c_lo, M);
-          if (n + 1 < c_hi) sg_columns<MT, 1>(a, As, ys, n + 1, c_lo, M);
+          sg_columns<MT, 1>(a, As, ys, n, c_lo, Mp);
+          if (n + 1 < c_hi) sg_columns<MT, 1>(a, As, ys, n + 1, c_lo, Mp);
         }
       }
       __syncthreads();
       const int nc = max(c_hi - c_lo, 0);
       {
         // (max, sum exp) of the slice per row.  Pass 1: row maxima.  Pass 2: the M x nc exponentials in 2M units of
-        // half a row, three units interleaved per warp (independent chains of the ~60-instruction float64 exp), so
+        // half a row, up to four units interleaved per warp (independent chains of the ~60-instruction float64 exp), so
         // that all eight warps carry about the same number of them; a row's two halves are added in a fixed order.
         __shared__ double mx_s[SG_MAXM];
         __shared__ double us_s[2 * SG_MAXM];
-        for (int m = warp; m < M; m += SG_WARPS) {
+        for (int m = warp; m < Mp; m += SG_WARPS) {
           const double* y = ys + (size_t)m * a.per;
           double mx = -INFINITY;
           for (int i = lane; i < nc; i += 32) mx = fmax(mx, y[i]);
@@ -1301,13 +1317,13 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
         }
         __syncthreads();
         const int h0 = (nc + 1) >> 1;                 // columns [0, h0) and [h0, nc)
-        const double* yu[3];
-        double mu[3], su[3] = {0.0, 0.0, 0.0};
-        int nu[3];
+        const double* yu[4];      // 2 x 16 units over eight warps
+        double mu[4], su[4] = {0.0, 0.0, 0.0, 0.0};
+        int nu[4];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const int u = warp + q * SG_WARPS;
-          const bool ok = u < 2 * M;
+          const bool ok = u < 2 * Mp;
           const int m = ok ? (u >> 1) : 0;
           yu[q] = ys + (size_t)m * a.per + ((u & 1) ? h0 : 0);
           nu[q] = ok ? ((u & 1) ? nc - h0 : h0) : 0;
@@ -1315,18 +1331,21 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
         }
         for (int i = lane; i < h0; i += 32) {
 #pragma unroll
-          for (int q = 0; q < 3; ++q)
+          for (int q = 0; q < 4; ++q)
             if (i < nu[q]) su[q] += exp(yu[q][i] - mu[q]);
         }
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
           for (int o = 16; o >= 1; o >>= 1) su[q] += __shfl_xor_sync(0xffffffffu, su[q], o);
           const int u = warp + q * SG_WARPS;
-          if (lane == 0 && u < 2 * M) us_s[u] = su[q];
+          if (lane == 0 && u < 2 * Mp) us_s[u] = su[q];
         }
         __syncthreads();
-        if (tid < M) a.part[(size_t)blockIdx.x * SG_MAXM + tid] = make_double2(mx_s[tid], us_s[2 * tid] + us_s[2 * tid + 1]);
+        if (tid < Mp)
+          a.part[(size_t)blockIdx.x * SG_MAXW + mp + tid] = make_double2(mx_s[tid], us_s[2 * tid] + us_s[2 * tid + 1]);
+      }
+      __syncthreads();
       }
       grid.sync();
     }
@@ -1335,15 +1354,15 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
     const int it0 = a.item0[t], n_it = a.item0[t + 1] - it0;
     if (blockIdx.x * SG_WARPS < n_it || blockIdx.x == 0) {
       if (a.use_lse) {
-        {
-          // rows warp and warp + 8 together (two independent chains of loads and float64 exponentials per lane)
-          const int m0 = warp, m1 = warp + SG_WARPS;
+        for (int mg = 0; mg < M; mg += 2 * SG_WARPS) {
+          // rows warp and warp + 8 of the group together (two independent chains of loads and float64 exponentials per lane)
+          const int m0 = mg + warp, m1 = mg + warp + SG_WARPS;
           const bool r0 = m0 < M, r1 = m1 < M;
           const int ma = r0 ? m0 : 0, mb = r1 ? m1 : ma;
           double mxa = -INFINITY, mxb = -INFINITY;
           for (int c = lane; c < (int)gridDim.x; c += 32) {
-            mxa = fmax(mxa, a.part[(size_t)c * SG_MAXM + ma].x);
-            mxb = fmax(mxb, a.part[(size_t)c * SG_MAXM + mb].x);
+            mxa = fmax(mxa, a.part[(size_t)c * SG_MAXW + ma].x);
+            mxb = fmax(mxb, a.part[(size_t)c * SG_MAXW + mb].x);
           }
 #pragma unroll
           for (int o = 16; o >= 1; o >>= 1) {
@@ -1352,7 +1371,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
           }
           double sa = 0.0, sb = 0.0;
           for (int c = lane; c < (int)gridDim.x; c += 32) {
-            const double2 pa = a.part[(size_t)c * SG_MAXM + ma], pb = a.part[(size_t)c * SG_MAXM + mb];
+            const double2 pa = a.part[(size_t)c * SG_MAXW + ma], pb = a.part[(size_t)c * SG_MAXW + mb];
             if (pa.x > -INFINITY) sa += pa.y * exp(pa.x - mxa);
             if (pb.x > -INFINITY) sb += pb.y * exp(pb.x - mxb);
           }
@@ -1763,7 +1782,7 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
     b->part_tiles = 0;
     for (int i = 0; i < h->n_seg; ++i) b->part_tiles += exact_tiles_n(h->seg[i].end - h->seg[i].start);
     b->part = (b->mode == JLM_DECODE_FULL && b->use_lse) ? a.take<double2>(mr * b->part_tiles) : nullptr;
-    b->spart = (b->S == 1 && b->mode == JLM_DECODE_FULL) ? a.take<double2>((size_t)SG_MAXM * std::max(h->sm_count, 1)) : nullptr;
+    b->spart = (b->S == 1 && b->mode == JLM_DECODE_FULL) ? a.take<double2>((size_t)SG_MAXW * std::max(h->sm_count, 1)) : nullptr;
   }
 }
 
@@ -1874,7 +1893,7 @@ int32_t single_try_run(jlm_batch* b, bool* done) {
     return e ? atoi(e) : 1;
   }();
   if (!enabled || b->backend != JLM_BACKEND_EXACT || b->S != 1 || b->mode != JLM_DECODE_FULL || b->dynamic || b->unlimited ||
-      b->W > SG_MAXM || b->timers || h->untied || !h->P1 || !b->T || !b->spart || b->n_steps > SG_MAXSTEPS)
+      b->W > SG_MAXW || b->timers || h->untied || !h->P1 || !b->T || !b->spart || b->n_steps > SG_MAXSTEPS)
     return 0;
   for (int i = 0; i < h->n_seg; ++i)
     if (h->seg[i].kpad % 32 != 0 || exact_use_q8(h, h->seg[i], b->W)) return 0;
@@ -1885,8 +1904,8 @@ int32_t single_try_run(jlm_batch* b, bool* done) {
   const int G = h->sm_count;
   const int per = ceil_div(h->V, G);
   const size_t r0 = (size_t)SG_MAXM * std::max<size_t>(std::max(h->Kg, h->Hp), (size_t)h->Kt + per);
-  const size_t smem = (r0 + SG_MAXM) * sizeof(double) + 2 * SG_MAXM * sizeof(int);
-  if (smem + 8 * 1024 > (size_t)dev_smem) return 0;      // + the prune phase's static buffers
+  const size_t smem = (r0 + SG_MAXW) * sizeof(double) + 2 * SG_MAXW * sizeof(int);
+  if (smem + 20 * 1024 > (size_t)dev_smem) return 0;     // + the prune phase's static buffers
   const void* kern = b->W <= 4 ? reinterpret_cast<const void*>(k_single_f64<4>)
                      : b->W <= 8 ? reinterpret_cast<const void*>(k_single_f64<8>)
                      : b->W <= 10 ? reinterpret_cast<const void*>(k_single_f64<10>)

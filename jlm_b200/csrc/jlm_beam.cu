@@ -51,7 +51,7 @@ __global__ void k_build_items(BeamDev d) {
   it.word = d.node_word[n];
   it.rows = d.bc[pf];
   it.node = n;
-  it.pad = 0;
+  it.pad = d.node_span ? d.node_span[n] : 0;
   it.ps0 = d.slot0[pf];
   it.cpos = d.cand_pos[n];
   d.items[i] = it;
@@ -83,7 +83,7 @@ __device__ __forceinline__ void load4(const double* p, double (&t)[4]) {
 template <typename TT, bool DYN>
 __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int64_t ldt, const BeamDev& d,
                                            const float* __restrict__ b2, int64_t item0, int item, int64_t row0, int use_lse,
-                                           int defer, const double* lse_rows) {
+                                           int defer, const double* lse_rows, int t_step = 0, int tstride = 0) {
   const int lane = threadIdx.x & 31;
   const int4* ip = reinterpret_cast<const int4*>(d.items + item0 + item);
   const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
@@ -163,8 +163,15 @@ __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int
       const int q = r0 / SC_RC;
       static_assert(SC_MAXPASS == 2, "select below is written for two prefetched passes");
       if (DYN) {
+        // _fix_neg_log (decoder_dynamic.py:150-175): the candidate is ranked at its END frame by (sum of the path's
+        // LSEs under that frame's vocabulary) - (sum of its logits).  Both sums of the parent path are final once
+        // k_dyn_prefix_lse of this step has run, so the score is formed here - the prune kernel then reads ONE
+        // coalesced array instead of three dependent random loads per candidate (cfg 4: 45 -> 2x us per frame).
         d.cand_val[cpos + r0 + r] = y;
         d.cand_parent[cpos + r0 + r] = (int32_t)ps;
+        // (fetching the two sums at the start of the kernel like the static path's `pre` was measured slower: 69 vs 61 us)
+        d.cand_score[cpos + r0 + r] =
+            (use_lse ? d.dyn_chain[ps * tstride + t_step + i0.w] : 0.0) - (d.slot_cumy[ps] + y);
       } else if (defer) {
         // the parent rows' LSE is still being computed (output GEMM on the main stream): leave -y, k_add_base
         // finishes the score with the same association, score + (LSE - y)
@@ -182,11 +189,11 @@ __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int
 template <typename TT, bool DYN>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
-              int64_t item0, int n_items, int64_t row0, int use_lse, int defer) {
+              int64_t item0, int n_items, int64_t row0, int use_lse, int defer, int t_step, int tstride) {
   pdl_enter();
   const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
   if (item >= n_items) return;
-  score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr);
+  score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride);
 }
 
 // Second half of a deferred k_score_nodes: cand_val holds -y; add the parent path's score and LSE.
@@ -288,7 +295,6 @@ __device__ __forceinline__ void prune_sentence(const BeamDev& d, int t, int warp
   // softmax over lattice_vocab[t].  dyn_chain[slot][t] already holds the sum of the path's LSEs under
   // that vocabulary (accumulated parent-to-child by k_dyn_prefix_lse), so a candidate's score is
   // (sum of LSEs) - (sum of logits) along its path, formed here from its parent slot.
-  const int32_t* cpar = DYN ? d.cand_parent + c0 : nullptr;
 
   double es[L];
   int ec[L];
@@ -298,10 +304,7 @@ __device__ __forceinline__ void prune_sentence(const BeamDev& d, int t, int warp
     ec[l] = -1;
   }
   auto value = [&](int c) -> double {
-    if (DYN) {
-      const int par = cpar[c];
-      return (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + val[c]);
-    }
+    if (DYN) return d.cand_score[c0 + c];      // formed by k_score_nodes (same expression, same operands)
     return val[c];
   };
 
@@ -472,12 +475,8 @@ k_prune_block(BeamDev d, int t, int W, int tstride, int use_lse, double guard_ep
   const int64_t c0 = d.frame_cand_lo[fid];
   const int nc = d.frame_ncand[fid];
   const double* val = d.cand_val + c0;
-  const int32_t* cpar = DYN ? d.cand_parent + c0 : nullptr;
   auto value = [&](int c) -> double {
-    if (DYN) {
-      const int par = cpar[c];
-      return (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + val[c]);
-    }
+    if (DYN) return d.cand_score[c0 + c];      // formed by k_score_nodes (same expression, same operands)
     return val[c];
   };
   // warp w owns ordinals [w*q, min(nc, (w+1)*q)), q a multiple of 32
@@ -733,8 +732,7 @@ k_keep_all(BeamDev d, int t, int tstride, int use_lse) {
     if (d.cand_pos[mid] <= cg) a = mid; else b = mid - 1;
   }
   const int par = (int)(d.slot0[d.node_pfid[a]] + (cg - d.cand_pos[a]));
-  double v = d.cand_val[cg];
-  if (DYN) v = (use_lse ? d.dyn_chain[(int64_t)par * tstride + t] : 0.0) - (d.slot_cumy[par] + v);
+  double v = DYN ? d.cand_score[cg] : d.cand_val[cg];
   const int64_t s = d.slot0[fid] + c;
   d.slot_score[s] = v;
   d.slot_parent[s] = par;
@@ -1404,6 +1402,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) k_single_f64(const SingleArgs a
 // host: plan
 // ------------------------------------------------------------------------------------------------
 struct HostPlan {
+  std::vector<int32_t> node_span;    // dynamic only
   std::vector<int32_t> node_word, node_pfid, frame_lo, frame_hi, frame_ncand, frame_minpf, bc, sent_T, start_items;
   std::vector<int64_t> cand_pos, frame_cand_lo, slot0, fbase;
   std::vector<int32_t> nstart;       // host only: nodes starting at each frame
@@ -1467,6 +1466,7 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
   b->N = N;
   P.node_word.assign(lat->node_word, lat->node_word + N);
   P.node_pfid.assign(N, -1);
+  P.node_span.assign(b->dynamic ? N : 0, 0);
   P.cand_pos.assign(N, 0);
   P.frame_lo.assign(F, 0);
   P.frame_hi.assign(F, 0);
@@ -1545,6 +1545,7 @@ int32_t build_plan(jlm_batch* b, const jlm_lattice_batch* lat, HostPlan& P) {
             return;
           }
           P.node_pfid[n] = (int32_t)(fb + st);
+          if (b->dynamic) P.node_span[n] = t - st;
           nstart[fb + st] += 1;
           P.cand_pos[n] = cand + ncand;
           ncand += P.bc[fb + st];
@@ -1728,6 +1729,7 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   BeamDev& d = b->d;
   d.node_word = place(a, P.node_word);
   d.node_pfid = place(a, P.node_pfid);
+  d.node_span = b->dynamic ? place(a, P.node_span) : nullptr;
   d.cand_pos = place(a, P.cand_pos);
   d.frame_lo = place(a, P.frame_lo);
   d.frame_hi = place(a, P.frame_hi);
@@ -1752,9 +1754,11 @@ void layout(jlm_batch* b, Arena& a, const HostPlan& P) {
   d.slot_word = a.take<int32_t>(ns);
   d.slot_cumy = d.dyn_lse = d.dyn_chain = nullptr;
   d.cand_parent = nullptr;
+  d.cand_score = nullptr;
   const size_t ncd = (size_t)std::max<int64_t>(b->n_cand, 1);
   if (b->dynamic) {
     d.cand_parent = a.take<int32_t>(ncd);
+    d.cand_score = a.take<double>(ncd);
     d.slot_cumy = a.take<double>(ns);
     d.dyn_chain = a.take<double>(ns * (size_t)(b->Tmax + 1));
     d.dyn_lse = a.take<double>(ns * (size_t)(b->Tmax + 1));
@@ -1802,9 +1806,9 @@ int32_t launch_score(jlm_batch* b, int t, const TT* T, int ldt, cudaStream_t st,
   const int grid = ceil_div(sp.n_items, SC_WARPS);
   const int ul = b->use_lse ? 1 : 0;
   if (b->dynamic)
-    JLM_CUDA(jlm_launch(k_score_nodes<TT, true>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0));
+    JLM_CUDA(jlm_launch(k_score_nodes<TT, true>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0, t, b->Tmax + 1));
   else
-    JLM_CUDA(jlm_launch(k_score_nodes<TT, false>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer));
+    JLM_CUDA(jlm_launch(k_score_nodes<TT, false>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer, t, b->Tmax + 1));
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   return 0;
@@ -2510,6 +2514,7 @@ extern "C" int32_t jlm_batch_upload(jlm_handle* h, const jlm_lattice_batch* lat,
       char* base = static_cast<char*>(b->mem.p);
       stage(host, base, b->d.node_word, P.node_word);
       stage(host, base, b->d.node_pfid, P.node_pfid);
+      if (b->dynamic) stage(host, base, b->d.node_span, P.node_span);
       stage(host, base, b->d.cand_pos, P.cand_pos);
       stage(host, base, b->d.frame_lo, P.frame_lo);
       stage(host, base, b->d.frame_hi, P.frame_hi);

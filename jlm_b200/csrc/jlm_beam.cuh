@@ -27,7 +27,7 @@ struct __align__(16) ScoreItem {
   int32_t word;     // node_word
   int32_t rows;     // kept paths of the node's start frame (bc)
   int32_t node;
-  int32_t pad;
+  int32_t pad;      // dynamic: frames the node spans (node_span), else 0
   int64_t ps0;      // first slot of the start frame
   int64_t cpos;     // first candidate slot of the node
 };
@@ -36,6 +36,7 @@ struct BeamDev {
   // ---- plan (read-only on the device) ----
   int32_t* node_word = nullptr;
   int32_t* node_pfid = nullptr;     // frame id of the node's start frame, -1 for <eos>
+  int32_t* node_span = nullptr;     // dynamic only: frames the node spans (end frame - start frame)
   int64_t* cand_pos = nullptr;      // first candidate slot of the node (candidates are END-frame major)
   int32_t* frame_lo = nullptr;      // per frame id: nodes ending here [lo, hi)
   int32_t* frame_hi = nullptr;
@@ -66,6 +67,7 @@ struct BeamDev {
   // (node order, then parent rank): candidate cand_pos[n] + r extends parent rank r with node n
   double* cand_val = nullptr;       // static: full path score ; dynamic: the transition's logit
   int32_t* cand_parent = nullptr;   // dynamic only: global slot of the candidate's parent path
+  double* cand_score = nullptr;     // dynamic only: the candidate's full score under its END frame's vocabulary
   // ---- near-tie guard (tensor-core back end): per sorted sentence, written by the prune kernel ----
   double* guard_gap = nullptr;      // smallest gap between adjacent ranks 0..W of any frame (kept vs kept, kept vs best rejected)
   int32_t* guard_flag = nullptr;    // bit 0: some gap fell below the bound (records queued); bit 1: re-decode in float64

@@ -1961,8 +1961,13 @@ int32_t single_try_run(jlm_batch* b, bool* done) {
   for (int t = 0; t < b->n_steps; ++t) sa.item0[t] = (int)b->steps[t].item0;
   sa.item0[b->n_steps] = (int)b->d.n_items;
   void* args[] = {&sa};
-  JLM_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(SG_THREADS), args, smem,
-                                       h->stream));
+  static bool coop_failed = false;      // a device / context that refuses cooperative launches: per-frame launches from then on
+  if (coop_failed) return 0;
+  if (cudaLaunchCooperativeKernel(kern, dim3(G), dim3(SG_THREADS), args, smem, h->stream) != cudaSuccess) {
+    cudaGetLastError();
+    coop_failed = true;
+    return 0;
+  }
   b->launches += 1;
   *done = true;
   return 0;

@@ -83,7 +83,9 @@ __device__ __forceinline__ void load4(const double* p, double (&t)[4]) {
 template <typename TT, bool DYN>
 __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int64_t ldt, const BeamDev& d,
                                            const float* __restrict__ b2, int64_t item0, int item, int64_t row0, int use_lse,
-                                           int defer, const double* lse_rows, int t_step = 0, int tstride = 0) {
+                                           int defer, const double* lse_rows, int t_step = 0, int tstride = 0,
+                                           const TT* tile0 = nullptr, int64_t tile_ps0 = -1, int tile_seg0 = -1,
+                                           const TT* tile1 = nullptr, int64_t tile_ps1 = -1, int tile_seg1 = -1) {
   const int lane = threadIdx.x & 31;
   const int4* ip = reinterpret_cast<const int4*>(d.items + item0 + item);
   const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
@@ -108,6 +110,14 @@ __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int
   const int kpad = seg.kpad[s];
   const float* wrow = seg.W[s] + (int64_t)(w - seg.start[s]) * kpad;
   const TT* trow = T + (ps0 - row0) * ldt + seg.koff[s];
+  // the start frame's stage-1 rows staged in shared memory by the CTA (k_score_nodes): [rows][kpad]
+  if (tile0 && ps0 == tile_ps0 && s == tile_seg0) {
+    trow = tile0;
+    ldt = kpad;
+  } else if (tile1 && ps0 == tile_ps1 && s == tile_seg1) {
+    trow = tile1;
+    ldt = kpad;
+  }
   const double bias = (double)b2[w];
   for (int r0 = 0; r0 < rows; r0 += SC_RC) {
     double acc[SC_RC];
@@ -186,14 +196,56 @@ __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int
   }
 }
 
+// The eight items of a CTA are consecutive in (sentence, node) order, so most of them extend the SAME start frame:
+// its stage-1 rows (beam x K floats, read once per node before: 66 MB per frame at cfg 2, the kernel's bandwidth)
+// are staged in shared memory once per CTA - for the first and for the last item's sentence - and the warps whose
+// item belongs to one of the two read them from there.  tile_elems = capacity of one tile in TT elements (0: off).
 template <typename TT, bool DYN>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
-              int64_t item0, int n_items, int64_t row0, int use_lse, int defer, int t_step, int tstride) {
+              int64_t item0, int n_items, int64_t row0, int use_lse, int defer, int t_step, int tstride, int tile_elems) {
   pdl_enter();
+  extern __shared__ float4 sc_dyn[];
+  __shared__ long long t_ps[2];
+  __shared__ int t_seg[2], t_rows[2];
   const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+  const TT* tiles = reinterpret_cast<const TT*>(sc_dyn);
+  if (tile_elems > 0) {
+    const int first = blockIdx.x * SC_WARPS, last = min(n_items, first + SC_WARPS) - 1;
+    if (threadIdx.x < 2) {
+      const ScoreItem it = d.items[item0 + (threadIdx.x == 0 ? first : last)];
+      int sg = 0;
+#pragma unroll
+      for (int i = 1; i < JLM_MAX_SEGMENTS; ++i)
+        if (i < seg.n && it.word >= seg.start[i]) sg = i;
+      t_ps[threadIdx.x] = it.rows * seg.kpad[sg] <= tile_elems ? (long long)it.ps0 : -1;
+      t_seg[threadIdx.x] = sg;
+      t_rows[threadIdx.x] = it.rows;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && t_ps[1] == t_ps[0] && t_seg[1] == t_seg[0]) t_ps[1] = -1;
+    __syncthreads();
+    TT* wt = reinterpret_cast<TT*>(sc_dyn);
+    constexpr int VEC = 16 / (int)sizeof(TT);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (t_ps[i] < 0) continue;
+      const int kp = seg.kpad[t_seg[i]], n = t_rows[i] * kp;
+      const TT* src = T + ((int64_t)t_ps[i] - row0) * ldt + seg.koff[t_seg[i]];
+      for (int e = threadIdx.x * VEC; e < n; e += SC_WARPS * 32 * VEC) {
+        const int r = e / kp, k = e - r * kp;
+        *reinterpret_cast<float4*>(wt + (size_t)i * tile_elems + e) = *reinterpret_cast<const float4*>(src + (int64_t)r * ldt + k);
+      }
+    }
+    __syncthreads();
+  }
   if (item >= n_items) return;
-  score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride);
+  if (tile_elems > 0)
+    score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride,
+                        t_ps[0] >= 0 ? tiles : nullptr, t_ps[0], t_seg[0],
+                        t_ps[1] >= 0 ? tiles + tile_elems : nullptr, t_ps[1], t_seg[1]);
+  else
+    score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride);
 }
 
 // Second half of a deferred k_score_nodes: cand_val holds -y; add the parent path's score and LSE.
@@ -1805,10 +1857,24 @@ int32_t launch_score(jlm_batch* b, int t, const TT* T, int ldt, cudaStream_t st,
   jlm_handle* h = b->h;
   const int grid = ceil_div(sp.n_items, SC_WARPS);
   const int ul = b->use_lse ? 1 : 0;
+  // shared-memory tiles for the stage-1 rows of two start frames per CTA (k_score_nodes): beam x widest segment each,
+  // while two of them stay within the default 48 KB (JLM_SCORE_TILES=0: off)
+  static const int tiles_on = [] {
+    const char* e = getenv("JLM_SCORE_TILES");
+    return e ? atoi(e) : 1;
+  }();
+  int kmax = 0;
+  for (int i = 0; i < h->n_seg; ++i) kmax = std::max(kmax, h->seg[i].kpad);
+  int tile_elems = b->W * kmax;
+  // measured: beam 20 (cfg 4) 61 -> 40 us per frame with the tiles, beam 10 (cfg 2) 24 -> 32 us (staging + two barriers cost
+  // more than ten re-read rows save): wide beams only
+  if (!tiles_on || b->W <= 12 || h->untied || (size_t)2 * tile_elems * sizeof(TT) > 48 * 1024 || (ldt * sizeof(TT)) % 16 != 0)
+    tile_elems = 0;
+  const size_t tile_bytes = (size_t)2 * tile_elems * sizeof(TT);
   if (b->dynamic)
-    JLM_CUDA(jlm_launch(k_score_nodes<TT, true>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0, t, b->Tmax + 1));
+    JLM_CUDA(jlm_launch(k_score_nodes<TT, true>, dim3(grid), dim3(SC_WARPS * 32), tile_bytes, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0, t, b->Tmax + 1, tile_elems));
   else
-    JLM_CUDA(jlm_launch(k_score_nodes<TT, false>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer, t, b->Tmax + 1));
+    JLM_CUDA(jlm_launch(k_score_nodes<TT, false>, dim3(grid), dim3(SC_WARPS * 32), tile_bytes, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer, t, b->Tmax + 1, tile_elems));
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   return 0;

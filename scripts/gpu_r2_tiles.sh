@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 )
+P='import json,sys
+d=[json.loads(l) for l in sys.stdin if l.startswith("{")][-1]
+def show(n, x): print(n, "value %.3fM e2e %.3fM (blk %.3fM) ms %.2f off %.2f" % (x["value"]/1e6, x["e2e"]["value"]/1e6, x["e2e"]["blocking_value"]/1e6, x["ms_per_step"], x["guard"]["ms_per_step_guard_off"]), "roof", round(x["roofline"].get("frac"),4), x["roofline"].get("avg_launch_ms"), "par", x["cpu_baseline"]["nbest_identical_to_gpu"])
+show(d["config"]["workload"][:4], d)
+for w in d["workloads"]: show(w["workload"], w)
+print(d["clocks"])'
+for rep in 1 2; do for v in 1 0; do
+  JLM_SCORE_TILES=$v timeout 600 python bench.py --steps 10 --cpu-baseline-sentences 4 --extra cfg4 --extra-steps 6 > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err; echo "== JLM_SCORE_TILES=$v rc=$?"; python -c "$P" < gpurun_out/bench_ab.json; tail -2 gpurun_out/bench_ab.err
+done; done
+for w in cfg2 cfg4; do
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$w.csv python bench.py --profile --steps 1 --sentences 1024 --workload $w > gpurun_out/prof_launch_$w.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches_$w.csv > gpurun_out/launch_summary_$w.txt; grep -E "score|prune" gpurun_out/launch_summary_$w.txt
+done

@@ -852,6 +852,9 @@ k_job_rows_lse(const SubsetJob* __restrict__ jobs, const double* __restrict__ yv
 // reference keeps in lattice_vocab[0].
 constexpr int DYN_CAP = 1024;   // columns of a sentence's cumulative word list the scan path buffers per warp
 
+// CAP: the scan buffer of a warp in columns (512 when every list of the step fits: 16 KB per CTA instead of 32 KB,
+// twice the resident warps of a kernel that is latency-bound)
+template <int CAP>
 __global__ void __launch_bounds__(128)
 k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restrict__ info,
                  const int32_t* __restrict__ vfp, const double* __restrict__ yv, double* __restrict__ dyn_lse,
@@ -871,9 +874,9 @@ k_dyn_prefix_lse(const SubsetJob* __restrict__ jobs, const DynJobInfo* __restric
   // of lattice_vocab[i] (all terms positive, so a prefix of the sum is as accurate as a sum of its own),
   // and lane i takes the log for frame i.  The per-frame two-pass loop below costs two warp reductions and
   // four float64 transcendentals per future frame and remains for word lists longer than the buffer.
-  __shared__ double csum_all[4][DYN_CAP];
+  __shared__ double csum_all[4][CAP];
   const int n_all = vfp[inf.vfp_off + inf.T + 1];
-  if (n_all <= DYN_CAP && n_all > 0) {
+  if (n_all <= CAP && n_all > 0) {
     double* csum = csum_all[threadIdx.x >> 5];
     __shared__ double offs_all[4][32];
     double* offs = offs_all[threadIdx.x >> 5];
@@ -1899,7 +1902,10 @@ int32_t lm_step_tail(jlm_batch* b, int t, const TT* T, int ldt) {
     dim3 grid(ceil_div(b->W, 4), sp.nstep);
     const int ns = (on_tc == 0) ? b->n_shared : 0;      // the shared block exists only when the tensor-core kernel ran
     if (b->dynamic)
-      JLM_CUDA(jlm_launch(k_dyn_prefix_lse, dim3(grid), dim3(128), 0, st, d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse, d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1, b->y0, b->ldy0, ns, on_tc == 0 ? 1 : 0));
+      if (sp.max_vocab_cols <= DYN_CAP / 2)
+        JLM_CUDA(jlm_launch(k_dyn_prefix_lse<DYN_CAP / 2>, dim3(grid), dim3(128), 0, st, d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse, d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1, b->y0, b->ldy0, ns, on_tc == 0 ? 1 : 0));
+      else
+        JLM_CUDA(jlm_launch(k_dyn_prefix_lse<DYN_CAP>, dim3(grid), dim3(128), 0, st, d.vocab_jobs + sp.job0, d.dyn_info + sp.job0, d.vfp, b->yv, d.dyn_lse, d.dyn_chain, d.slot_parent, sp.row0, t, b->Tmax + 1, b->y0, b->ldy0, ns, on_tc == 0 ? 1 : 0));
     else
       JLM_CUDA(jlm_launch(k_job_rows_lse, dim3(grid), dim3(128), 0, st, d.vocab_jobs + sp.job0, b->yv, d.slot_lse + sp.row0, b->y0, b->ldy0, ns));
     JLM_CUDA(cudaGetLastError());

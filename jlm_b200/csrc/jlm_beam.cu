@@ -200,17 +200,24 @@ __device__ __forceinline__ void score_item(const SegTable& seg, const TT* T, int
 // its stage-1 rows (beam x K floats, read once per node before: 66 MB per frame at cfg 2, the kernel's bandwidth)
 // are staged in shared memory once per CTA - for the first and for the last item's sentence - and the warps whose
 // item belongs to one of the two read them from there.  tile_elems = capacity of one tile in TT elements (0: off).
-template <typename TT, bool DYN>
+// TILES = false is the plain warp-per-item kernel (a separate instantiation: with the staging code in the same kernel the
+// untiled path ran 24 -> 33 us per frame at cfg 2).
+template <typename TT, bool DYN, bool TILES>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, const float* __restrict__ b2,
               int64_t item0, int n_items, int64_t row0, int use_lse, int defer, int t_step, int tstride, int tile_elems) {
   pdl_enter();
+  const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
+  if constexpr (!TILES) {
+    if (item >= n_items) return;
+    score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride);
+    return;
+  } else {
   extern __shared__ float4 sc_dyn[];
   __shared__ long long t_ps[2];
   __shared__ int t_seg[2], t_rows[2];
-  const int item = blockIdx.x * SC_WARPS + (threadIdx.x >> 5);
   const TT* tiles = reinterpret_cast<const TT*>(sc_dyn);
-  if (tile_elems > 0) {
+  {
     const int first = blockIdx.x * SC_WARPS, last = min(n_items, first + SC_WARPS) - 1;
     if (threadIdx.x < 2) {
       const ScoreItem it = d.items[item0 + (threadIdx.x == 0 ? first : last)];
@@ -240,12 +247,10 @@ k_score_nodes(SegTable seg, const TT* __restrict__ T, int64_t ldt, BeamDev d, co
     __syncthreads();
   }
   if (item >= n_items) return;
-  if (tile_elems > 0)
-    score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride,
-                        t_ps[0] >= 0 ? tiles : nullptr, t_ps[0], t_seg[0],
-                        t_ps[1] >= 0 ? tiles + tile_elems : nullptr, t_ps[1], t_seg[1]);
-  else
-    score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride);
+  score_item<TT, DYN>(seg, T, ldt, d, b2, item0, item, row0, use_lse, defer, nullptr, t_step, tstride,
+                      t_ps[0] >= 0 ? tiles : nullptr, t_ps[0], t_seg[0],
+                      t_ps[1] >= 0 ? tiles + tile_elems : nullptr, t_ps[1], t_seg[1]);
+  }
 }
 
 // Second half of a deferred k_score_nodes: cand_val holds -y; add the parent path's score and LSE.
@@ -1875,9 +1880,15 @@ int32_t launch_score(jlm_batch* b, int t, const TT* T, int ldt, cudaStream_t st,
     tile_elems = 0;
   const size_t tile_bytes = (size_t)2 * tile_elems * sizeof(TT);
   if (b->dynamic)
-    JLM_CUDA(jlm_launch(k_score_nodes<TT, true>, dim3(grid), dim3(SC_WARPS * 32), tile_bytes, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0, t, b->Tmax + 1, tile_elems));
+    if (tile_elems > 0)
+      JLM_CUDA(jlm_launch(k_score_nodes<TT, true, true>, dim3(grid), dim3(SC_WARPS * 32), tile_bytes, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0, t, b->Tmax + 1, tile_elems));
+    else
+      JLM_CUDA(jlm_launch(k_score_nodes<TT, true, false>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, 0, t, b->Tmax + 1, 0));
   else
-    JLM_CUDA(jlm_launch(k_score_nodes<TT, false>, dim3(grid), dim3(SC_WARPS * 32), tile_bytes, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer, t, b->Tmax + 1, tile_elems));
+    if (tile_elems > 0)
+      JLM_CUDA(jlm_launch(k_score_nodes<TT, false, true>, dim3(grid), dim3(SC_WARPS * 32), tile_bytes, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer, t, b->Tmax + 1, tile_elems));
+    else
+      JLM_CUDA(jlm_launch(k_score_nodes<TT, false, false>, dim3(grid), dim3(SC_WARPS * 32), 0, st, make_seg_table(h), T, ldt, b->d, h->b2, sp.item0, sp.n_items, sp.row0, ul, defer, t, b->Tmax + 1, 0));
   JLM_CUDA(cudaGetLastError());
   b->launches += 1;
   return 0;

@@ -537,7 +537,13 @@ def bench_workload(env, name, steps, warmup, cpu_sentences, headline):
     roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': sus, 'peak_source': src + ' bf16 sustained', 'traffic': traffic}
     if proj_ms > 0 and args.backend == 2:
         ach = f_proj_row * rows_total / (proj_ms * 1e-3) / 1e12
-        roof.update({'kernel': 'k_tc_gemm<256,EPI_LSE,cta_group::2> (output projection + online LSE)', 'achieved': ach,
+        if wl['mode'] == 'dsoftmax_star':
+            # one launch per segment and frame: K <= 128 -> row-stationary k_tc_lse_rs<1|2>, K = 256 -> k_tc_gemm<256,EPI_LSE>
+            kname = ('k_tc_lse_rs<K/64> (row-stationary, K <= 128) + k_tc_gemm<256,EPI_LSE,cta_group::2> (K = 256): output '
+                     'projection segments + online LSE, all launches of a frame')
+        else:
+            kname = 'k_tc_gemm<256,EPI_LSE,cta_group::2> (output projection + online LSE)'
+        roof.update({'kernel': kname, 'achieved': ach,
                      'frac': ach / sus, 'issued_frac': 3 * ach / sus,
                      'flops_per_launch': f_proj_row * rows_total / max(n_proj, 1),
                      'avg_launch_ms': proj_ms / max(n_proj, 1), 'launches': n_proj,

@@ -1876,7 +1876,9 @@ int32_t launch_score(jlm_batch* b, int t, const TT* T, int ldt, cudaStream_t st,
   int tile_elems = b->W * kmax;
   // measured: beam 20 (cfg 4) 61 -> 40 us per frame with the tiles, beam 10 (cfg 2) 24 -> 32 us (staging + two barriers cost
   // more than ten re-read rows save): wide beams only
-  if (!tiles_on || b->W <= 12 || h->untied || (size_t)2 * tile_elems * sizeof(TT) > 48 * 1024 || (ldt * sizeof(TT)) % 16 != 0)
+  // (tensor-core back end only - float32 stage-1 rows: the float64 instantiation exists but no measured or tested shape uses it)
+  if (!tiles_on || sizeof(TT) != 4 || b->W <= 12 || h->untied || (size_t)2 * tile_elems * sizeof(TT) > 48 * 1024 ||
+      (ldt * sizeof(TT)) % 16 != 0)
     tile_elems = 0;
   const size_t tile_bytes = (size_t)2 * tile_elems * sizeof(TT);
   if (b->dynamic)

@@ -38,6 +38,10 @@ class Decoder(object):
         self.perf_sen = 0
         self.perf_log_lstm = []
         self.perf_log_softmax = []
+        # perf_log_lstm / perf_log_softmax (decoder.py:211-212) need CUDA events between the kernels of every frame, and
+        # with those a sentence decoded alone goes through ~8 launches per frame instead of the one cooperative kernel
+        # (k_single_f64): set perf_timers = False where the two perf logs are not read (interactive, one sentence at a time)
+        self.perf_timers = True
         self._builder = lattice.LatticeBuilder(self.w2i, self.full_lexicon, self.full_reading_dict)
         self._native_lexicon = None
         self._lib = _lib.load()
@@ -151,7 +155,7 @@ class Decoder(object):
         _lib.check(lib.jlm_decode_texts_submit(h, nlex.handle, S, _lib.ptr(tptr, C.c_int64), _lib.ptr(cps, C.c_uint32),
                                                int(beam_width), top, int(mode), n_extra,
                                                _lib.ptr(extra, C.c_int32) if n_extra else None, int(backend),
-                                               int(n_chunks), 1, C.byref(job)))
+                                               int(n_chunks), 1 if self.perf_timers else 0, C.byref(job)))
         return {'job': job, 'texts': texts, 'top': top, 'topN': topN, 'max_len': int(lens.max()) + 1}
 
     def _collect_texts_arrays(self, pending):
@@ -296,11 +300,12 @@ class Decoder(object):
         # a vocabulary selected by an earlier call keeps being used (decoder.py:66,179; quirk 6)
         lv = self.lattice_vocab if self.lattice_vocab else None
         packed, mode = self._pack([frames], [lv])
-        out = self._run(packed, mode, topN, beam_width, backend, timers=True)[0]
+        out = self._run(packed, mode, topN, beam_width, backend, timers=self.perf_timers)[0]
         info = self.last_info
         steps = max(int(info.n_steps), 1)
-        self.perf_log_lstm += [info.ms_lstm * 1e-3 / steps] * steps          # decoder.py:211-212
-        self.perf_log_softmax += [info.ms_softmax * 1e-3 / steps] * steps
+        if self.perf_timers:
+            self.perf_log_lstm += [info.ms_lstm * 1e-3 / steps] * steps          # decoder.py:211-212
+            self.perf_log_softmax += [info.ms_softmax * 1e-3 / steps] * steps
         self.perf_sen += 1
         return out
 
@@ -355,7 +360,8 @@ class Decoder(object):
         CUDA-event time of that step for the whole batch."""
         info = self.last_info
         steps = max(int(info.n_steps) - (0 if last_frame_stepped else 1), 1)
-        self.perf_log_lstm += [info.ms_lstm * 1e-3 / steps] * steps
-        self.perf_log_softmax += [info.ms_softmax * 1e-3 / steps] * steps
+        if self.perf_timers:
+            self.perf_log_lstm += [info.ms_lstm * 1e-3 / steps] * steps
+            self.perf_log_softmax += [info.ms_softmax * 1e-3 / steps] * steps
         self.perf_sen += n_sent
         return steps

@@ -177,6 +177,20 @@ def test_single_sentence_kernel_matches_fixtures(name, tmp_path_factory):
         single = dec._run(packed, mode, topN, beam, EXACT, timers=False)[0]
         assert dec.last_info.kernel_launches == 2 < n_launch, (name, dec.last_info.kernel_launches)
         trace = dec._last_batch_trace[0]
+        if si == 0:      # the reference-shaped entry points reach the kernel with the perf logs switched off
+            n_log = len(dec.perf_log_lstm)
+            dec.perf_timers = False
+            try:
+                again = dec.decode(sent, backend=EXACT, **kw)
+                assert dec.last_info.kernel_launches == 2 and len(dec.perf_log_lstm) == n_log
+                assert again == single
+                if not case.get('dynamic'):
+                    dec._want_trace = False
+                    assert dec.decode_batch([sent], backend=EXACT, **kw)[0] == single
+                    assert dec.last_info.kernel_launches == 2
+            finally:
+                dec.perf_timers = True
+                dec._want_trace = True
         assert [ws for _, ws in single] == [ws for _, ws in g['nbest']] == [ws for _, ws in launch], (name, si)
         np.testing.assert_allclose([s for s, _ in single], [s for s, _ in g['nbest']], rtol=0, atol=SCORE_TOL[EXACT])
         np.testing.assert_allclose([s for s, _ in single], [s for s, _ in launch], rtol=0, atol=1e-12)

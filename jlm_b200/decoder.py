@@ -339,7 +339,7 @@ class Decoder(object):
                 self._log_batch_perf(len(inputs))
                 return out
             packed = lattice.NativeLattices(self._native(), inputs, mode, extra)
-            out = self._run(packed, mode, topN, beam_width, backend, timers=True)
+            out = self._run(packed, mode, topN, beam_width, backend, timers=self.perf_timers)
             if vocab_select:
                 self.lattice_vocab = packed.vocab_list(len(inputs) - 1)
             self._log_batch_perf(len(inputs))
@@ -351,7 +351,7 @@ class Decoder(object):
             all_frames.append(frames)
             vocabs.append(list(self.lattice_vocab) if self.lattice_vocab else None)
         packed, mode = self._pack(all_frames, vocabs)
-        out = self._run(packed, mode, topN, beam_width, backend, timers=True)
+        out = self._run(packed, mode, topN, beam_width, backend, timers=self.perf_timers)
         self._log_batch_perf(len(inputs))
         return out
 

@@ -207,7 +207,10 @@ typedef struct {
 
 /* Decoder.decode / DynamicDecoder.decode (decoder.py:220-241, decoder_dynamic.py:177-194) for a
  * batch of independent sentences decoded in lock-step: plan + host->device copy + all frames +
- * device->host copy of the n-best lists.  1 <= beam_width <= JLM_MAX_BEAM, or JLM_BEAM_UNLIMITED. */
+ * device->host copy of the n-best lists.  1 <= beam_width <= JLM_MAX_BEAM, or JLM_BEAM_UNLIMITED.
+ * A batch of ONE sentence on the float64 back end (JLM_BACKEND_EXACT, or AUTO below 512 rows per frame) with
+ * beam_width <= 64, full softmax and a tied / segmented projection runs its whole frame loop in one cooperative
+ * kernel (2 launches per call instead of ~8 per frame) unless timers are enabled on the batch. */
 int32_t jlm_decode_batch(jlm_handle* h, const jlm_lattice_batch* lat, int32_t beam_width, int32_t top_n,
                          int32_t mode, int32_t backend, jlm_nbest* out);
 
@@ -302,6 +305,8 @@ typedef struct jlm_batch_info_s {
                              tensor-core ranking, mass ties, or a vocabulary-selection mode) */
 } jlm_batch_info;
 int32_t jlm_batch_get_info(jlm_batch* b, jlm_batch_info* info);
+/* CUDA events between the kernels of every frame (ms_lstm / ms_softmax / ms_beam buckets).  A one-sentence batch then
+ * takes the per-frame launch path instead of the cooperative single-sentence kernel. */
 int32_t jlm_batch_enable_timers(jlm_batch* b, int32_t on);
 
 /* Per-frame beams of one sentence after jlm_batch_run (+ synchronize): for frame t the entries
